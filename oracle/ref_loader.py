@@ -1,0 +1,103 @@
+"""Import the *real* reference modules from /root/reference (build container only).
+
+TEST INFRASTRUCTURE.  Used by ``tests/golden/make_golden.py`` (to generate the committed
+fixtures) and by ``tests/test_oracle_vs_reference.py`` (skipped when /root/reference is
+absent, i.e. on the GPU box).  The reference needs timm / clip / mmcv / mmaction, none of
+which is installed; they are only used for ``DropPath``, ``trunc_normal_``, the registry
+decorator and a logger, so ~30 lines of stand-ins are inserted into ``sys.modules``
+(recipe of SURVEY.md §8c / Appendix C).  No reference source is copied into this repo.
+"""
+from __future__ import annotations
+
+import importlib.util
+import logging
+import os
+import sys
+import types
+
+import torch.nn as nn
+
+REF_ROOT = "/root/reference/mmaction/models/backbones/"
+
+
+def available() -> bool:
+    return os.path.isfile(REF_ROOT + "vitclip_aim.py")
+
+
+class _DropPath(nn.Module):
+    """timm 0.5.4 DropPath semantics (external dependency of the reference)."""
+
+    def __init__(self, drop_prob=0.0):
+        super().__init__()
+        self.drop_prob = drop_prob
+
+    def forward(self, x):
+        if self.drop_prob == 0.0 or not self.training:
+            return x
+        keep = 1 - self.drop_prob
+        m = x.new_empty((x.shape[0],) + (1,) * (x.ndim - 1)).bernoulli_(keep)
+        if keep > 0:
+            m.div_(keep)
+        return x * m
+
+
+class _Registry:
+    def __init__(self):
+        self.d = {}
+
+    def register_module(self, *a, **k):
+        return lambda c: self.d.setdefault(c.__name__, c)
+
+    def build(self, cfg):
+        cfg = dict(cfg)
+        return self.d[cfg.pop("type")](**cfg)
+
+
+_loaded = {}
+
+
+def _install_stubs():
+    if "mmaction.models.builder" in sys.modules and hasattr(sys.modules["mmaction.models.builder"], "_aimb200_stub"):
+        return
+    tl = types.ModuleType("timm.models.layers")
+    tl.DropPath = _DropPath
+    tl.to_2tuple = lambda v: (v, v)
+    tl.trunc_normal_ = nn.init.trunc_normal_
+    mb = types.ModuleType("mmaction.models.builder")
+    mb.BACKBONES = _Registry()
+    mb._aimb200_stub = True
+    mu = types.ModuleType("mmaction.utils")
+    mu.get_root_logger = lambda *a, **k: logging.getLogger("mmaction")
+    for n in ("timm", "timm.models", "clip", "mmaction", "mmaction.models", "mmaction.models.backbones"):
+        m = types.ModuleType(n)
+        m.__path__ = []
+        sys.modules[n] = m
+    sys.modules.update({"timm.models.layers": tl, "mmaction.models.builder": mb, "mmaction.utils": mu})
+
+
+def load(fname: str):
+    if fname in _loaded:
+        return _loaded[fname]
+    _install_stubs()
+    name = "mmaction.models.backbones." + fname[:-3]
+    spec = importlib.util.spec_from_file_location(name, REF_ROOT + fname)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    _loaded[fname] = mod
+    return mod
+
+
+def reference_module(cfg, state_dict, drop_path_rate=0.0):
+    """Build the reference class for ``cfg.block`` ('aim' -> vitclip_aim.AIM(wind_attn=False),
+    'fork' -> vit_clip.ViT_CLIP(shift=False)) and load ``state_dict`` into it."""
+    kw = dict(input_resolution=cfg.input_resolution, num_frames=cfg.num_frames, patch_size=cfg.patch_size,
+              width=cfg.width, layers=cfg.layers, heads=cfg.heads, drop_path_rate=drop_path_rate,
+              adapter_scale=cfg.adapter_scale)
+    if cfg.block == "aim":
+        m = load("vitclip_aim.py").AIM(num_tadapter=cfg.num_tadapter, **kw)
+    else:
+        m = load("vit_clip.py").ViT_CLIP(**kw)
+    m.init_weights()
+    missing = m.load_state_dict(state_dict, strict=True)
+    return m
