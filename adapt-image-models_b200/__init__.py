@@ -1,0 +1,8 @@
+"""aimb200 — B200-native (sm_100a) implementation of the AIM ``ViT_CLIP`` backbone hot path.
+
+The directory is named ``adapt-image-models_b200`` (not importable as such); import it as ``aimb200``
+(the sibling ``aimb200/`` shim points its ``__path__`` here).
+"""
+from . import lib  # noqa: F401
+
+__all__ = ["lib"]

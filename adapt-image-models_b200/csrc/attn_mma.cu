@@ -1,0 +1,395 @@
+// Fused flash-style spatial attention for bf16 (vit_clip.py:140-156): one CTA per (frame, head),
+// the whole K/V (n = 197 or 257 tokens, head_dim 64) resident in shared memory, scores never leave
+// registers.  Tensor-core path: mma.sync m16n8k16 bf16 with fp32 accumulation and fp32 softmax
+// statistics.  Q/K/V are read in place from the fused QKV buffer [M, 3D]; O is written head-major
+// into [M, D] (== permute(2,0,1,3).flatten(2) of the reference) so out_proj consumes it directly.
+//
+// Backward runs in the same residency: phase 1 (warp = 16 query rows) recomputes P and produces dQ,
+// phase 2 (warp = 16 key rows) recomputes P^T and produces dK, dV — no atomics, no score matrix in HBM.
+#include "common.cuh"
+
+namespace aimb {
+
+constexpr int HD = 64;
+constexpr int LDS = 72;  // smem row stride in bf16 (144 B): conflict-free ldmatrix
+constexpr float SCALE_LOG2 = 0.125f * 1.4426950408889634f;
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const bf16* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(s_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const bf16* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(s_u32(p)));
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_u32(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// A fragment (16 rows x 16 k) of a row-major [row][k] smem tile; p -> element (row0, k0)
+__device__ __forceinline__ void lda_frag(uint32_t (&a)[4], const bf16* p, int lane) {
+    ldsm_x4(a, p + (lane & 15) * LDS + (lane >> 4) * 8);
+}
+// B fragments for TWO k-steps (k0..k0+31) of an [n][k] smem tile (8 n rows): r0,r1 = k-step 0; r2,r3 = k-step 1
+__device__ __forceinline__ void ldb_frag_nk(uint32_t (&r)[4], const bf16* p, int lane) {
+    ldsm_x4(r, p + (lane & 7) * LDS + (lane >> 3) * 8);
+}
+// B fragments for TWO n-tiles (n0..n0+15) of a [k][n] smem tile (16 k rows): r0,r1 = n-tile 0; r2,r3 = n-tile 1
+__device__ __forceinline__ void ldb_frag_kn(uint32_t (&r)[4], const bf16* p, int lane) {
+    ldsm_x4_t(r, p + ((lane & 7) + ((lane >> 3) & 1) * 8) * LDS + (lane >> 4) * 8);
+}
+
+// Load `n` rows x 64 bf16 (row stride `ld` elements in global) into smem [npad][LDS], zero the pad rows.
+__device__ __forceinline__ void load_tile_async(bf16* dst, const bf16* src, int64_t ld, int n, int npad, int tid, int nthr) {
+    for (int e = tid; e < npad * 8; e += nthr) {
+        int r = e >> 3, c = (e & 7) * 8;
+        if (r < n) cp_async16(dst + r * LDS + c, src + (int64_t)r * ld + c);
+        else *reinterpret_cast<uint4*>(dst + r * LDS + c) = make_uint4(0, 0, 0, 0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ forward
+__global__ void __launch_bounds__(576) attn_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o,
+                                                           float* __restrict__ lse, int n, int heads) {
+    extern __shared__ __align__(16) uint8_t smraw[];
+    const int D = heads * HD, ld = 3 * D;
+    const int f = blockIdx.x / heads, h = blockIdx.x % heads;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int npad = (n + 31) & ~31;
+    bf16* sQ = reinterpret_cast<bf16*>(smraw);
+    bf16* sK = sQ + npad * LDS;
+    bf16* sV = sK + npad * LDS;
+    const bf16* base = qkv + (int64_t)f * n * ld + h * HD;
+    load_tile_async(sQ, base, ld, n, npad, tid, blockDim.x);
+    load_tile_async(sK, base + D, ld, n, npad, tid, blockDim.x);
+    load_tile_async(sV, base + 2 * D, ld, n, npad, tid, blockDim.x);
+    cp_async_wait_all();
+    __syncthreads();
+
+    const int q0 = warp * 16;
+    if (q0 >= n) return;
+    const int g = lane >> 2, t = lane & 3;
+    uint32_t qa[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) lda_frag(qa[ks], sQ + q0 * LDS + ks * 16, lane);
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    float oacc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) oacc[i][j] = 0.f;
+
+    for (int kc = 0; kc < npad; kc += 32) {
+        float s[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s[nt][j] = 0.f;
+#pragma unroll
+            for (int kp = 0; kp < 2; ++kp) {
+                uint32_t kb[4];
+                ldb_frag_nk(kb, sK + (kc + nt * 8) * LDS + kp * 32, lane);
+                mma16816(s[nt], qa[2 * kp], kb[0], kb[1]);
+                mma16816(s[nt], qa[2 * kp + 1], kb[2], kb[3]);
+            }
+        }
+        float cm0 = -INFINITY, cm1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            int key = kc + nt * 8 + 2 * t;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float v = s[nt][j] * SCALE_LOG2;
+                if (key + (j & 1) >= n) v = -INFINITY;
+                s[nt][j] = v;
+            }
+            cm0 = fmaxf(cm0, fmaxf(s[nt][0], s[nt][1]));
+            cm1 = fmaxf(cm1, fmaxf(s[nt][2], s[nt][3]));
+        }
+        cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 1));
+        cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 2));
+        cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 1));
+        cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
+        // every 32-key chunk that is processed holds at least one valid key (npad - n < 32), so the max is finite
+        const float mn0 = fmaxf(m0, cm0), mn1 = fmaxf(m1, cm1);
+        const float c0 = exp2f(m0 - mn0), c1 = exp2f(m1 - mn1);
+        m0 = mn0; m1 = mn1;
+        l0 *= c0; l1 *= c1;
+#pragma unroll
+        for (int dt = 0; dt < 8; ++dt) { oacc[dt][0] *= c0; oacc[dt][1] *= c0; oacc[dt][2] *= c1; oacc[dt][3] *= c1; }
+        uint32_t pa[2][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            float p0 = exp2f(s[nt][0] - m0), p1 = exp2f(s[nt][1] - m0);
+            float p2 = exp2f(s[nt][2] - m1), p3 = exp2f(s[nt][3] - m1);
+            l0 += p0 + p1; l1 += p2 + p3;
+            pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(p0, p1);
+            pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p2, p3);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll
+            for (int dp = 0; dp < 4; ++dp) {
+                uint32_t vb[4];
+                ldb_frag_kn(vb, sV + (kc + kk * 16) * LDS + dp * 16, lane);
+                mma16816(oacc[2 * dp], pa[kk], vb[0], vb[1]);
+                mma16816(oacc[2 * dp + 1], pa[kk], vb[2], vb[3]);
+            }
+        }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    const int r0 = q0 + g, r1 = q0 + g + 8;
+    bf16* ob = o + (int64_t)f * n * D + h * HD;
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) {
+        int c = dt * 8 + 2 * t;
+        if (r0 < n) *reinterpret_cast<uint32_t*>(ob + (int64_t)r0 * D + c) = pack_bf16(oacc[dt][0] * i0, oacc[dt][1] * i0);
+        if (r1 < n) *reinterpret_cast<uint32_t*>(ob + (int64_t)r1 * D + c) = pack_bf16(oacc[dt][2] * i1, oacc[dt][3] * i1);
+    }
+    if (lse && t == 0) {
+        float* lr = lse + ((int64_t)f * heads + h) * n;
+        if (r0 < n) lr[r0] = m0 * LN2 + __logf(l0);
+        if (r1 < n) lr[r1] = m1 * LN2 + __logf(l1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ backward
+__global__ void __launch_bounds__(576) attn_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o,
+                                                           const bf16* __restrict__ d_o, const float* __restrict__ lse,
+                                                           bf16* __restrict__ d_qkv, int n, int heads) {
+    extern __shared__ __align__(16) uint8_t smraw[];
+    const int D = heads * HD, ld = 3 * D;
+    const int f = blockIdx.x / heads, h = blockIdx.x % heads;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int npad = (n + 31) & ~31;
+    bf16* sQ = reinterpret_cast<bf16*>(smraw);
+    bf16* sK = sQ + npad * LDS;
+    bf16* sV = sK + npad * LDS;
+    bf16* sG = sV + npad * LDS;                                   // dO
+    float* sL = reinterpret_cast<float*>(sG + npad * LDS);        // lse * log2(e)
+    float* sDl = sL + npad;                                       // delta
+    const bf16* base = qkv + (int64_t)f * n * ld + h * HD;
+    const bf16* gb = d_o + (int64_t)f * n * D + h * HD;
+    const bf16* ob = o + (int64_t)f * n * D + h * HD;
+    bf16* db = d_qkv + (int64_t)f * n * ld + h * HD;
+    load_tile_async(sQ, base, ld, n, npad, tid, blockDim.x);
+    load_tile_async(sK, base + D, ld, n, npad, tid, blockDim.x);
+    load_tile_async(sV, base + 2 * D, ld, n, npad, tid, blockDim.x);
+    load_tile_async(sG, gb, D, n, npad, tid, blockDim.x);
+    const float* lr = lse + ((int64_t)f * heads + h) * n;
+    for (int i = tid; i < npad; i += blockDim.x) sL[i] = i < n ? lr[i] * LOG2E : 0.f;
+    // delta_i = sum_d dO[i,d] * O[i,d]   (one warp per row; coalesced 128 B rows)
+    for (int i = warp; i < npad; i += nwarps) {
+        float acc = 0.f;
+        if (i < n) {
+            __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(gb + (int64_t)i * D + 2 * lane);
+            __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(ob + (int64_t)i * D + 2 * lane);
+            float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+            acc = fa.x * fb.x + fa.y * fb.y;
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) sDl[i] = acc;
+    }
+    cp_async_wait_all();
+    __syncthreads();
+
+    const int g = lane >> 2, t = lane & 3;
+    const int r0 = warp * 16;   // this warp's 16 rows (queries in phase 1, keys in phase 2)
+    if (r0 >= n) return;        // no further block-wide barriers below
+
+    // ---------------- phase 1: dQ for query rows r0..r0+15
+    {
+        float dq[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dq[i][j] = 0.f;
+        const float ls0 = sL[r0 + g], ls1 = sL[r0 + g + 8];
+        const float dl0 = sDl[r0 + g], dl1 = sDl[r0 + g + 8];
+        for (int kc = 0; kc < npad; kc += 32) {
+            float s[4][4], dp[4][4];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { s[nt][j] = 0.f; dp[nt][j] = 0.f; }
+#pragma unroll
+            for (int kp = 0; kp < 2; ++kp) {
+                uint32_t qa0[4], qa1[4], ga0[4], ga1[4];
+                lda_frag(qa0, sQ + r0 * LDS + kp * 32, lane);
+                lda_frag(qa1, sQ + r0 * LDS + kp * 32 + 16, lane);
+                lda_frag(ga0, sG + r0 * LDS + kp * 32, lane);
+                lda_frag(ga1, sG + r0 * LDS + kp * 32 + 16, lane);
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    uint32_t kb[4], vb[4];
+                    ldb_frag_nk(kb, sK + (kc + nt * 8) * LDS + kp * 32, lane);
+                    ldb_frag_nk(vb, sV + (kc + nt * 8) * LDS + kp * 32, lane);
+                    mma16816(s[nt], qa0, kb[0], kb[1]);
+                    mma16816(s[nt], qa1, kb[2], kb[3]);
+                    mma16816(dp[nt], ga0, vb[0], vb[1]);
+                    mma16816(dp[nt], ga1, vb[2], vb[3]);
+                }
+            }
+            uint32_t dsa[2][4];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                int key = kc + nt * 8 + 2 * t;
+                float v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float lsj = (j < 2) ? ls0 : ls1, dlj = (j < 2) ? dl0 : dl1;
+                    float p = (key + (j & 1) < n) ? exp2f(s[nt][j] * SCALE_LOG2 - lsj) : 0.f;
+                    v[j] = p * (dp[nt][j] - dlj) * 0.125f;
+                }
+                dsa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(v[0], v[1]);
+                dsa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(v[2], v[3]);
+            }
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll
+                for (int dpair = 0; dpair < 4; ++dpair) {
+                    uint32_t kb[4];
+                    ldb_frag_kn(kb, sK + (kc + kk * 16) * LDS + dpair * 16, lane);
+                    mma16816(dq[2 * dpair], dsa[kk], kb[0], kb[1]);
+                    mma16816(dq[2 * dpair + 1], dsa[kk], kb[2], kb[3]);
+                }
+            }
+        }
+        const int ra = r0 + g, rb = r0 + g + 8;
+#pragma unroll
+        for (int dt = 0; dt < 8; ++dt) {
+            int c = dt * 8 + 2 * t;
+            if (ra < n) *reinterpret_cast<uint32_t*>(db + (int64_t)ra * ld + c) = pack_bf16(dq[dt][0], dq[dt][1]);
+            if (rb < n) *reinterpret_cast<uint32_t*>(db + (int64_t)rb * ld + c) = pack_bf16(dq[dt][2], dq[dt][3]);
+        }
+    }
+    // ---------------- phase 2: dK, dV for key rows r0..r0+15
+    {
+        float dk[8][4], dv[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { dk[i][j] = 0.f; dv[i][j] = 0.f; }
+        for (int qc = 0; qc < npad; qc += 32) {
+            float s[4][4], dp[4][4];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { s[nt][j] = 0.f; dp[nt][j] = 0.f; }
+#pragma unroll
+            for (int kp = 0; kp < 2; ++kp) {
+                uint32_t ka0[4], ka1[4], va0[4], va1[4];
+                lda_frag(ka0, sK + r0 * LDS + kp * 32, lane);
+                lda_frag(ka1, sK + r0 * LDS + kp * 32 + 16, lane);
+                lda_frag(va0, sV + r0 * LDS + kp * 32, lane);
+                lda_frag(va1, sV + r0 * LDS + kp * 32 + 16, lane);
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    uint32_t qb[4], gbf[4];
+                    ldb_frag_nk(qb, sQ + (qc + nt * 8) * LDS + kp * 32, lane);
+                    ldb_frag_nk(gbf, sG + (qc + nt * 8) * LDS + kp * 32, lane);
+                    mma16816(s[nt], ka0, qb[0], qb[1]);      // S^T[key, q]
+                    mma16816(s[nt], ka1, qb[2], qb[3]);
+                    mma16816(dp[nt], va0, gbf[0], gbf[1]);   // dP^T[key, q]
+                    mma16816(dp[nt], va1, gbf[2], gbf[3]);
+                }
+            }
+            uint32_t pa[2][4], dsa[2][4];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                int q = qc + nt * 8 + 2 * t;
+                float lq0 = sL[q], lq1 = sL[q + 1], dq0 = sDl[q], dq1 = sDl[q + 1];
+                float p[4], v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float lsj = (j & 1) ? lq1 : lq0, dlj = (j & 1) ? dq1 : dq0;
+                    p[j] = (q + (j & 1) < n) ? exp2f(s[nt][j] * SCALE_LOG2 - lsj) : 0.f;
+                    v[j] = p[j] * (dp[nt][j] - dlj) * 0.125f;
+                }
+                pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(p[0], p[1]);
+                pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p[2], p[3]);
+                dsa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(v[0], v[1]);
+                dsa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(v[2], v[3]);
+            }
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll
+                for (int dpair = 0; dpair < 4; ++dpair) {
+                    uint32_t gb4[4], qb4[4];
+                    ldb_frag_kn(gb4, sG + (qc + kk * 16) * LDS + dpair * 16, lane);
+                    ldb_frag_kn(qb4, sQ + (qc + kk * 16) * LDS + dpair * 16, lane);
+                    mma16816(dv[2 * dpair], pa[kk], gb4[0], gb4[1]);
+                    mma16816(dv[2 * dpair + 1], pa[kk], gb4[2], gb4[3]);
+                    mma16816(dk[2 * dpair], dsa[kk], qb4[0], qb4[1]);
+                    mma16816(dk[2 * dpair + 1], dsa[kk], qb4[2], qb4[3]);
+                }
+            }
+        }
+        const int ra = r0 + g, rb = r0 + g + 8;
+#pragma unroll
+        for (int dt = 0; dt < 8; ++dt) {
+            int c = dt * 8 + 2 * t;
+            if (ra < n) {
+                *reinterpret_cast<uint32_t*>(db + (int64_t)ra * ld + D + c) = pack_bf16(dk[dt][0], dk[dt][1]);
+                *reinterpret_cast<uint32_t*>(db + (int64_t)ra * ld + 2 * D + c) = pack_bf16(dv[dt][0], dv[dt][1]);
+            }
+            if (rb < n) {
+                *reinterpret_cast<uint32_t*>(db + (int64_t)rb * ld + D + c) = pack_bf16(dk[dt][2], dk[dt][3]);
+                *reinterpret_cast<uint32_t*>(db + (int64_t)rb * ld + 2 * D + c) = pack_bf16(dv[dt][2], dv[dt][3]);
+            }
+        }
+    }
+}
+
+int attn_spatial_fwd_mma(const void* qkv, void* o, float* lse, int frames, int n, int heads, cudaStream_t s) {
+    int npad = (n + 31) & ~31;
+    int nwarps = (n + 15) / 16;
+    if (nwarps * 32 > 576) return AIMB_ERR_UNSUPPORTED;
+    size_t smem = (size_t)3 * npad * LDS * 2;
+    if (smem > 227 * 1024) return AIMB_ERR_UNSUPPORTED;
+    if (cudaFuncSetAttribute(attn_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return AIMB_ERR_CUDA;
+    attn_fwd_mma_kernel<<<frames * heads, nwarps * 32, smem, s>>>((const bf16*)qkv, (bf16*)o, lse, n, heads);
+    AIMB_CHECK_LAUNCH();
+    return AIMB_OK;
+}
+
+int attn_spatial_bwd_mma(const void* qkv, const void* o, const void* d_o, const float* lse, void* d_qkv, int frames, int n,
+                         int heads, cudaStream_t s) {
+    int npad = (n + 31) & ~31;
+    int nwarps = (n + 15) / 16;
+    if (nwarps * 32 > 576) return AIMB_ERR_UNSUPPORTED;
+    size_t smem = (size_t)4 * npad * LDS * 2 + (size_t)2 * npad * 4;
+    if (smem > 227 * 1024) return AIMB_ERR_UNSUPPORTED;
+    if (cudaFuncSetAttribute(attn_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return AIMB_ERR_CUDA;
+    attn_bwd_mma_kernel<<<frames * heads, nwarps * 32, smem, s>>>((const bf16*)qkv, (const bf16*)o, (const bf16*)d_o, lse,
+                                                                  (bf16*)d_qkv, n, heads);
+    AIMB_CHECK_LAUNCH();
+    return AIMB_OK;
+}
+
+}  // namespace aimb

@@ -1,0 +1,548 @@
+// HBM-bound kernels of the path: stem assembly, LayerNorm fwd/bwd, tail, bias/temporal-embedding
+// reductions, transpose.  One warp per row, 16-byte vector loads, fp32 statistics.
+#include "common.cuh"
+
+namespace aimb {
+
+template <typename T> struct VecIO;
+template <> struct VecIO<float> {
+    static constexpr int N = 4;
+    static __device__ __forceinline__ void ld(const float* p, float* v) {
+        float4 t = *reinterpret_cast<const float4*>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    static __device__ __forceinline__ void st(float* p, const float* v) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+template <> struct VecIO<bf16> {
+    static constexpr int N = 8;
+    static __device__ __forceinline__ void ld(const bf16* p, float* v) {
+        uint4 t = *reinterpret_cast<const uint4*>(p);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+    }
+    static __device__ __forceinline__ void st(bf16* p, const float* v) {
+        uint4 t;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        *reinterpret_cast<uint4*>(p) = t;
+    }
+};
+
+// Rows up to MAXD elements are kept in registers: NIT chunks of (32 lanes * VEC) elements.
+constexpr int MAXD = 1024;
+
+template <typename T> struct RowRegs {
+    static constexpr int V = VecIO<T>::N;
+    static constexpr int NIT = MAXD / (32 * V);
+    float v[NIT][V];
+    __device__ __forceinline__ void load(const T* row, int D, int lane) {
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            int c = (it * 32 + lane) * V;
+            if (c < D) VecIO<T>::ld(row + c, v[it]);
+            else {
+#pragma unroll
+                for (int j = 0; j < V; ++j) v[it][j] = 0.f;
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------ LayerNorm forward
+template <typename T>
+__device__ __forceinline__ void ln_row(RowRegs<T>& r, int D, int lane, float eps, float& mean, float& rstd) {
+    constexpr int V = RowRegs<T>::V, NIT = RowRegs<T>::NIT;
+    float s = 0.f;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it)
+#pragma unroll
+        for (int j = 0; j < V; ++j) s += r.v[it][j];
+    mean = warp_sum(s) / D;
+    float q = 0.f;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        int c = (it * 32 + lane) * V;
+        if (c < D) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) { float d = r.v[it][j] - mean; q += d * d; }
+        }
+    }
+    rstd = rsqrtf(warp_sum(q) / D + eps);
+}
+
+template <typename T>
+__device__ __forceinline__ void ln_apply_store(const RowRegs<T>& r, const T* gamma, const T* beta, T* y, int D, int lane,
+                                               float mean, float rstd) {
+    constexpr int V = RowRegs<T>::V, NIT = RowRegs<T>::NIT;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        int c = (it * 32 + lane) * V;
+        if (c < D) {
+            float g[V], b[V], o[V];
+            VecIO<T>::ld(gamma + c, g);
+            VecIO<T>::ld(beta + c, b);
+#pragma unroll
+            for (int j = 0; j < V; ++j) o[j] = (r.v[it][j] - mean) * rstd * g[j] + b[j];
+            VecIO<T>::st(y + c, o);
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) layernorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ gamma,
+                                                            const T* __restrict__ beta, T* __restrict__ y,
+                                                            float* __restrict__ mean_o, float* __restrict__ rstd_o,
+                                                            int64_t rows, int D, float eps) {
+    int lane = threadIdx.x & 31;
+    int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    RowRegs<T> r;
+    r.load(x + row * D, D, lane);
+    float mean, rstd;
+    ln_row<T>(r, D, lane, eps, mean, rstd);
+    ln_apply_store<T>(r, gamma, beta, y + row * D, D, lane, mean, rstd);
+    if (lane == 0) {
+        if (mean_o) mean_o[row] = mean;
+        if (rstd_o) rstd_o[row] = rstd;
+    }
+}
+
+// ------------------------------------------------------------------ LayerNorm backward (input grad only)
+template <typename T>
+__global__ void __launch_bounds__(128) layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                            const float* __restrict__ mean_i,
+                                                            const float* __restrict__ rstd_i,
+                                                            const T* __restrict__ gamma, const T* dres, T* dx,
+                                                            int64_t rows, int D) {
+    constexpr int V = RowRegs<T>::V, NIT = RowRegs<T>::NIT;
+    int lane = threadIdx.x & 31;
+    int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    RowRegs<T> g, xh;
+    g.load(dy + row * D, D, lane);
+    xh.load(x + row * D, D, lane);
+    float mean = mean_i[row], rstd = rstd_i[row];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        int c = (it * 32 + lane) * V;
+        if (c < D) {
+            float gm[V];
+            VecIO<T>::ld(gamma + c, gm);
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                float gg = g.v[it][j] * gm[j];
+                float h = (xh.v[it][j] - mean) * rstd;
+                g.v[it][j] = gg;
+                xh.v[it][j] = h;
+                s1 += gg;
+                s2 += gg * h;
+            }
+        }
+    }
+    s1 = warp_sum(s1) / D;
+    s2 = warp_sum(s2) / D;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        int c = (it * 32 + lane) * V;
+        if (c < D) {
+            float o[V];
+            if (dres) VecIO<T>::ld(dres + row * D + c, o);
+            else {
+#pragma unroll
+                for (int j = 0; j < V; ++j) o[j] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < V; ++j) o[j] += rstd * (g.v[it][j] - s1 - xh.v[it][j] * s2);
+            VecIO<T>::st(dx + row * D + c, o);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ stem: cls | tok + pos + temb -> z ; ln_pre -> x
+template <typename T>
+__global__ void __launch_bounds__(128) stem_assemble_ln_kernel(const T* __restrict__ tok, const T* __restrict__ cls,
+                                                               const T* __restrict__ pos, const T* __restrict__ temb,
+                                                               const T* __restrict__ gamma, const T* __restrict__ beta,
+                                                               T* __restrict__ z, T* __restrict__ xo,
+                                                               float* __restrict__ mean_o, float* __restrict__ rstd_o,
+                                                               int BT, int T_, int n, int D, float eps) {
+    constexpr int V = RowRegs<T>::V, NIT = RowRegs<T>::NIT;
+    int lane = threadIdx.x & 31;
+    int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (row >= (int64_t)BT * n) return;
+    int f = (int)(row / n), tk = (int)(row % n), t = f % T_;
+    const T* src = (tk == 0) ? cls : tok + ((int64_t)f * (n - 1) + (tk - 1)) * D;
+    RowRegs<T> r;
+    r.load(src, D, lane);
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        int c = (it * 32 + lane) * V;
+        if (c < D) {
+            float a[V], b[V];
+            VecIO<T>::ld(pos + (int64_t)tk * D + c, a);
+            VecIO<T>::ld(temb + (int64_t)t * D + c, b);
+            // same association order as the reference: (x + pos) + temb   (vitclip_aim.py:452,456)
+#pragma unroll
+            for (int j = 0; j < V; ++j) r.v[it][j] = roundT<T>(roundT<T>(r.v[it][j] + a[j]) + b[j]);
+            if (z) VecIO<T>::st(z + row * D + c, r.v[it]);
+        }
+    }
+    float mean, rstd;
+    ln_row<T>(r, D, lane, eps, mean, rstd);
+    ln_apply_store<T>(r, gamma, beta, xo + row * D, D, lane, mean, rstd);
+    if (lane == 0) {
+        if (mean_o) mean_o[row] = mean;
+        if (rstd_o) rstd_o[row] = rstd;
+    }
+}
+
+// ------------------------------------------------------------------ im2col of the patch conv
+template <typename TI> __device__ __forceinline__ float ld_in(const TI* p) { return (float)*p; }
+template <> __device__ __forceinline__ float ld_in<bf16>(const bf16* p) { return __bfloat162float(*p); }
+
+template <typename TI, typename T>
+__global__ void __launch_bounds__(256) im2col_kernel(const TI* __restrict__ x, const float* __restrict__ mean,
+                                                     const float* __restrict__ std_, T* __restrict__ cols, int B,
+                                                     int T_, int H, int W, int p, int kpad) {
+    int G = W / p, Gy = H / p;
+    int64_t total = (int64_t)B * T_ * 3 * Gy * p * G;  // one thread per (b, t, c, gy, ky, gx): p contiguous pixels
+    int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= total) return;
+    int gx = (int)(id % G); id /= G;
+    int ky = (int)(id % p); id /= p;
+    int gy = (int)(id % Gy); id /= Gy;
+    int c = (int)(id % 3); id /= 3;
+    int t = (int)(id % T_);
+    int b = (int)(id / T_);
+    const TI* src = x + ((((int64_t)b * 3 + c) * T_ + t) * H + (gy * p + ky)) * W + gx * p;
+    int64_t row = ((int64_t)(b * T_ + t) * Gy + gy) * G + gx;
+    T* dst = cols + row * kpad + (c * p + ky) * p;
+    float m = 0.f, rs = 1.f;
+    if (mean) { m = mean[c]; rs = 1.f / std_[c]; }
+    for (int kx = 0; kx < p; ++kx) stf<T>(dst + kx, (ld_in<TI>(src + kx) - m) * rs);
+    if (c == 2 && ky == p - 1)
+        for (int k = 3 * p * p; k < kpad; ++k) stf<T>(cols + row * kpad + k, 0.f);
+}
+
+// ------------------------------------------------------------------ tail: ln_post on cls rows -> feat [B, D, T] fp32
+template <typename T>
+__global__ void __launch_bounds__(128) tail_fwd_kernel(const T* __restrict__ x, const T* __restrict__ gamma,
+                                                       const T* __restrict__ beta, float* __restrict__ feat,
+                                                       float* __restrict__ mean_o, float* __restrict__ rstd_o, int BT,
+                                                       int T_, int n, int D, float eps) {
+    constexpr int V = RowRegs<T>::V, NIT = RowRegs<T>::NIT;
+    int lane = threadIdx.x & 31;
+    int f = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (f >= BT) return;
+    int b = f / T_, t = f % T_;
+    RowRegs<T> r;
+    r.load(x + (int64_t)f * n * D, D, lane);
+    float mean, rstd;
+    ln_row<T>(r, D, lane, eps, mean, rstd);
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        int c = (it * 32 + lane) * V;
+        if (c < D) {
+            float g[V], bb[V];
+            VecIO<T>::ld(gamma + c, g);
+            VecIO<T>::ld(beta + c, bb);
+#pragma unroll
+            for (int j = 0; j < V; ++j)
+                feat[((int64_t)b * D + c + j) * T_ + t] = (r.v[it][j] - mean) * rstd * g[j] + bb[j];
+        }
+    }
+    if (lane == 0) { mean_o[f] = mean; rstd_o[f] = rstd; }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) tail_bwd_kernel(const float* __restrict__ dfeat, const T* __restrict__ x,
+                                                       const float* __restrict__ mean_i,
+                                                       const float* __restrict__ rstd_i, const T* __restrict__ gamma,
+                                                       T* __restrict__ dx, float* __restrict__ dgamma,
+                                                       float* __restrict__ dbeta, int BT, int T_, int n, int D) {
+    constexpr int V = RowRegs<T>::V, NIT = RowRegs<T>::NIT;
+    int lane = threadIdx.x & 31;
+    int f = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (f >= BT) return;
+    int b = f / T_, t = f % T_;
+    RowRegs<T> xh, g;
+    xh.load(x + (int64_t)f * n * D, D, lane);
+    float mean = mean_i[f], rstd = rstd_i[f];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        int c = (it * 32 + lane) * V;
+        if (c < D) {
+            float gm[V];
+            VecIO<T>::ld(gamma + c, gm);
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                float dy = dfeat[((int64_t)b * D + c + j) * T_ + t];
+                float h = (xh.v[it][j] - mean) * rstd;
+                atomicAdd(dgamma + c + j, dy * h);
+                atomicAdd(dbeta + c + j, dy);
+                float gg = dy * gm[j];
+                g.v[it][j] = gg;
+                xh.v[it][j] = h;
+                s1 += gg;
+                s2 += gg * h;
+            }
+        }
+    }
+    s1 = warp_sum(s1) / D;
+    s2 = warp_sum(s2) / D;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        int c = (it * 32 + lane) * V;
+        if (c < D) {
+            float o[V];
+#pragma unroll
+            for (int j = 0; j < V; ++j) o[j] = rstd * (g.v[it][j] - s1 - xh.v[it][j] * s2);
+            VecIO<T>::st(dx + (int64_t)f * n * D + c, o);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ column sums (bias grads, temporal-embedding grad)
+// block = 32 (columns) x 8 (row lanes); each block reduces ROWS rows of 32 columns, then one atomicAdd per column.
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, int64_t ld,
+                                                     const float* __restrict__ row_scale, int row_mod, float alpha,
+                                                     float* __restrict__ out, int64_t R, int C, int rows_per_block) {
+    __shared__ float red[8][33];
+    int c = blockIdx.x * 32 + threadIdx.x;
+    int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+    int64_t r1 = r0 + rows_per_block < R ? r0 + rows_per_block : R;
+    float s = 0.f;
+    if (c < C)
+        for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
+            float v = ldf<T>(x + r * ld + c);
+            if (row_scale) v *= row_scale[r % row_mod];
+            s += v;
+        }
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+        atomicAdd(out + c, alpha * t);
+    }
+}
+
+// out[t, d] += sum_{tok} dz[(f*n + tok), d] for frame f = blockIdx.y (t = f % T)
+template <typename T>
+__global__ void __launch_bounds__(256) temb_grad_kernel(const T* __restrict__ dz, float* __restrict__ out, int T_, int n,
+                                                        int D) {
+    __shared__ float red[8][33];
+    int c = blockIdx.x * 32 + threadIdx.x;
+    int f = blockIdx.y;
+    float s = 0.f;
+    if (c < D)
+        for (int tk = threadIdx.y; tk < n; tk += 8) s += ldf<T>(dz + ((int64_t)f * n + tk) * D + c);
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < D) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+        atomicAdd(out + (int64_t)(f % T_) * D + c, t);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ in, T* __restrict__ out, int R, int C) {
+    __shared__ T tile[32][33];
+    int c = blockIdx.x * 32 + threadIdx.x;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        int r = blockIdx.y * 32 + i;
+        if (r < R && c < C) tile[i][threadIdx.x] = in[(int64_t)r * C + c];
+    }
+    __syncthreads();
+    int r = blockIdx.y * 32 + threadIdx.x;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        int cc = blockIdx.x * 32 + i;
+        if (r < R && cc < C) out[(int64_t)cc * R + r] = tile[threadIdx.x][i];
+    }
+}
+
+static inline bool vec_ok(int D, int dtype) {
+    int v = dtype == AIMB_BF16 ? 8 : 4;
+    return D > 0 && D % v == 0 && D <= MAXD;
+}
+
+}  // namespace aimb
+
+using namespace aimb;
+
+extern "C" int aimb_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd,
+                                  int64_t rows, int32_t D, float eps, int32_t dtype, void* stream) {
+    if (!x || !gamma || !beta || !y || rows < 0 || !vec_ok(D, dtype)) return AIMB_ERR_ARG;
+    if (rows == 0) return AIMB_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned grid = (unsigned)((rows + 3) / 4);
+    if (dtype == AIMB_BF16)
+        layernorm_fwd_kernel<bf16><<<grid, 128, 0, s>>>((const bf16*)x, (const bf16*)gamma, (const bf16*)beta, (bf16*)y,
+                                                        mean, rstd, rows, D, eps);
+    else if (dtype == AIMB_F32)
+        layernorm_fwd_kernel<float><<<grid, 128, 0, s>>>((const float*)x, (const float*)gamma, (const float*)beta,
+                                                         (float*)y, mean, rstd, rows, D, eps);
+    else return AIMB_ERR_ARG;
+    AIMB_CHECK_LAUNCH();
+    return AIMB_OK;
+}
+
+extern "C" int aimb_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma,
+                                  const void* dres, void* dx, int64_t rows, int32_t D, int32_t dtype, void* stream) {
+    if (!dy || !x || !mean || !rstd || !gamma || !dx || rows < 0 || !vec_ok(D, dtype)) return AIMB_ERR_ARG;
+    if (rows == 0) return AIMB_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned grid = (unsigned)((rows + 3) / 4);
+    if (dtype == AIMB_BF16)
+        layernorm_bwd_kernel<bf16><<<grid, 128, 0, s>>>((const bf16*)dy, (const bf16*)x, mean, rstd, (const bf16*)gamma,
+                                                        (const bf16*)dres, (bf16*)dx, rows, D);
+    else if (dtype == AIMB_F32)
+        layernorm_bwd_kernel<float><<<grid, 128, 0, s>>>((const float*)dy, (const float*)x, mean, rstd,
+                                                         (const float*)gamma, (const float*)dres, (float*)dx, rows, D);
+    else return AIMB_ERR_ARG;
+    AIMB_CHECK_LAUNCH();
+    return AIMB_OK;
+}
+
+extern "C" int aimb_stem_assemble_ln(const void* tok, const void* cls, const void* pos, const void* temb,
+                                     const void* gamma, const void* beta, void* z, void* x, float* mean, float* rstd,
+                                     int32_t B, int32_t T, int32_t n, int32_t D, float eps, int32_t dtype, void* stream) {
+    if (!tok || !cls || !pos || !temb || !gamma || !beta || !x || B < 0 || T <= 0 || n < 2 || !vec_ok(D, dtype))
+        return AIMB_ERR_ARG;
+    if (B == 0) return AIMB_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t rows = (int64_t)B * T * n;
+    unsigned grid = (unsigned)((rows + 3) / 4);
+    if (dtype == AIMB_BF16)
+        stem_assemble_ln_kernel<bf16><<<grid, 128, 0, s>>>((const bf16*)tok, (const bf16*)cls, (const bf16*)pos,
+                                                           (const bf16*)temb, (const bf16*)gamma, (const bf16*)beta,
+                                                           (bf16*)z, (bf16*)x, mean, rstd, B * T, T, n, D, eps);
+    else if (dtype == AIMB_F32)
+        stem_assemble_ln_kernel<float><<<grid, 128, 0, s>>>((const float*)tok, (const float*)cls, (const float*)pos,
+                                                            (const float*)temb, (const float*)gamma, (const float*)beta,
+                                                            (float*)z, (float*)x, mean, rstd, B * T, T, n, D, eps);
+    else return AIMB_ERR_ARG;
+    AIMB_CHECK_LAUNCH();
+    return AIMB_OK;
+}
+
+template <typename TI>
+static int im2col_dispatch(const void* x, const float* mean, const float* std_, void* cols, int dtype, int B, int T, int H,
+                           int W, int p, int kpad, cudaStream_t s) {
+    int64_t total = (int64_t)B * T * 3 * (H / p) * p * (W / p);
+    unsigned grid = (unsigned)((total + 255) / 256);
+    if (dtype == AIMB_BF16)
+        im2col_kernel<TI, bf16><<<grid, 256, 0, s>>>((const TI*)x, mean, std_, (bf16*)cols, B, T, H, W, p, kpad);
+    else if (dtype == AIMB_F32)
+        im2col_kernel<TI, float><<<grid, 256, 0, s>>>((const TI*)x, mean, std_, (float*)cols, B, T, H, W, p, kpad);
+    else return AIMB_ERR_ARG;
+    AIMB_CHECK_LAUNCH();
+    return AIMB_OK;
+}
+
+extern "C" int aimb_im2col(const void* x, int32_t x_dtype, const float* mean, const float* std_, void* cols, int32_t dtype,
+                           int32_t B, int32_t T, int32_t H, int32_t W, int32_t patch, int32_t kpad, void* stream) {
+    if (!x || !cols || B < 0 || T <= 0 || patch <= 0 || H % patch || W % patch || kpad < 3 * patch * patch)
+        return AIMB_ERR_ARG;
+    if ((mean == nullptr) != (std_ == nullptr)) return AIMB_ERR_ARG;
+    if (B == 0) return AIMB_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (x_dtype == AIMB_F32) return im2col_dispatch<float>(x, mean, std_, cols, dtype, B, T, H, W, patch, kpad, s);
+    if (x_dtype == AIMB_BF16) return im2col_dispatch<bf16>(x, mean, std_, cols, dtype, B, T, H, W, patch, kpad, s);
+    if (x_dtype == AIMB_U8) return im2col_dispatch<uint8_t>(x, mean, std_, cols, dtype, B, T, H, W, patch, kpad, s);
+    return AIMB_ERR_ARG;
+}
+
+extern "C" int aimb_tail_fwd(const void* x, const void* gamma, const void* beta, float* feat, float* mean, float* rstd,
+                             int32_t B, int32_t T, int32_t n, int32_t D, float eps, int32_t dtype, void* stream) {
+    if (!x || !gamma || !beta || !feat || !mean || !rstd || B < 0 || T <= 0 || n <= 0 || !vec_ok(D, dtype))
+        return AIMB_ERR_ARG;
+    if (B == 0) return AIMB_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned grid = (unsigned)((B * T + 3) / 4);
+    if (dtype == AIMB_BF16)
+        tail_fwd_kernel<bf16><<<grid, 128, 0, s>>>((const bf16*)x, (const bf16*)gamma, (const bf16*)beta, feat, mean, rstd,
+                                                   B * T, T, n, D, eps);
+    else if (dtype == AIMB_F32)
+        tail_fwd_kernel<float><<<grid, 128, 0, s>>>((const float*)x, (const float*)gamma, (const float*)beta, feat, mean,
+                                                    rstd, B * T, T, n, D, eps);
+    else return AIMB_ERR_ARG;
+    AIMB_CHECK_LAUNCH();
+    return AIMB_OK;
+}
+
+extern "C" int aimb_tail_bwd(const float* dfeat, const void* x, const float* mean, const float* rstd, const void* gamma,
+                             void* dx, float* dgamma, float* dbeta, int32_t B, int32_t T, int32_t n, int32_t D,
+                             int32_t dtype, void* stream) {
+    if (!dfeat || !x || !mean || !rstd || !gamma || !dx || !dgamma || !dbeta || B < 0 || T <= 0 || n <= 0 ||
+        !vec_ok(D, dtype))
+        return AIMB_ERR_ARG;
+    if (B == 0) return AIMB_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    size_t esz = dtype == AIMB_BF16 ? 2 : 4;
+    if (cudaMemsetAsync(dx, 0, (size_t)B * T * n * D * esz, s) != cudaSuccess) return AIMB_ERR_CUDA;
+    if (cudaMemsetAsync(dgamma, 0, (size_t)D * 4, s) != cudaSuccess) return AIMB_ERR_CUDA;
+    if (cudaMemsetAsync(dbeta, 0, (size_t)D * 4, s) != cudaSuccess) return AIMB_ERR_CUDA;
+    unsigned grid = (unsigned)((B * T + 3) / 4);
+    if (dtype == AIMB_BF16)
+        tail_bwd_kernel<bf16><<<grid, 128, 0, s>>>(dfeat, (const bf16*)x, mean, rstd, (const bf16*)gamma, (bf16*)dx, dgamma,
+                                                   dbeta, B * T, T, n, D);
+    else if (dtype == AIMB_F32)
+        tail_bwd_kernel<float><<<grid, 128, 0, s>>>(dfeat, (const float*)x, mean, rstd, (const float*)gamma, (float*)dx,
+                                                    dgamma, dbeta, B * T, T, n, D);
+    else return AIMB_ERR_ARG;
+    AIMB_CHECK_LAUNCH();
+    return AIMB_OK;
+}
+
+extern "C" int aimb_colsum(const void* x, int64_t ld, const float* row_scale, int32_t row_mod, float alpha, float* out,
+                           int64_t R, int32_t C, int32_t accumulate, int32_t dtype, void* stream) {
+    if (!x || !out || R < 0 || C <= 0 || ld < C || (row_scale && row_mod <= 0)) return AIMB_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!accumulate && cudaMemsetAsync(out, 0, (size_t)C * 4, s) != cudaSuccess) return AIMB_ERR_CUDA;
+    if (R == 0) return AIMB_OK;
+    const int rpb = 256;
+    dim3 grid((C + 31) / 32, (unsigned)((R + rpb - 1) / rpb)), block(32, 8);
+    if (dtype == AIMB_BF16)
+        colsum_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)x, ld, row_scale, row_mod, alpha, out, R, C, rpb);
+    else if (dtype == AIMB_F32)
+        colsum_kernel<float><<<grid, block, 0, s>>>((const float*)x, ld, row_scale, row_mod, alpha, out, R, C, rpb);
+    else return AIMB_ERR_ARG;
+    AIMB_CHECK_LAUNCH();
+    return AIMB_OK;
+}
+
+extern "C" int aimb_temb_grad(const void* dz, float* out, int32_t B, int32_t T, int32_t n, int32_t D, int32_t dtype,
+                              void* stream) {
+    if (!dz || !out || B < 0 || T <= 0 || n <= 0 || D <= 0) return AIMB_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cudaMemsetAsync(out, 0, (size_t)T * D * 4, s) != cudaSuccess) return AIMB_ERR_CUDA;
+    if (B == 0) return AIMB_OK;
+    dim3 grid((D + 31) / 32, B * T), block(32, 8);
+    if (dtype == AIMB_BF16) temb_grad_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)dz, out, T, n, D);
+    else if (dtype == AIMB_F32) temb_grad_kernel<float><<<grid, block, 0, s>>>((const float*)dz, out, T, n, D);
+    else return AIMB_ERR_ARG;
+    AIMB_CHECK_LAUNCH();
+    return AIMB_OK;
+}
+
+extern "C" int aimb_transpose(const void* in, void* out, int32_t R, int32_t C, int32_t dtype, void* stream) {
+    if (!in || !out || R <= 0 || C <= 0) return AIMB_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
+    if (dtype == AIMB_BF16) transpose_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)in, (bf16*)out, R, C);
+    else if (dtype == AIMB_F32) transpose_kernel<float><<<grid, block, 0, s>>>((const float*)in, (float*)out, R, C);
+    else return AIMB_ERR_ARG;
+    AIMB_CHECK_LAUNCH();
+    return AIMB_OK;
+}

@@ -1,0 +1,151 @@
+/* aimb200 — C ABI of the B200-native AIM `ViT_CLIP` hot path (libaimb200.so).
+ *
+ * The reference (bobochow/adapt-image-models) is 100 % Python and has no FFI of its own
+ * (SURVEY.md §2.2); what it *launches* on this path are ATen / cuBLAS / cuDNN library calls.
+ * Each entry point below replaces one group of those calls; the reference call site it
+ * stands in for is cited as file:line (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain device pointers + explicit shapes; the CALLER allocates every output/workspace
+ *   - `dtype`: AIMB_F32 (fp32 storage + fp32 SIMT math; the 1e-3 parity mode) or
+ *              AIMB_BF16 (bf16 storage, fp32 accumulate/statistics; tcgen05 tensor cores)
+ *   - `stream`: a cudaStream_t passed as void*; every call only enqueues work on it
+ *   - return 0 on success, negative AIMB_ERR_* otherwise; never throws, never exits
+ *   - activations are row-major [rows, D]; row m = (b*T + t)*n + token  (frame-major; token 0 = cls,
+ *     token 1+gy*G+gx = patch (gy,gx)); head h = columns h*64 .. h*64+63; q/k/v = columns
+ *     0:D / D:2D / 2D:3D of the fused QKV buffer (== rows of attn.in_proj_weight)
+ */
+#ifndef AIMB200_H
+#define AIMB200_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AIMB_OK 0
+#define AIMB_ERR_ARG (-1)         /* bad shape / alignment / null pointer */
+#define AIMB_ERR_CUDA (-2)        /* a CUDA runtime call or launch failed */
+#define AIMB_ERR_UNSUPPORTED (-3) /* configuration outside what the kernels implement */
+#define AIMB_ERR_DRIVER (-4)      /* cuTensorMapEncodeTiled unavailable / failed */
+
+#define AIMB_F32 0
+#define AIMB_BF16 1
+#define AIMB_U8 2 /* input clips only */
+
+#define AIMB_ACT_NONE 0
+#define AIMB_ACT_QUICKGELU 1 /* u*sigmoid(1.702u)   vit_clip.py:80-82 */
+#define AIMB_ACT_GELU 2      /* exact erf GELU      vit_clip.py:56 (nn.GELU) */
+
+#define AIMB_IMPL_AUTO 0 /* bf16 -> tensor-core kernels, f32 -> SIMT kernels */
+#define AIMB_IMPL_SIMT 1 /* force the SIMT kernel (debug / cross-check) */
+
+/* GEMM epilogue, applied per output element (m, n) of the fp32 accumulator `acc`:
+ *   v = acc + bias[n] * (bias_rowscaled ? row_scale[m % row_mod] : 1)
+ *   if (out_pre)  out_pre[m,n] = v                      (saved pre-activation for backward)
+ *   v = act(v)
+ *   if (dact_src) v *= dact'(dact_src[m,n])             (backward through an activation)
+ *   v *= alpha
+ *   if (row_scale && !bias_rowscaled) v *= row_scale[m % row_mod]   (DropPath per-token multiplier)
+ *   v += res1[m,n] + res2[m,n]
+ *   out[m,n] = v          (or out[m,n] += v when accumulate && out_f32)
+ * NULL pointers disable the corresponding term. */
+typedef struct aimb_epilogue {
+    const void* bias;       /* [N], dtype */
+    const float* row_scale; /* [row_mod] fp32 */
+    const void* res1;       /* [M, ldo] dtype */
+    const void* res2;       /* [M, ldo] dtype */
+    const void* dact_src;   /* [M, ldo] dtype */
+    void* out;              /* [M, ldo] dtype (fp32 if out_f32) */
+    void* out_pre;          /* [M, ldo] dtype */
+    float alpha;
+    int32_t row_mod;
+    int32_t act;
+    int32_t dact;
+    int32_t bias_rowscaled;
+    int32_t out_f32;
+    int32_t accumulate;
+    int64_t ldo; /* 0 -> N */
+} aimb_epilogue_t;
+
+int aimb_version(void);
+/* 0 if `device` is an sm_100 part this library can run on. */
+int aimb_device_ok(int device);
+const char* aimb_last_error(void);
+
+/* ---- stem: vit_clip.py:433-447 / vitclip_aim.py:445-459 ------------------------------------ */
+/* `(b t)` flatten + im2col of the k=s=p patch conv (replaces rearrange + cuDNN conv1 + reshape/permute).
+ * x [B,3,T,H,W] (x_dtype f32 / bf16 / u8; u8 applies (v-mean[c])/std[c] = GPUNormalize,
+ * mmaction/utils/module_hooks.py:35-87) -> cols [B*T*G*G, kpad] in `dtype`,
+ * row (b*T+t)*G*G + gy*G + gx, column c*p*p + ky*p + kx, zero padded up to kpad. */
+int aimb_im2col(const void* x, int32_t x_dtype, const float* mean, const float* std_, void* cols, int32_t dtype,
+                int32_t B, int32_t T, int32_t H, int32_t W, int32_t patch, int32_t kpad, void* stream);
+/* cls prepend + positional + temporal embedding + ln_pre in one pass (vit_clip.py:439-447).
+ * tok [B*T*G*G, D]; z (pre-LN sum, optional, kept for backward) and x (ln_pre output) are [B*T*n, D]. */
+int aimb_stem_assemble_ln(const void* tok, const void* cls, const void* pos, const void* temb, const void* gamma,
+                          const void* beta, void* z, void* x, float* mean, float* rstd, int32_t B, int32_t T,
+                          int32_t n, int32_t D, float eps, int32_t dtype, void* stream);
+/* grad of temporal_embedding: out[t, d] (+)= sum_{b, token} dz[(b*T+t)*n + token, d]  (fp32 out). */
+int aimb_temb_grad(const void* dz, float* out, int32_t B, int32_t T, int32_t n, int32_t D, int32_t dtype,
+                   void* stream);
+
+/* ---- LayerNorm: vit_clip.py:71-77 (fp32 statistics, eps 1e-5) ------------------------------ */
+int aimb_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd,
+                       int64_t rows, int32_t D, float eps, int32_t dtype, void* stream);
+/* dx = dres + LN'(dy) ; dres may be NULL; dx may alias dres or dy. */
+int aimb_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma,
+                       const void* dres, void* dx, int64_t rows, int32_t D, int32_t dtype, void* stream);
+
+/* ---- tail: vit_clip.py:450-456 (ln_post on the cls rows only, '(b t) d -> b d t') ----------- */
+/* feat is fp32 [B, D, T]. mean/rstd [B*T] saved for backward. */
+int aimb_tail_fwd(const void* x, const void* gamma, const void* beta, float* feat, float* mean, float* rstd,
+                  int32_t B, int32_t T, int32_t n, int32_t D, float eps, int32_t dtype, void* stream);
+/* dfeat fp32 [B, D, T] -> dx [B*T*n, D] (cls rows written, all other rows zeroed); dgamma/dbeta fp32 [D]
+ * (overwritten). */
+int aimb_tail_bwd(const float* dfeat, const void* x, const float* mean, const float* rstd, const void* gamma,
+                  void* dx, float* dgamma, float* dbeta, int32_t B, int32_t T, int32_t n, int32_t D, int32_t dtype,
+                  void* stream);
+
+/* ---- GEMMs: every nn.Linear on the path (vit_clip.py:60-69, 93-97, 132-138, 157) ------------- */
+/* C = epilogue(A[M,K] * W[N,K]^T).  A row stride lda, W row stride ldw (elements), K contiguous.
+ * bf16 + AIMB_IMPL_AUTO runs the TMA + tcgen05/TMEM kernel (needs K % 64 == 0, N % 64 == 0,
+ * 16-byte aligned rows); f32 or AIMB_IMPL_SIMT runs the SIMT kernel. */
+int aimb_gemm_nt(const void* A, int64_t lda, const void* W, int64_t ldw, const aimb_epilogue_t* epi, int64_t M,
+                 int32_t N, int32_t K, int32_t dtype, int32_t impl, void* stream);
+/* Fully strided SIMT GEMM: C[m,n] = epilogue(sum_k A[m*a_sm + k*a_sk] * B[n*b_sn + k*b_sk]). */
+int aimb_gemm_strided(const void* A, int64_t a_sm, int64_t a_sk, const void* B, int64_t b_sn, int64_t b_sk,
+                      const aimb_epilogue_t* epi, int64_t M, int32_t N, int32_t K, int32_t dtype, void* stream);
+/* Adapter weight gradient (autograd of vit_clip.py:62,64): dW[N,K] (fp32) (+)= alpha * dY[R,N]^T * X[R,K]. */
+int aimb_gemm_wgrad(const void* dY, int64_t ldy, const void* X, int64_t ldx, float* dW, int64_t R, int32_t N,
+                    int32_t K, float alpha, int32_t accumulate, int32_t dtype, int32_t impl, void* stream);
+/* Bias gradient: out[c] (+)= alpha * sum_r x[r, c] * (row_scale ? row_scale[r % row_mod] : 1)  (fp32 out). */
+int aimb_colsum(const void* x, int64_t ld, const float* row_scale, int32_t row_mod, float alpha, float* out,
+                int64_t R, int32_t C, int32_t accumulate, int32_t dtype, void* stream);
+int aimb_transpose(const void* in, void* out, int32_t R, int32_t C, int32_t dtype, void* stream);
+
+/* ---- attention cores: vit_clip.py:140-156 (the part between the QKV and out_proj GEMMs) ------ */
+/* Spatial: one softmax(q k^T / 8) v problem per (frame, head); n tokens, head_dim 64.
+ * qkv [frames*n, 3D], o [frames*n, D], lse fp32 [frames, heads, n] (may be NULL in inference). */
+int aimb_attn_spatial_fwd(const void* qkv, void* o, float* lse, int32_t frames, int32_t n, int32_t heads,
+                          int32_t dtype, int32_t impl, void* stream);
+int aimb_attn_spatial_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* d_qkv,
+                          int32_t frames, int32_t n, int32_t heads, int32_t dtype, int32_t impl, void* stream);
+/* Temporal (T-Adapter attention, vitclip_aim.py:200-206): one problem per (clip b, token, head) over the
+ * T frames; rows of the sequence are (b*T + t)*n + token, i.e. the `n (b t) d -> t (b n) d` view is read
+ * in place through the row stride n*3D — no transpose kernel. */
+int aimb_attn_temporal_fwd(const void* qkv, void* o, int32_t B, int32_t T, int32_t n, int32_t heads, int32_t dtype,
+                           void* stream);
+int aimb_attn_temporal_bwd(const void* qkv, const void* d_o, void* d_qkv, int32_t B, int32_t T, int32_t n,
+                           int32_t heads, int32_t dtype, void* stream);
+
+/* ---- fork block extras (vit_clip.py:147-151, 182-186, 264-275) ------------------------------ */
+/* w_o[f] = sum_{i,j} exp(sum_h q_{f,h,i}.k_{f,h,j} / 8)  and  w_c[f] = sum_i exp(q_{f,i}.kc_f / 8)
+ * (full-width D dot products; fp32, no max subtraction, as the reference).  kc [frames, D]. */
+int aimb_fork_weights(const void* qkv, const void* kc, float* w_o, float* w_c, int32_t frames, int32_t n,
+                      int32_t D, int32_t dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AIMB200_H */

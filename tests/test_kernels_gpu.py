@@ -1,0 +1,309 @@
+"""Per-kernel numerics on a real B200: every C-ABI entry point against a plain torch fp32 reference
+of the same op (fp64 where cheap).  fp32 kernels: tight tolerance; bf16 kernels: compared with the
+reference evaluated on the *same bf16-rounded inputs*, tolerance = a few bf16 ulps of the output scale."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DT = {"f32": torch.float32, "bf16": torch.bfloat16}
+
+
+def _lib():
+    from aimb200 import lib
+    lib.load()
+    return lib
+
+
+def _err(a, ref):
+    return float((a.double() - ref.double()).abs().max() / ref.double().abs().max().clamp_min(1e-30))
+
+
+def _tol(dt):
+    return 2e-5 if dt == "f32" else 1.5e-2
+
+
+@pytest.mark.parametrize("dt", ["f32", "bf16"])
+@pytest.mark.parametrize("rows,D", [(1576, 768), (257, 1024), (5, 128)])
+def test_layernorm_fwd_bwd(dt, rows, D):
+    lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = (torch.randn(rows, D, device="cuda", generator=g) * 2 + 0.5).to(DT[dt])
+    w = (1 + 0.1 * torch.randn(D, device="cuda", generator=g)).to(DT[dt])
+    b = (0.1 * torch.randn(D, device="cuda", generator=g)).to(DT[dt])
+    y = torch.empty_like(x)
+    mean = torch.empty(rows, device="cuda")
+    rstd = torch.empty(rows, device="cuda")
+    lib.layernorm_fwd(x, w, b, y, mean, rstd)
+    xr = x.double().requires_grad_(True)
+    ref = F.layer_norm(xr, (D,), w.double(), b.double(), 1e-5)
+    assert _err(y, ref.detach()) < _tol(dt)
+    assert _err(mean, x.double().mean(-1)) < 1e-5
+    dy = torch.randn(rows, D, device="cuda", generator=g).to(DT[dt])
+    dres = torch.randn(rows, D, device="cuda", generator=g).to(DT[dt])
+    dx = torch.empty_like(x)
+    lib.layernorm_bwd(dy, x, mean, rstd, w, dres, dx)
+    ref.backward(dy.double())
+    assert _err(dx, xr.grad + dres.double()) < _tol(dt)
+    lib.layernorm_bwd(dy, x, mean, rstd, w, None, dx)
+    assert _err(dx, xr.grad) < _tol(dt)
+
+
+EPI_CASES = ["plain", "bias", "bias_qgelu_pre", "bias_gelu_rowscale", "res2", "dact", "bias_rowscaled_alpha"]
+
+
+def _gemm_case(lib, dt, M, N, K, case, impl, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    T = DT[dt]
+    a = torch.randn(M, K, device="cuda", generator=g).to(T)
+    w = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).to(T)
+    bias = torch.randn(N, device="cuda", generator=g).to(T)
+    r1 = torch.randn(M, N, device="cuda", generator=g).to(T)
+    r2 = torch.randn(M, N, device="cuda", generator=g).to(T)
+    pre = torch.randn(M, N, device="cuda", generator=g).to(T)
+    rs = (torch.rand(7, device="cuda", generator=g) > 0.3).float() / 0.7
+    out = torch.empty(M, N, device="cuda", dtype=T)
+    acc = a.double() @ w.double().T
+    rsm = rs.double()[torch.arange(M, device="cuda") % 7][:, None]
+    qg = lambda u: u * torch.sigmoid(1.702 * u)
+    kw, ref, extra = {}, None, None
+    if case == "plain":
+        ref = acc
+    elif case == "bias":
+        kw = dict(bias=bias)
+        ref = acc + bias.double()
+    elif case == "bias_qgelu_pre":
+        op = torch.empty_like(out)
+        kw = dict(bias=bias, act=lib.ACT_QUICKGELU, out_pre=op)
+        h = acc + bias.double()
+        ref = qg(h.to(T).double()) if dt == "bf16" else qg(h)
+        extra = (op, h)
+    elif case == "bias_gelu_rowscale":
+        kw = dict(bias=bias, act=lib.ACT_GELU, row_scale=rs, alpha=0.5, res1=r1)
+        ref = F.gelu(acc + bias.double()) * 0.5 * rsm + r1.double()
+    elif case == "res2":
+        kw = dict(bias=bias, res1=r1, res2=r2)
+        ref = acc + bias.double() + r1.double() + r2.double()
+    elif case == "dact":
+        kw = dict(dact_src=pre, dact=lib.ACT_GELU, row_scale=rs, alpha=0.5)
+        u = pre.double().requires_grad_(True)
+        F.gelu(u).sum().backward()
+        ref = acc * u.grad * 0.5 * rsm
+    elif case == "bias_rowscaled_alpha":
+        kw = dict(bias=bias, row_scale=rs, bias_rowscaled=True, alpha=0.5, res1=r1)
+        ref = (acc + bias.double() * rsm) * 0.5 + r1.double()
+    lib.gemm_nt(a, w, out, impl=impl, **kw)
+    torch.cuda.synchronize()
+    e = _err(out, ref)
+    if extra is not None:
+        e = max(e, _err(extra[0], extra[1]))
+    return e
+
+
+@pytest.mark.parametrize("case", EPI_CASES)
+def test_gemm_simt_f32(case):
+    lib = _lib()
+    assert _gemm_case(lib, "f32", 333, 200, 136, case, lib.IMPL_SIMT) < 2e-5
+
+
+@pytest.mark.parametrize("case", EPI_CASES)
+def test_gemm_simt_bf16(case):
+    lib = _lib()
+    assert _gemm_case(lib, "bf16", 333, 192, 128, case, lib.IMPL_SIMT) < 1.5e-2
+
+
+@pytest.mark.parametrize("bn", [64, 128, 192, 256])
+@pytest.mark.parametrize("M,N,K", [(128, 768, 64), (1576, 768, 768), (300, 768, 3072), (12608, 2304, 768)])
+def test_gemm_tc_shapes(bn, M, N, K):
+    """tcgen05 kernel, every N-tile instantiation, ragged M (TMA zero fill + masked rows), deep K."""
+    lib = _lib()
+    if N % bn:
+        pytest.skip("N not divisible")
+    lib.load().aimb_debug_force_bn(bn)
+    try:
+        assert _gemm_case(lib, "bf16", M, N, K, "bias", lib.IMPL_AUTO, seed=bn) < 1e-2
+    finally:
+        lib.load().aimb_debug_force_bn(0)
+
+
+@pytest.mark.parametrize("case", EPI_CASES)
+def test_gemm_tc_epilogues(case):
+    lib = _lib()
+    assert _gemm_case(lib, "bf16", 1000, 768, 192, case, lib.IMPL_AUTO) < 1.5e-2
+
+
+@pytest.mark.parametrize("N,K", [(192, 768), (768, 192), (3072, 768), (768, 3072), (2304, 768), (256, 1024), (4096, 1024)])
+def test_gemm_tc_model_shapes(N, K):
+    lib = _lib()
+    assert _gemm_case(lib, "bf16", 1576, N, K, "bias", lib.IMPL_AUTO) < 1e-2
+
+
+def test_gemm_tc_matches_simt_bitwise_inputs():
+    """Same bf16 inputs through both kernels: the two fp32-accumulating paths must agree to ~1 bf16 ulp."""
+    lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randn(777, 768, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(768, 768, device="cuda", generator=g) / 28).bfloat16()
+    o1 = torch.empty(777, 768, device="cuda", dtype=torch.bfloat16)
+    o2 = torch.empty_like(o1)
+    lib.gemm_nt(a, w, o1, impl=lib.IMPL_AUTO)
+    lib.gemm_nt(a, w, o2, impl=lib.IMPL_SIMT)
+    assert _err(o1, o2.double()) < 8e-3
+
+
+@pytest.mark.parametrize("dt", ["f32", "bf16"])
+def test_wgrad_colsum_transpose(dt):
+    lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    T = DT[dt]
+    R, N, K = 1576, 192, 768
+    dy = torch.randn(R, N, device="cuda", generator=g).to(T)
+    x = torch.randn(R, K, device="cuda", generator=g).to(T)
+    dw = torch.zeros(N, K, device="cuda")
+    lib.gemm_wgrad(dy, x, dw, alpha=0.5)
+    ref = 0.5 * dy.double().T @ x.double()
+    assert _err(dw, ref) < 1e-4
+    lib.gemm_wgrad(dy, x, dw, alpha=0.5, accumulate=True)
+    assert _err(dw, 2 * ref) < 1e-4
+    rs = torch.rand(197, device="cuda", generator=g)
+    out = torch.zeros(N, device="cuda")
+    lib.colsum(dy, out, row_scale=rs, alpha=2.0)
+    refc = 2.0 * (dy.double() * rs.double()[torch.arange(R, device="cuda") % 197][:, None]).sum(0)
+    assert _err(out, refc) < 1e-4
+    tr = torch.empty(K, R, device="cuda", dtype=T)
+    lib.transpose(x, tr)
+    assert torch.equal(tr, x.T.contiguous())
+
+
+def _attn_ref(qkv, S, L, heads):
+    """qkv [S*L, 3D] (sequence-major) -> o [S*L, D], lse [S, heads, L]"""
+    D = qkv.shape[1] // 3
+    q, k, v = [t.reshape(S, L, heads, 64).transpose(1, 2) for t in qkv.double().split(D, dim=1)]
+    aff = q @ k.transpose(-1, -2) / 8.0
+    o = torch.softmax(aff, -1) @ v
+    return o.transpose(1, 2).reshape(S * L, D), torch.logsumexp(aff, -1)
+
+
+@pytest.mark.parametrize("dt,impl", [("f32", "simt"), ("bf16", "simt"), ("bf16", "auto")])
+@pytest.mark.parametrize("frames,n,heads", [(3, 197, 2), (2, 257, 1), (2, 17, 2), (1, 33, 1)])
+def test_attn_spatial_fwd_bwd(dt, impl, frames, n, heads):
+    lib = _lib()
+    T = DT[dt]
+    imp = lib.IMPL_SIMT if impl == "simt" else lib.IMPL_AUTO
+    D = heads * 64
+    g = torch.Generator(device="cuda").manual_seed(n)
+    qkv = torch.randn(frames * n, 3 * D, device="cuda", generator=g).to(T)
+    o = torch.empty(frames * n, D, device="cuda", dtype=T)
+    lse = torch.empty(frames, heads, n, device="cuda")
+    lib.attn_spatial_fwd(qkv, o, lse, frames, n, heads, impl=imp)
+    qr = qkv.double().requires_grad_(True)
+    oref, lref = _attn_ref(qr, frames, n, heads)
+    assert _err(o, oref.detach()) < _tol(dt)
+    assert _err(lse, lref.detach()) < 1e-4
+    do = torch.randn(frames * n, D, device="cuda", generator=g).to(T)
+    dqkv = torch.full_like(qkv, float("nan"))
+    lib.attn_spatial_bwd(qkv, o, do, lse, dqkv, frames, n, heads, impl=imp)
+    oref.backward(do.double())
+    assert _err(dqkv, qr.grad) < (2e-5 if dt == "f32" else 2.5e-2)
+
+
+@pytest.mark.parametrize("dt", ["f32", "bf16"])
+@pytest.mark.parametrize("B,T,n,heads", [(2, 8, 197, 2), (1, 16, 17, 1), (1, 32, 5, 2), (2, 4, 17, 2)])
+def test_attn_temporal_fwd_bwd(dt, B, T, n, heads):
+    lib = _lib()
+    Tt = DT[dt]
+    D = heads * 64
+    g = torch.Generator(device="cuda").manual_seed(T)
+    qkv = torch.randn(B * T * n, 3 * D, device="cuda", generator=g).to(Tt)
+    o = torch.empty(B * T * n, D, device="cuda", dtype=Tt)
+    lib.attn_temporal_fwd(qkv, o, B, T, n, heads)
+    qr = qkv.double().requires_grad_(True)
+    # rows (b, t, tok) -> sequences (b, tok) over t
+    seq = qr.reshape(B, T, n, 3 * D).permute(0, 2, 1, 3).reshape(B * n * T, 3 * D)
+    oref, _ = _attn_ref(seq, B * n, T, heads)
+    oref = oref.reshape(B, n, T, D).permute(0, 2, 1, 3).reshape(B * T * n, D)
+    assert _err(o, oref.detach()) < _tol(dt)
+    do = torch.randn(B * T * n, D, device="cuda", generator=g).to(Tt)
+    dqkv = torch.full_like(qkv, float("nan"))
+    lib.attn_temporal_bwd(qkv, do, dqkv, B, T, n, heads)
+    oref.backward(do.double())
+    assert _err(dqkv, qr.grad) < (2e-5 if dt == "f32" else 2e-2)
+
+
+@pytest.mark.parametrize("dt", ["f32", "bf16"])
+@pytest.mark.parametrize("patch,res,D", [(16, 64, 128), (14, 56, 128), (16, 224, 768)])
+def test_stem_and_tail(dt, patch, res, D):
+    lib = _lib()
+    T = DT[dt]
+    B, Tn = 2, 4
+    G = res // patch
+    n = G * G + 1
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(B, 3, Tn, res, res, device="cuda", generator=g)
+    K = 3 * patch * patch
+    kpad = (K + 63) // 64 * 64
+    cols = torch.full((B * Tn * G * G, kpad), float("nan"), device="cuda", dtype=T)
+    lib.im2col(x, cols, patch)
+    ref = x.permute(0, 2, 1, 3, 4).reshape(B * Tn, 3, G, patch, G, patch).permute(0, 2, 4, 1, 3, 5).reshape(-1, K)
+    assert torch.equal(cols[:, :K], ref.to(T))          # bit-exact patch / token indexing
+    assert torch.all(cols[:, K:] == 0)
+    xu8 = torch.randint(0, 256, (B, 3, Tn, res, res), device="cuda", dtype=torch.uint8, generator=g)
+    mean = torch.tensor([122.769, 116.74, 104.04], device="cuda")
+    std = torch.tensor([68.493, 66.63, 70.321], device="cuda")
+    lib.im2col(xu8, cols, patch, mean, std)
+    xn = (xu8.float() - mean.view(1, 3, 1, 1, 1)) / std.view(1, 3, 1, 1, 1)
+    refn = xn.permute(0, 2, 1, 3, 4).reshape(B * Tn, 3, G, patch, G, patch).permute(0, 2, 4, 1, 3, 5).reshape(-1, K)
+    assert _err(cols[:, :K], refn) < (1e-6 if dt == "f32" else 5e-3)
+    # assemble + ln_pre
+    tok = torch.randn(B * Tn * G * G, D, device="cuda", generator=g).to(T)
+    cls = torch.randn(D, device="cuda", generator=g).to(T)
+    pos = torch.randn(n, D, device="cuda", generator=g).to(T)
+    temb = torch.randn(Tn, D, device="cuda", generator=g).to(T)
+    w = (1 + 0.1 * torch.randn(D, device="cuda", generator=g)).to(T)
+    b = (0.1 * torch.randn(D, device="cuda", generator=g)).to(T)
+    z = torch.empty(B * Tn * n, D, device="cuda", dtype=T)
+    xo = torch.empty_like(z)
+    mean_o = torch.empty(B * Tn * n, device="cuda")
+    rstd_o = torch.empty_like(mean_o)
+    lib.stem_assemble_ln(tok, cls, pos, temb, w, b, z, xo, mean_o, rstd_o, B, Tn, n)
+    zr = torch.cat([cls.double().view(1, 1, D).expand(B * Tn, 1, D), tok.double().reshape(B * Tn, G * G, D)], 1)
+    zr = zr + pos.double().view(1, n, D)
+    zr = (zr.reshape(B, Tn, n, D) + temb.double().view(1, Tn, 1, D)).reshape(B * Tn * n, D)
+    assert _err(z, zr) < (1e-6 if dt == "f32" else 1e-2)
+    assert _err(xo, F.layer_norm(z.double(), (D,), w.double(), b.double())) < _tol(dt)
+    # tail fwd/bwd
+    feat = torch.empty(B, D, Tn, device="cuda")
+    tm = torch.empty(B * Tn, device="cuda")
+    tr = torch.empty(B * Tn, device="cuda")
+    lib.tail_fwd(xo, w, b, feat, tm, tr, B, Tn, n)
+    xr = xo.double().requires_grad_(True)
+    wr = w.double().requires_grad_(True)
+    br = b.double().requires_grad_(True)
+    fr = F.layer_norm(xr.reshape(B * Tn, n, D)[:, 0], (D,), wr, br).reshape(B, Tn, D).permute(0, 2, 1)
+    assert _err(feat, fr.detach()) < (2e-5 if dt == "f32" else 1e-5 + 0)  # fp32 output of fp32 math on T inputs
+    df = torch.randn(B, D, Tn, device="cuda", generator=g)
+    dx = torch.full_like(xo, float("nan"))
+    dg = torch.empty(D, device="cuda")
+    db = torch.empty(D, device="cuda")
+    lib.tail_bwd(df, xo, tm, tr, w, dx, dg, db, B, Tn, n)
+    fr.backward(df.double())
+    assert _err(dx, xr.grad) < _tol(dt)
+    assert _err(dg, wr.grad) < 1e-4 and _err(db, br.grad) < 1e-4
+    # temporal-embedding gradient reduction
+    dz = torch.randn(B * Tn * n, D, device="cuda", generator=g).to(T)
+    out = torch.empty(Tn, D, device="cuda")
+    lib.temb_grad(dz, out, B, Tn, n)
+    assert _err(out, dz.double().reshape(B, Tn, n, D).sum((0, 2))) < 1e-4
+
+
+def test_errors_are_reported_not_thrown():
+    lib = _lib()
+    x = torch.zeros(4, 100, device="cuda")  # D=100 not a multiple of 4? it is; use 102
+    x = torch.zeros(4, 102, device="cuda")
+    with pytest.raises(lib.AimbError):
+        lib.layernorm_fwd(x, x[0], x[0], torch.empty_like(x))
+    with pytest.raises(lib.AimbError):
+        lib.layernorm_fwd(torch.zeros(4, 128), torch.zeros(128), torch.zeros(128), torch.zeros(4, 128))  # CPU tensors
