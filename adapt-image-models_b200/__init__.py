@@ -6,3 +6,8 @@ The directory is named ``adapt-image-models_b200`` (not importable as such); imp
 from . import lib  # noqa: F401
 
 __all__ = ["lib"]
+from .registry import BACKBONES, build_backbone  # noqa: E402,F401
+from .backbone import ViT_CLIP  # noqa: E402,F401
+from .parallel import GradSync  # noqa: E402,F401
+
+__all__ += ["BACKBONES", "build_backbone", "ViT_CLIP", "GradSync"]

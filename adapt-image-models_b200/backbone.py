@@ -1,0 +1,408 @@
+"""``ViT_CLIP`` — drop-in replacement of ``mmaction/models/backbones/vit_clip.py::ViT_CLIP``.
+
+Same registry name, constructor arguments (superset of vit_clip.py:330-331 and vitclip_aim.py:343,
+so every ``configs/recognition/vit/vitclip_*.py`` constructs), ``init_weights()``, ``forward(x[B,3,T,H,W])
+-> [B, width, T, 1, 1]`` and ``state_dict`` key/shape layout (CLIP ``visual.*`` dicts and AIM
+checkpoints load unchanged).  What differs is *how* forward/backward run: as a fixed sequence of
+hand-written sm_100a kernels (``engine.py``) with an adapter-only backward; autograd sees one node.
+
+No CPU / eager fallback: calling ``forward`` with a CPU tensor or without the built library raises.
+"""
+from __future__ import annotations
+
+import math
+import os
+from collections import OrderedDict
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import lib
+from .engine import Dims, Engine
+from .registry import BACKBONES
+
+
+class LayerNorm(nn.LayerNorm):
+    """Parameter container; statistics are always fp32 in the kernels (vit_clip.py:71-77)."""
+
+
+class QuickGELU(nn.Module):
+    def forward(self, x):  # only used if someone calls the sub-module directly; the engine fuses it
+        return x * torch.sigmoid(1.702 * x)
+
+
+class Adapter(nn.Module):
+    """vit_clip.py:51-69 — D_fc1 (D->r), exact GELU, D_fc2 (r->D), optional skip."""
+
+    def __init__(self, D_features, mlp_ratio=0.25, skip_connect=True):
+        super().__init__()
+        self.skip_connect = skip_connect
+        hidden = int(D_features * mlp_ratio)
+        self.act = nn.GELU()
+        self.D_fc1 = nn.Linear(D_features, hidden)
+        self.D_fc2 = nn.Linear(hidden, D_features)
+
+
+class ResidualAttentionBlock(nn.Module):
+    """Parameter tree of vit_clip.py:85-113 / vitclip_aim.py:111-135 (the math lives in engine.py)."""
+
+    def __init__(self, d_model, n_head, scale=1.0, num_tadapter=1, num_frames=8, drop_path=0.0, block="aim"):
+        super().__init__()
+        self.attn = nn.MultiheadAttention(d_model, n_head)          # parameter container only, as in the reference
+        self.ln_1 = LayerNorm(d_model)
+        self.mlp = nn.Sequential(OrderedDict([("c_fc", nn.Linear(d_model, d_model * 4)), ("gelu", QuickGELU()),
+                                              ("c_proj", nn.Linear(d_model * 4, d_model))]))
+        self.ln_2 = LayerNorm(d_model)
+        self.n_head, self.d_model, self.scale, self.num_frames = n_head, d_model, scale, num_frames
+        self.num_tadapter = num_tadapter
+        self.MLP_Adapter = Adapter(d_model, skip_connect=False)
+        self.S_Adapter = Adapter(d_model, skip_connect=(block == "aim"))   # aim: skip (vitclip_aim.py:130); fork: none
+        self.T_Adapter = Adapter(d_model, skip_connect=False)
+        if num_tadapter == 2:
+            self.T_Adapter_in = Adapter(d_model)
+        self.drop_path_rate = float(drop_path)
+
+
+class Transformer(nn.Module):
+    def __init__(self, num_frames, width, layers, heads, num_tadapter=1, scale=1.0, drop_path=0.1, block="aim"):
+        super().__init__()
+        self.width, self.layers = width, layers
+        dpr = [x.item() for x in torch.linspace(0, drop_path, layers)]      # vit_clip.py:297
+        self.resblocks = nn.Sequential(*[ResidualAttentionBlock(width, heads, scale, num_tadapter, num_frames, dpr[i],
+                                                                block) for i in range(layers)])
+
+
+def _is_trainable_name(name: str) -> bool:
+    """Freeze rule of vit_clip.py:413-415 (``cls_head`` lives outside the backbone)."""
+    return ("temporal_embedding" in name) or ("ln_post" in name) or ("Adapter" in name)
+
+
+class _BackboneFn(torch.autograd.Function):
+    """One autograd node for the whole backbone; backward = Engine.backward (adapter-only grads)."""
+
+    @staticmethod
+    def forward(ctx, mod, x, *params):
+        ctx.mod = mod
+        return mod._run_forward(x, training=True)
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        mod = ctx.mod
+        grads = mod._run_backward(dfeat)
+        return (None, None) + tuple(grads)
+
+
+@BACKBONES.register_module()
+class ViT_CLIP(nn.Module):
+    def __init__(self, input_resolution: int, num_frames: int, patch_size: int, width: int, layers: int, heads: int,
+                 drop_path_rate, num_tadapter=1, adapter_scale=0.5, pretrained=None, shift=False, checkpoint=False,
+                 block: Optional[str] = None, compute_dtype: Optional[str] = None):
+        super().__init__()
+        block = os.environ.get("AIMB200_BLOCK", block or "aim")
+        if block not in ("aim", "fork"):
+            raise ValueError("block must be 'aim' (upstream AIM math, vitclip_aim.py:196-211) or 'fork' (vit_clip.py:199-288)")
+        if block == "fork":
+            raise NotImplementedError("block='fork' (vit_clip.py:199-288) is not built yet; see DESIGN.md")
+        if shift:
+            raise NotImplementedError("shift=True (PatchShift, vit_clip.py:15-49,233-254) is outside the built path")
+        if width % heads or width // heads != 64:
+            raise ValueError("head_dim must be 64 (CLIP ViT-B/16, ViT-L/14)")
+        if num_tadapter not in (1, 2):
+            raise ValueError("num_tadapter must be 1 or 2")
+        compute_dtype = os.environ.get("AIMB200_DTYPE", compute_dtype or "bf16")
+        if compute_dtype not in ("bf16", "fp32"):
+            raise ValueError("compute_dtype must be 'bf16' or 'fp32'")
+        self.block = block
+        self.compute_dtype = torch.bfloat16 if compute_dtype == "bf16" else torch.float32
+        self.input_resolution, self.patch_size, self.num_frames = input_resolution, patch_size, num_frames
+        self.width, self.layers, self.heads = width, layers, heads
+        self.num_tadapter, self.adapter_scale = num_tadapter, float(adapter_scale)
+        self.drop_path_rate = float(drop_path_rate)
+        self.pretrained = pretrained
+        self.checkpoint = checkpoint   # accepted for config compatibility; activations are kept (fits 180 GB)
+        self.conv1 = nn.Conv2d(3, width, kernel_size=patch_size, stride=patch_size, bias=False)
+        scale = width ** -0.5
+        self.class_embedding = nn.Parameter(scale * torch.randn(width))
+        self.positional_embedding = nn.Parameter(scale * torch.randn((input_resolution // patch_size) ** 2 + 1, width))
+        self.ln_pre = LayerNorm(width)
+        self.temporal_embedding = nn.Parameter(torch.zeros(1, num_frames, width))
+        self.transformer = Transformer(num_frames, width, layers, heads, num_tadapter=num_tadapter, scale=adapter_scale,
+                                       drop_path=drop_path_rate, block=block)
+        self.ln_post = LayerNorm(width)
+        # runtime state (not parameters)
+        self._engine: Optional[Engine] = None
+        self._frozen_cache: Dict[str, tuple] = {}
+        self._train_names: Optional[List[str]] = None
+        self._flat: Optional[torch.Tensor] = None
+        self._flat_ptrs = None
+        self._grad_sync = None
+        self._input_norm = None
+        self._step_ctx = None
+
+    # ------------------------------------------------------------------ reference API
+    def init_weights(self, pretrained=None):
+        """vit_clip.py:352-423: trunc-normal(.02) linears, LN 1/0, optional CLIP load, zero D_fc2, freeze."""
+        def _init(m):
+            if isinstance(m, nn.Linear):
+                nn.init.trunc_normal_(m.weight, std=.02)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+            elif isinstance(m, nn.LayerNorm):
+                nn.init.constant_(m.bias, 0)
+                nn.init.constant_(m.weight, 1.0)
+
+        if pretrained:
+            self.pretrained = pretrained
+        if isinstance(self.pretrained, str):
+            self.apply(_init)
+            self.load_state_dict(self._load_pretrained(self.pretrained), strict=False)
+        elif self.pretrained is None:
+            self.apply(_init)
+        else:
+            raise TypeError('pretrained must be a str or None')
+        for n, m in self.transformer.named_modules():
+            if 'Adapter' in n and n.endswith('D_fc2') and isinstance(m, nn.Linear):
+                nn.init.constant_(m.weight, 0)
+                nn.init.constant_(m.bias, 0)
+        for name, param in self.named_parameters():
+            param.requires_grad = _is_trainable_name(name)
+        self.invalidate_cache()
+
+    def _load_pretrained(self, spec: str):
+        if os.path.isfile(spec):
+            sd = torch.load(spec, map_location="cpu")
+            sd = sd.get("state_dict", sd)
+            sd = {k[len("backbone."):] if k.startswith("backbone.") else k: v for k, v in sd.items()}
+            sd.pop("proj", None)
+            return sd
+        try:  # the reference path: OpenAI CLIP (vit_clip.py:369-376)
+            import clip  # type: ignore
+        except ImportError as e:
+            raise RuntimeError(f"pretrained={spec!r} needs the OpenAI `clip` package and weights (not available "
+                               "offline); pass a path to a state_dict file instead") from e
+        model, _ = clip.load("ViT-B/16" if self.layers == 12 else "ViT-L/14", device="cpu")
+        sd = model.visual.state_dict()
+        sd.pop("proj", None)
+        return sd
+
+    @torch.jit.ignore
+    def no_weight_decay(self):
+        return {'absolute_pos_embed', 'temporal_embedding'}
+
+    @torch.jit.ignore
+    def no_weight_decay_keywords(self):
+        return {'relative_position_bias_table', 'temporal_position_bias_table'}
+
+    # ------------------------------------------------------------------ extras either side of the path
+    def set_input_normalization(self, mean, std):
+        """Fuse GPUNormalize (mmaction/utils/module_hooks.py:35-87) into the patch load: uint8 clips in."""
+        self._input_norm = (torch.tensor(mean, dtype=torch.float32), torch.tensor(std, dtype=torch.float32))
+
+    def attach_grad_sync(self, sync):
+        """sync: object with ``bucket_done(flat_grad, lo, hi)`` and ``finish()`` (see parallel.GradSync)."""
+        self._grad_sync = sync
+
+    def invalidate_cache(self):
+        self._frozen_cache.clear()
+        self._flat = None
+        self._flat_ptrs = None
+
+    def train(self, mode: bool = True):
+        return super().train(mode)
+
+    def _apply(self, fn, *a, **k):      # .to()/.cuda()/.half() replace parameter storage
+        self.invalidate_cache()
+        if self._engine is not None:
+            self._engine.release()
+            self._engine = None
+        return super()._apply(fn, *a, **k)
+
+    # ------------------------------------------------------------------ weights in compute dtype
+    def _dims(self, B: int) -> Dims:
+        p, res = self.patch_size, self.input_resolution
+        K = 3 * p * p
+        return Dims(B=B, T=self.num_frames, n=(res // p) ** 2 + 1, D=self.width, heads=self.heads, L=self.layers,
+                    r=int(self.width * 0.25), patch=p, res=res, kpad=(K + 63) // 64 * 64, num_tadapter=self.num_tadapter,
+                    scale=self.adapter_scale)
+
+    def trainable_names(self) -> List[str]:
+        """Flat-buffer order: temporal_embedding, block 0 .. L-1 adapters, ln_post — so that the gradient
+        slices completed by backward (ln_post, block L-1, ..., block 0, temporal_embedding) are contiguous."""
+        if self._train_names is None:
+            names = ["temporal_embedding"]
+            ads = ["T_Adapter", "S_Adapter", "MLP_Adapter"] + (["T_Adapter_in"] if self.num_tadapter == 2 else [])
+            for i in range(self.layers):
+                for a in ads:
+                    for leaf in ("D_fc1.weight", "D_fc1.bias", "D_fc2.weight", "D_fc2.bias"):
+                        names.append(f"transformer.resblocks.{i}.{a}.{leaf}")
+            names += ["ln_post.weight", "ln_post.bias"]
+            self._train_names = names
+        return self._train_names
+
+    def _flatten_trainable(self, params: Dict[str, nn.Parameter]):
+        """Make the trainable fp32 masters views of one flat buffer (one cast per step, bucketable grads)."""
+        names = self.trainable_names()
+        ptrs = tuple(params[n].data_ptr() for n in names)
+        if self._flat is not None and ptrs == self._flat_ptrs:
+            return
+        total = sum(params[n].numel() for n in names)
+        dev = params[names[0]].device
+        flat = torch.empty(total, dtype=torch.float32, device=dev)
+        offs, o = {}, 0
+        for n in names:
+            p = params[n]
+            if p.dtype != torch.float32:
+                raise lib.AimbError("trainable parameters must be fp32 masters (compute dtype is chosen by compute_dtype)")
+            k = p.numel()
+            flat[o:o + k].copy_(p.data.reshape(-1).float())
+            p.data = flat[o:o + k].view(p.shape)
+            offs[n] = (o, k)
+            o += k
+        self._flat, self._offsets = flat, offs
+        self._flat_ptrs = tuple(params[n].data_ptr() for n in names)
+        # gradient bucket boundaries (in elements): [temb | block 0 .. L-1 | ln_post]
+        self._block_lo = [offs[f"transformer.resblocks.{i}.T_Adapter.D_fc1.weight"][0] for i in range(self.layers)]
+
+    def _weights(self, training: bool):
+        """Return (W, WT): every weight in the compute dtype; WT = transposes for the dgrad GEMMs."""
+        cd = self.compute_dtype
+        params = dict(self.named_parameters())
+        self._flatten_trainable(params)
+        W: Dict[str, torch.Tensor] = {}
+        WT: Dict[str, torch.Tensor] = {}
+        tset = set(self.trainable_names())
+        # ---- frozen: cached, refreshed when the source parameter changes (load_state_dict, .to())
+        for name, p in params.items():
+            if name in tset:
+                continue
+            ver = (p.data_ptr(), p._version, p.dtype, cd)
+            ent = self._frozen_cache.get(name)
+            if ent is None or ent[0] != ver:
+                src = p.detach()
+                if name == "conv1.weight":
+                    K = src[0].numel()
+                    kpad = (K + 63) // 64 * 64
+                    w2 = torch.zeros(src.shape[0], kpad, dtype=cd, device=src.device)
+                    w2[:, :K] = src.reshape(src.shape[0], K).to(cd)
+                    ent = (ver, w2, None)
+                elif name == "temporal_embedding":
+                    ent = (ver, src.to(cd).reshape(-1, src.shape[-1]).contiguous(), None)
+                else:
+                    w = src.to(cd).contiguous()
+                    wt = None
+                    if w.dim() == 2 and (name.endswith("in_proj_weight") or name.endswith("out_proj.weight")
+                                         or name.endswith("c_fc.weight") or name.endswith("c_proj.weight")):
+                        wt = w.t().contiguous()
+                    ent = (ver, w, wt)
+                self._frozen_cache[name] = ent
+            W[name] = ent[1]
+            if ent[2] is not None:
+                WT[name] = ent[2]
+        # ---- trainable: one cast of the flat master per step
+        flat_c = self._flat if cd == torch.float32 else self._flat.to(cd)
+        for name in self.trainable_names():
+            o, k = self._offsets[name]
+            shape = params[name].shape
+            t = flat_c[o:o + k].view(shape)
+            if name == "temporal_embedding":
+                t = t.reshape(-1, shape[-1])
+            W[name] = t
+        if training:
+            for name in self.trainable_names():
+                if name.endswith("D_fc1.weight") or name.endswith("D_fc2.weight"):
+                    w = W[name]
+                    wt = torch.empty(w.shape[1], w.shape[0], dtype=cd, device=w.device)
+                    lib.transpose(w, wt)
+                    WT[name] = wt
+        if self._input_norm is not None:
+            dev = self._flat.device
+            W["input_mean"], W["input_std"] = self._input_norm[0].to(dev), self._input_norm[1].to(dev)
+        return W, WT
+
+    # ------------------------------------------------------------------ forward / backward
+    def _drop_masks(self, d: Dims, device):
+        if not self.training or self.drop_path_rate <= 0.0:
+            return None
+        rates = torch.linspace(0, self.drop_path_rate, self.layers)
+        keep = (1.0 - rates).to(device).view(-1, 1, 1)
+        # timm DropPath on LND tensors: one Bernoulli draw per token index, shared by all frames;
+        # two independent draws per block (temporal branch, MLP-adapter branch)
+        m = (torch.rand(self.layers, 2, d.n, device=device) < keep).float() / keep
+        out = []
+        for i in range(self.layers):
+            if float(rates[i]) == 0.0:
+                out.append((None, None))
+            else:
+                out.append((m[i, 0].contiguous(), m[i, 1].contiguous()))
+        return out
+
+    def _run_forward(self, x: torch.Tensor, training: bool) -> torch.Tensor:
+        if self._engine is None or self._engine.dtype != self.compute_dtype or self._engine.device != x.device:
+            self._engine = Engine(self.compute_dtype, x.device)
+        d = self._dims(x.shape[0])
+        W, WT = self._weights(training)
+        masks = self._drop_masks(d, x.device) if training else None
+        if training:
+            self._step_ctx = (W, WT, d)
+        return self._engine.forward(x.contiguous(), W, d, training, masks)
+
+    def _run_backward(self, dfeat: torch.Tensor):
+        W, WT, d = self._step_ctx
+        names = self.trainable_names()
+        flat_grad = torch.empty_like(self._flat)
+        params = dict(self.named_parameters())
+        grads = {}
+        for n in names:
+            o, k = self._offsets[n]
+            g = flat_grad[o:o + k].view(params[n].shape)
+            grads[n] = g
+        sync = self._grad_sync
+        L = self.layers
+        total = flat_grad.numel()
+        done_hi = [total]
+
+        def on_done(i):
+            if sync is None:
+                return
+            # completed so far (from the top of the flat buffer): ln_post (i == L), blocks i..L-1, temb (i == -1)
+            lo = 0 if i == -1 else (self._block_lo[i] if i < L else self._offsets["ln_post.weight"][0])
+            if sync.want_bucket(i, L):
+                sync.bucket_done(flat_grad, lo, done_hi[0])
+                done_hi[0] = lo
+
+        self._engine.backward(dfeat.reshape(d.B, d.D, d.T).float(), W, WT, grads, on_done)
+        if sync is not None:
+            if done_hi[0] > 0:
+                sync.bucket_done(flat_grad, 0, done_hi[0])
+            sync.finish()
+        self._step_ctx = None
+        out = []
+        for p_name, p in self.named_parameters():
+            out.append(grads.get(p_name) if p.requires_grad else None)
+        return out
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x [B, 3, T, H, W] -> [B, width, T, 1, 1] (fp32), as vit_clip.py:433-458."""
+        if not x.is_cuda:
+            raise lib.AimbError("aimb200.ViT_CLIP runs on sm_100a only: move the module and the clip to a CUDA device "
+                                "(there is no CPU fallback)")
+        B, C, T, H, Wd = x.shape
+        if C != 3 or T != self.num_frames or H != self.input_resolution or Wd != self.input_resolution:
+            raise ValueError(f"expected [B,3,{self.num_frames},{self.input_resolution},{self.input_resolution}], got {tuple(x.shape)}")
+        if x.dtype == torch.uint8 and self._input_norm is None:
+            raise ValueError("uint8 clips need set_input_normalization(mean, std)")
+        if B == 0:
+            return torch.zeros(0, self.width, T, 1, 1, device=x.device, dtype=torch.float32)
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if need_grad:
+            params = list(self.parameters())
+            for name, p in self.named_parameters():
+                if p.requires_grad and not _is_trainable_name(name):
+                    raise lib.AimbError(
+                        f"parameter {name} requires grad, but the hand-written backward produces gradients only for "
+                        "the AIM trainable set (temporal_embedding, ln_post, *Adapter*); call init_weights() or freeze it")
+            feat = _BackboneFn.apply(self, x, *params)
+        else:
+            feat = self._run_forward(x, training=False)
+        return feat.view(B, self.width, T, 1, 1)

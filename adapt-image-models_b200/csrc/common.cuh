@@ -45,7 +45,7 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ---- activations (reference: QuickGELU vit_clip.py:80-82; nn.GELU exact erf vit_clip.py:56) ----
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float quick_gelu(float u) { return u * sigmoidf_(1.702f * u); }
 __device__ __forceinline__ float quick_gelu_grad(float u) {
     float s = sigmoidf_(1.702f * u);

@@ -122,9 +122,22 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t saddr) {
     d |= (uint64_t)2 << 61;                   // SWIZZLE_128B
     return d;
 }
+// MN-major operand (the contraction index is the slow one in memory), 128-byte swizzle: the tile is a
+// stack of [k rows][64 elements = 128 B] boxes; 8 k-rows form a 1024 B swizzle atom (SBO), and the next
+// 64 elements along M/N live `lbo_bytes` further (LBO).  (cute::UMMA::make_umma_desc<Major::MN>)
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 // Instruction descriptor: kind::f16, A=B=bf16, D=fp32, both operands K-major, M x N tile.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major = 0, int b_mn_major = 0) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 }  // namespace ptx

@@ -1,0 +1,276 @@
+"""Explicit forward / adapter-only backward of the AIM ViT_CLIP backbone on the aimb200 kernels.
+
+The engine owns no parameters.  ``forward`` takes the clip and a dict of weights already in the
+compute dtype, runs the stem, the L blocks and the tail as a fixed sequence of C-ABI calls and (in
+training) keeps exactly the tensors the hand-written backward needs.  ``backward`` walks the blocks
+in reverse: grad-input flows through every frozen GEMM (pre-transposed frozen weights, same tcgen05
+kernel), weight/bias grads are produced only for the adapters, ``ln_post`` and
+``temporal_embedding`` (freeze rule of vit_clip.py:413-415) and are written straight into a flat
+fp32 gradient buffer whose per-block slices can be all-reduced while earlier blocks are still in
+backward.
+
+Reference math: block 'aim' = vitclip_aim.py:196-211, stem = vit_clip.py:433-447, tail = :450-456.
+Rows of every activation are (b*T + t)*n + token (frame-major), so spatial attention reads
+contiguous row ranges and temporal attention reads rows at stride n in place.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional
+
+import torch
+
+from . import lib
+
+ADAPTERS_AIM = ("T_Adapter", "S_Adapter", "MLP_Adapter")
+
+
+@dataclass(frozen=True)
+class Dims:
+    B: int
+    T: int
+    n: int
+    D: int
+    heads: int
+    L: int
+    r: int
+    patch: int
+    res: int
+    kpad: int
+    num_tadapter: int
+    scale: float
+
+    @property
+    def BT(self):
+        return self.B * self.T
+
+    @property
+    def M(self):
+        return self.B * self.T * self.n
+
+    @property
+    def G(self):
+        return self.res // self.patch
+
+
+class Engine:
+    def __init__(self, dtype: torch.dtype, device: torch.device):
+        assert dtype in (torch.float32, torch.bfloat16)
+        self.dtype = dtype
+        self.device = device
+        self._bufs: Dict[tuple, torch.Tensor] = {}
+        self.saved: Optional[dict] = None
+        self.attn_impl = lib.IMPL_AUTO
+        self.gemm_impl = lib.IMPL_AUTO
+
+    # ------------------------------------------------------------------ buffers (stable pointers across steps)
+    def buf(self, name, shape, dtype=None, key=None):
+        dtype = dtype or self.dtype
+        k = (name, tuple(shape), dtype, key)
+        t = self._bufs.get(k)
+        if t is None:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self._bufs[k] = t
+        return t
+
+    def release(self):
+        self._bufs.clear()
+        self.saved = None
+
+    def gemm(self, a, w, out, **kw):
+        return lib.gemm_nt(a, w, out, impl=self.gemm_impl, **kw)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x: torch.Tensor, W: Dict[str, torch.Tensor], d: Dims, training: bool,
+                drop_masks: Optional[List] = None) -> torch.Tensor:
+        """x [B,3,T,H,W] (fp32 / bf16 / uint8) -> feat fp32 [B, D, T].  W: weights in compute dtype.
+        drop_masks[i] = (mask_t, mask_m): fp32 [n] DropPath multipliers (0 or 1/keep) or None."""
+        M, D, r, n, BT = d.M, d.D, d.r, d.n, d.BT
+        sv = {"d": d, "blocks": []} if training else None
+        key = "train" if training else "eval"
+        # ---- stem
+        cols = self.buf("cols", (BT * d.G * d.G, d.kpad))
+        lib.im2col(x, cols, d.patch, W.get("input_mean"), W.get("input_std"))
+        tok = self.buf("tok", (BT * d.G * d.G, D))
+        self.gemm(cols, W["conv1.weight"], tok)
+        z = self.buf("z", (M, D), key=key) if training else None
+        xcur = self.buf("x", (M, D), key=(key, 0))
+        mean0 = self.buf("ln_pre_mean", (M,), torch.float32, key)
+        rstd0 = self.buf("ln_pre_rstd", (M,), torch.float32, key)
+        lib.stem_assemble_ln(tok, W["class_embedding"], W["positional_embedding"], W["temporal_embedding"],
+                             W["ln_pre.weight"], W["ln_pre.bias"], z, xcur, mean0, rstd0, d.B, d.T, n)
+        if training:
+            sv["z"], sv["ln_pre"] = z, (mean0, rstd0)
+        for i in range(d.L):
+            masks = drop_masks[i] if (drop_masks is not None) else (None, None)
+            xcur = self._block_fwd(i, xcur, W, d, training, masks, sv)
+        # ---- tail
+        feat = torch.empty(d.B, D, d.T, device=self.device, dtype=torch.float32)
+        tm = self.buf("tail_mean", (BT,), torch.float32, key)
+        tr = self.buf("tail_rstd", (BT,), torch.float32, key)
+        lib.tail_fwd(xcur, W["ln_post.weight"], W["ln_post.bias"], feat, tm, tr, d.B, d.T, n)
+        if training:
+            sv["x_last"], sv["tail"] = xcur, (tm, tr)
+            self.saved = sv
+        return feat
+
+    def _adapter_fwd(self, name, pre, a, W, d, bk, training, rs, alpha, res1, res2, out):
+        """out = res1 + res2 + alpha * rs * (fc2(gelu(fc1(a))))   (rs folded into the hidden, see backward)."""
+        M, r = d.M, d.r
+        h = self.buf(name + "_h", (M, r), key=bk) if training else None
+        g = self.buf(name + "_g", (M, r), key=bk)
+        self.gemm(a, W[pre + name + ".D_fc1.weight"], g, bias=W[pre + name + ".D_fc1.bias"], act=lib.ACT_GELU,
+                  out_pre=h, row_scale=rs)
+        self.gemm(g, W[pre + name + ".D_fc2.weight"], out, bias=W[pre + name + ".D_fc2.bias"], row_scale=rs,
+                  bias_rowscaled=rs is not None, alpha=alpha, res1=res1, res2=res2)
+        return h, g
+
+    def _block_fwd(self, i, x, W, d, training, masks, sv):
+        M, D, r, n = d.M, d.D, d.r, d.n
+        pre = f"transformer.resblocks.{i}."
+        bk = ("train", i) if training else "eval"          # per-block buffers only when they must survive
+        mask_t, mask_m = masks
+        S = {} if training else None
+        f32 = torch.float32
+        Wqkv, bqkv = W[pre + "attn.in_proj_weight"], W[pre + "attn.in_proj_bias"]
+        Wo, bo = W[pre + "attn.out_proj.weight"], W[pre + "attn.out_proj.bias"]
+        ln1w, ln1b = W[pre + "ln_1.weight"], W[pre + "ln_1.bias"]
+        # ---------------- temporal adaptation (vitclip_aim.py:199-206)
+        xn = self.buf("xn", (M, D), key=bk if (training and d.num_tadapter == 2) else None)
+        m1, r1 = self.buf("ln1t_m", (M,), f32, bk), self.buf("ln1t_r", (M,), f32, bk)
+        lib.layernorm_fwd(x, ln1w, ln1b, xn, m1, r1)
+        qkv_in = xn
+        if d.num_tadapter == 2:
+            xin = self.buf("xn_in", (M, D), key=bk)
+            hi, gi = self._adapter_fwd("T_Adapter_in", pre, xn, W, d, bk, training, None, 1.0, xn, None, xin)
+            qkv_in = xin
+            if training:
+                S["tin"] = (xn, hi, gi)
+        qkv_t = self.buf("qkv_t", (M, 3 * D), key=bk)
+        self.gemm(qkv_in, Wqkv, qkv_t, bias=bqkv)
+        o_t = self.buf("o_t", (M, D), key=bk)
+        lib.attn_temporal_fwd(qkv_t, o_t, d.B, d.T, n, d.heads)
+        a_t = self.buf("a_t", (M, D), key=bk)
+        self.gemm(o_t, Wo, a_t, bias=bo)
+        x1 = self.buf("x1", (M, D), key=bk)
+        h_t, g_t = self._adapter_fwd("T_Adapter", pre, a_t, W, d, bk, training, mask_t, 1.0, x, None, x1)
+        # ---------------- spatial adaptation (:208)
+        xn_s = self.buf("xn", (M, D))
+        m2, r2 = self.buf("ln1s_m", (M,), f32, bk), self.buf("ln1s_r", (M,), f32, bk)
+        lib.layernorm_fwd(x1, ln1w, ln1b, xn_s, m2, r2)
+        qkv_s = self.buf("qkv_s", (M, 3 * D), key=bk)
+        self.gemm(xn_s, Wqkv, qkv_s, bias=bqkv)
+        o_s = self.buf("o_s", (M, D), key=bk)
+        lse = self.buf("lse_s", (d.BT, d.heads, n), f32, bk) if training else None
+        lib.attn_spatial_fwd(qkv_s, o_s, lse, d.BT, n, d.heads, impl=self.attn_impl)
+        a_s = self.buf("a_s", (M, D), key=bk)
+        self.gemm(o_s, Wo, a_s, bias=bo)
+        x2 = self.buf("x2", (M, D), key=bk)
+        h_s, g_s = self._adapter_fwd("S_Adapter", pre, a_s, W, d, bk, training, None, 1.0, x1, a_s, x2)
+        # ---------------- joint adaptation (:210-211)
+        xn2 = self.buf("xn2", (M, D), key=bk)
+        m3, r3 = self.buf("ln2_m", (M,), f32, bk), self.buf("ln2_r", (M,), f32, bk)
+        lib.layernorm_fwd(x2, W[pre + "ln_2.weight"], W[pre + "ln_2.bias"], xn2, m3, r3)
+        tmp = self.buf("tmp", (M, D))
+        h_m, g_m = self._adapter_fwd("MLP_Adapter", pre, xn2, W, d, bk, training, mask_m, d.scale, x2, None, tmp)
+        hf = self.buf("hf", (M, 4 * D), key=bk) if training else None
+        gf = self.buf("gf", (M, 4 * D))
+        self.gemm(xn2, W[pre + "mlp.c_fc.weight"], gf, bias=W[pre + "mlp.c_fc.bias"], act=lib.ACT_QUICKGELU, out_pre=hf)
+        xo = self.buf("x", (M, D), key=("train", i + 1) if training else ("eval", (i + 1) % 2))
+        self.gemm(gf, W[pre + "mlp.c_proj.weight"], xo, bias=W[pre + "mlp.c_proj.bias"], res1=tmp)
+        if training:
+            S.update(x=x, ln1t=(m1, r1), qkv_t=qkv_t, o_t=o_t, a_t=a_t, h_t=h_t, g_t=g_t, x1=x1, ln1s=(m2, r2),
+                     qkv_s=qkv_s, o_s=o_s, lse=lse, a_s=a_s, h_s=h_s, g_s=g_s, x2=x2, ln2=(m3, r3), xn2=xn2, h_m=h_m,
+                     g_m=g_m, hf=hf, masks=masks)
+            sv["blocks"].append(S)
+        return xo
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, dfeat: torch.Tensor, W: Dict[str, torch.Tensor], WT: Dict[str, torch.Tensor],
+                 grads: Dict[str, torch.Tensor], on_block_done: Optional[Callable[[int], None]] = None):
+        """dfeat fp32 [B, D, T].  WT: transposed weights ([K,N] contiguous) for the dgrad GEMMs.
+        grads: name -> fp32 tensor (views of the flat gradient buffer), overwritten.
+        on_block_done(i) is called after block i's gradients are complete (i = L for ln_post, -1 for
+        temporal_embedding) so the caller can start that bucket's all-reduce."""
+        sv = self.saved
+        assert sv is not None, "backward() without a training forward"
+        d: Dims = sv["d"]
+        M, D, n = d.M, d.D, d.n
+        dx = self.buf("dx", (M, D))
+        tm, tr = sv["tail"]
+        lib.tail_bwd(dfeat.contiguous(), sv["x_last"], tm, tr, W["ln_post.weight"], dx, grads["ln_post.weight"],
+                     grads["ln_post.bias"], d.B, d.T, n)
+        if on_block_done:
+            on_block_done(d.L)
+        for i in reversed(range(d.L)):
+            dx = self._block_bwd(i, dx, W, WT, grads, d, sv["blocks"][i])
+            if on_block_done:
+                on_block_done(i)
+        # ln_pre backward -> dz ; temporal_embedding grad = sum over (b, token)   (vit_clip.py:443-447)
+        m0, r0 = sv["ln_pre"]
+        dz = self.buf("dz", (M, D))
+        lib.layernorm_bwd(dx, sv["z"], m0, r0, W["ln_pre.weight"], None, dz)
+        lib.temb_grad(dz, grads["temporal_embedding"], d.B, d.T, n)
+        if on_block_done:
+            on_block_done(-1)
+        self.saved = None
+
+    def _adapter_bwd(self, name, pre, dy, a, h, g, W, WT, grads, d, rs, alpha, d_a_out, d_a_res):
+        """y = alpha * rs * (fc2(gelu(fc1(a)))).  Given dy: adapter weight/bias grads, and
+        d_a_out = d_a_res + d(a) (d_a_res may be None)."""
+        M, r, D = d.M, d.r, d.D
+        k1w, k1b = pre + name + ".D_fc1.weight", pre + name + ".D_fc1.bias"
+        k2w, k2b = pre + name + ".D_fc2.weight", pre + name + ".D_fc2.bias"
+        # fc2: g' = rs*gelu(h) was stored, so dW2 = alpha * dy^T g' ; db2 = alpha * sum_m rs[m] dy[m]
+        lib.gemm_wgrad(dy, g, grads[k2w], alpha=alpha)
+        lib.colsum(dy, grads[k2b], row_scale=rs, alpha=alpha)
+        # d_h = rs * alpha * (dy W2) * gelu'(h)
+        d_h = self.buf("d_h", (M, r))
+        self.gemm(dy, WT[k2w], d_h, dact_src=h, dact=lib.ACT_GELU, alpha=alpha, row_scale=rs)
+        lib.gemm_wgrad(d_h, a, grads[k1w])
+        lib.colsum(d_h, grads[k1b])
+        self.gemm(d_h, WT[k1w], d_a_out, res1=d_a_res)
+        return d_a_out
+
+    def _block_bwd(self, i, dx, W, WT, grads, d, S):
+        M, D, n = d.M, d.D, d.n
+        pre = f"transformer.resblocks.{i}."
+        mask_t, mask_m = S["masks"]
+        # ---------------- joint adaptation: x_out = x2 + mlp(xn2) + scale*mask_m*MLP_Adapter(xn2)
+        d_hf = self.buf("d_big", (M, 4 * D))
+        self.gemm(dx, WT[pre + "mlp.c_proj.weight"], d_hf, dact_src=S["hf"], dact=lib.ACT_QUICKGELU)
+        d_xn2 = self.buf("d_xn", (M, D))
+        self.gemm(d_hf, WT[pre + "mlp.c_fc.weight"], d_xn2)
+        self._adapter_bwd("MLP_Adapter", pre, dx, S["xn2"], S["h_m"], S["g_m"], W, WT, grads, d, mask_m, d.scale,
+                          d_xn2, d_xn2)
+        m3, r3 = S["ln2"]
+        dx2 = dx                                              # residual grads accumulate in place in `dx`
+        lib.layernorm_bwd(d_xn2, S["x2"], m3, r3, W[pre + "ln_2.weight"], dx, dx2)
+        # ---------------- spatial: x2 = x1 + a_s + S_Adapter_noskip(a_s)
+        d_as = self.buf("d_a", (M, D))
+        self._adapter_bwd("S_Adapter", pre, dx2, S["a_s"], S["h_s"], S["g_s"], W, WT, grads, d, None, 1.0, d_as, dx2)
+        d_os = self.buf("d_o", (M, D))
+        self.gemm(d_as, WT[pre + "attn.out_proj.weight"], d_os)
+        d_qkv = self.buf("d_qkv", (M, 3 * D))
+        lib.attn_spatial_bwd(S["qkv_s"], S["o_s"], d_os, S["lse"], d_qkv, d.BT, n, d.heads, impl=self.attn_impl)
+        d_xn1 = self.buf("d_xn", (M, D))
+        self.gemm(d_qkv, WT[pre + "attn.in_proj_weight"], d_xn1)
+        m2, r2 = S["ln1s"]
+        dx1 = dx
+        lib.layernorm_bwd(d_xn1, S["x1"], m2, r2, W[pre + "ln_1.weight"], dx2, dx1)
+        # ---------------- temporal: x1 = x + mask_t * T_Adapter(attn(ln_1(x)))
+        d_at = self.buf("d_a", (M, D))
+        self._adapter_bwd("T_Adapter", pre, dx1, S["a_t"], S["h_t"], S["g_t"], W, WT, grads, d, mask_t, 1.0, d_at, None)
+        d_ot = self.buf("d_o", (M, D))
+        self.gemm(d_at, WT[pre + "attn.out_proj.weight"], d_ot)
+        lib.attn_temporal_bwd(S["qkv_t"], d_ot, d_qkv, d.B, d.T, n, d.heads)
+        d_xn1t = self.buf("d_xn", (M, D))
+        self.gemm(d_qkv, WT[pre + "attn.in_proj_weight"], d_xn1t)
+        if d.num_tadapter == 2:
+            xn, hi, gi = S["tin"]
+            d_xn_tot = self.buf("d_xn_b", (M, D))
+            self._adapter_bwd("T_Adapter_in", pre, d_xn1t, xn, hi, gi, W, WT, grads, d, None, 1.0, d_xn_tot, d_xn1t)
+            d_xn1t = d_xn_tot
+        m1, r1 = S["ln1t"]
+        lib.layernorm_bwd(d_xn1t, S["x"], m1, r1, W[pre + "ln_1.weight"], dx1, dx)
+        return dx

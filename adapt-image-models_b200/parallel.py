@@ -1,0 +1,73 @@
+"""Data parallelism by clip: the only parallelism of the reference (mmaction/apis/train.py:106-110,
+MMDistributedDataParallel -> torch DDP, 25 MB buckets).  Here it is explicit: the backbone's backward
+fills one flat fp32 gradient buffer from the top (ln_post, block L-1, ...) down; every
+``bucket_blocks`` blocks the finished slice is all-reduced (average) over NCCL/NVLink on a side
+stream while the earlier blocks are still in backward.  One process per GPU; no other collective
+exists on this path."""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+class GradSync:
+    def __init__(self, group: Optional["dist.ProcessGroup"] = None, bucket_blocks: int = 3):
+        self.group = group
+        self.bucket_blocks = max(1, int(bucket_blocks))
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._works: List = []
+        self._side = None
+        self.buckets_launched = 0
+        self.bytes_reduced = 0
+
+    def want_bucket(self, i: int, L: int) -> bool:
+        """i = block whose gradients just completed (L = ln_post, -1 = temporal_embedding)."""
+        if i == -1 or i == L:
+            return False
+        return (L - i) % self.bucket_blocks == 0
+
+    def bucket_done(self, flat_grad: torch.Tensor, lo: int, hi: int):
+        if self.world == 1 or hi <= lo:
+            return
+        sl = flat_grad[lo:hi]
+        if sl.is_cuda:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=sl.device)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(sl.device))
+            self._side.wait_event(ev)
+            with torch.cuda.stream(self._side):
+                w = dist.all_reduce(sl, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+            sl.record_stream(self._side)
+        else:  # gloo (CPU tests): no AVG op
+            w = dist.all_reduce(sl, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._post_scale = getattr(self, "_post_scale", [])
+            self._post_scale.append(sl)
+        self._works.append(w)
+        self.buckets_launched += 1
+        self.bytes_reduced += sl.numel() * 4
+
+    def finish(self):
+        """Make the compute stream wait for every outstanding bucket."""
+        for w in self._works:
+            w.wait()
+        self._works.clear()
+        for sl in getattr(self, "_post_scale", []):
+            sl.div_(self.world)
+        self._post_scale = []
+
+
+def allreduce_mean_(tensors: List[torch.Tensor], group=None):
+    """Coalesced average of a few small tensors (the head FC grads, log scalars): one collective."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1 or not tensors:
+        return
+    flat = torch.cat([t.reshape(-1).float() for t in tensors])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat.div_(dist.get_world_size(group))
+    o = 0
+    for t in tensors:
+        k = t.numel()
+        t.copy_(flat[o:o + k].view_as(t))
+        o += k

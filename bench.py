@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py — AIM ViT-B/16 8x224 training step (cfg2 of BASELINE.json) on N B200s, one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" = one pass of the hot path over one batch of synthetic clips: backbone forward, I3D head,
+cross-entropy, adapter-only backward, gradient all-reduce (N>1), AdamW.  8 clips per GPU (weak
+scaling; global batch 64 at N=8, the reference recipe, configs/recognition/vit/vitclip_base_k400.py:66-67).
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle port of the reference path on
+the host cores (the reference is pure Python/PyTorch-CPU; `/root/reference` does not travel to the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+METRIC = "AIM ViT-B/16 8x224 train clips/s"
+UNIT = "clips/s"
+CLIPS_PER_GPU = 8
+NUM_CLASSES = 400
+MODEL = dict(input_resolution=224, patch_size=16, num_frames=8, width=768, layers=12, heads=12, drop_path_rate=0.2,
+             num_tadapter=1, adapter_scale=0.5)       # vitclip_base_k400.py:5-8 with num_frames 32 -> 8 (k700 :6)
+TFLOP_PER_CLIP_STEP = 0.858    # BASELINE.md §2 (algorithmic: fwd 0.404 + bwd 1.12x)
+TFLOP_PER_CLIP_FWD = 0.404
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1389.8), d.get("hbm_gbs", 6542.1), "measured (MEASURED_PEAKS.json, sustained)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                                          "100", "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [c.strip() for c in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_step_rate(steps: int, warmup: int, clips: int = 1):
+    """Training step of the oracle port on the host cores: fwd + CE + bwd (trainable set) + AdamW, `clips` per step."""
+    from oracle import aim_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.OracleCfg(input_resolution=224, num_frames=8, patch_size=16, width=768, layers=12, heads=12)
+    p = O.fixture_state_dict(cfg)
+    params = {k: v.clone().requires_grad_(O.is_trainable(k)) for k, v in p.items()}
+    hw, hb = O.fixture_head(cfg, NUM_CLASSES)
+    hw.requires_grad_(True), hb.requires_grad_(True)
+    train = [v for v in params.values() if v.requires_grad] + [hw, hb]
+    opt = torch.optim.AdamW(train, lr=3e-4, weight_decay=0.05)
+    x = O.fixture_clip(cfg, clips)
+    labels = torch.arange(clips) % NUM_CLASSES
+    g = torch.Generator().manual_seed(0)
+    rates = torch.linspace(0, MODEL["drop_path_rate"], cfg.layers)
+
+    def step():
+        masks = []
+        for i in range(cfg.layers):
+            keep = 1 - float(rates[i])
+            if keep == 1.0:
+                masks.append((None, None))
+            else:
+                masks.append(tuple((torch.rand(cfg.tokens, generator=g) < keep).float() / keep for _ in range(2)))
+        feat = O.backbone(params, x, cfg, masks)
+        lg = F.dropout(feat.mean(dim=(2, 3, 4)), 0.5, True) @ hw.T + hb
+        loss = F.cross_entropy(lg, labels)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return clips * steps / dt, dt / steps, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 10)), max(0, min(args.warmup, 2))
+    v, spstep, cores = cpu_reference_step_rate(steps, warmup, clips=1)
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+           "warmup": warmup, "ms_per_step": spstep * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "AIM ViT-B/16 8x224 training step (fwd+CE+bwd adapters+AdamW), 1 clip per step (bounded sample of the 8-clips/GPU workload)"},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": f"{steps} steps x 1 clip, torch CPU fp32, {cores} threads"},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+class Trainer:
+    """Minimal recognizer glue around the backbone: I3D head (T-mean, dropout .5, FC), CE, AdamW, grad sync."""
+
+    def __init__(self, device, world, dtype="bf16", seed=0):
+        import aimb200
+        from oracle import aim_oracle as O   # fixture weights only (deterministic random init); not on the timed path
+        self.aimb = aimb200
+        cfg = O.OracleCfg(input_resolution=224, num_frames=8, patch_size=16, width=768, layers=12, heads=12)
+        m = aimb200.build_backbone(dict(type="ViT_CLIP", compute_dtype=dtype, **MODEL))
+        m.init_weights()
+        m.load_state_dict(O.fixture_state_dict(cfg, seed=seed))
+        self.backbone = m.to(device).train()
+        hw, hb = O.fixture_head(cfg, NUM_CLASSES)
+        self.hw = hw.to(device).requires_grad_(True)
+        self.hb = hb.to(device).requires_grad_(True)
+        self.world = world
+        self.sync = aimb200.GradSync(bucket_blocks=3) if world > 1 else None
+        if self.sync is not None:
+            self.backbone.attach_grad_sync(self.sync)
+        decay = [p for n, p in self.backbone.named_parameters() if p.requires_grad and "Adapter" in n and n.endswith("weight")]
+        nodecay = [p for n, p in self.backbone.named_parameters() if p.requires_grad and not ("Adapter" in n and n.endswith("weight"))]
+        self.opt = torch.optim.AdamW([{"params": decay + [self.hw], "weight_decay": 0.05},
+                                      {"params": nodecay + [self.hb], "weight_decay": 0.0}], lr=3e-4, fused=True)
+
+    def step(self, x, labels):
+        feat = self.backbone(x)
+        pooled = F.dropout(feat.mean(dim=(2, 3, 4)), 0.5, True)
+        logits = F.linear(pooled, self.hw, self.hb)
+        loss = F.cross_entropy(logits, labels)
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if self.sync is not None:
+            self.aimb.parallel.allreduce_mean_([self.hw.grad, self.hb.grad])
+        self.opt.step()
+        return loss
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200 (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import aimb200
+    from aimb200 import lib
+    lib.load()
+    tr = Trainer(dev, world, dtype=args.dtype)
+    B = CLIPS_PER_GPU
+    g = torch.Generator().manual_seed(2 + rank)
+    host_x = torch.randn(B, 3, 8, 224, 224, generator=g).pin_memory()      # synthetic clips, K400 shape
+    host_y = torch.randint(0, NUM_CLASSES, (B,), generator=g).pin_memory()
+    dev_x, dev_y = host_x.to(dev), host_y.to(dev)
+    l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """Device time of `steps` calls (CUDA events on the current stream), max over ranks."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    def step_resident():
+        l2_flush.zero_()
+        return tr.step(dev_x, dev_y)
+
+    losses = []
+
+    def step_e2e():
+        l2_flush.zero_()
+        x = host_x.to(dev, non_blocking=True)
+        y = host_y.to(dev, non_blocking=True)
+        losses.append(float(tr.step(x, y)))       # D2H read of the step's loss
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    # cost of the L2 flush alone (subtracted: it is measurement hygiene, not work)
+    flush_ms = timed(lambda: l2_flush.zero_(), 10) / 10
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = lib.launches
+    ms = timed(step_resident, args.steps)
+    launches = (lib.launches - l0) // args.steps
+    clocks = sampler.stop() if sampler else None
+    ms_step = ms / args.steps - flush_ms
+    ms_e2e = timed(step_e2e, args.steps) / args.steps - flush_ms
+    value = world * B / (ms_step / 1e3)
+    e2e = world * B / (ms_e2e / 1e3)
+
+    # ---- roofline of the dominant kernel (tcgen05 GEMM): CUDA events around every GEMM launch, live, same steps
+    peak_tf, peak_hbm, peak_src = _peaks()
+    recs = []
+    orig = lib.gemm_nt
+
+    def timed_gemm(a, w, out, impl=lib.IMPL_AUTO, **kw):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        r = orig(a, w, out, impl=impl, **kw)
+        e.record()
+        recs.append((s, e, 2.0 * a.shape[0] * w.shape[0] * a.shape[1]))
+        return r
+
+    lib.gemm_nt = timed_gemm
+    import aimb200.engine as eng
+    eng.lib.gemm_nt = timed_gemm
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    nprof = min(args.steps, 5)
+    for _ in range(nprof):
+        tr.step(dev_x, dev_y)
+    e1.record()
+    barrier()
+    lib.gemm_nt = orig
+    eng.lib.gemm_nt = orig
+    gemm_ms = sum(s.elapsed_time(e) for s, e, _ in recs)
+    gemm_fl = sum(f for _, _, f in recs)
+    prof_ms = e0.elapsed_time(e1)
+    achieved = gemm_fl / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (TMA + tcgen05/TMEM bf16 GEMM)", "achieved": achieved,
+                "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                "launches_per_step": len(recs) // nprof, "avg_launch_us": gemm_ms * 1e3 / max(1, len(recs)),
+                "share_of_step": gemm_ms / prof_ms,
+                "step_tflops_algorithmic": TFLOP_PER_CLIP_STEP * B / (ms_step / 1e3),
+                "step_frac_of_peak": TFLOP_PER_CLIP_STEP * B / (ms_step / 1e3) / peak_tf}
+
+    if rank == 0:
+        v_cpu, sp, cores = cpu_reference_step_rate(2, 1, clips=1) if world == 1 else (None, None, None)
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+               "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": args.dtype, "data": "synthetic",
+               "config": {"workload": "AIM ViT-B/16 8x224 K400-shape training step (cfg2): 8 clips/GPU, fwd + I3D head + CE + "
+                          "adapter-only bwd + grad all-reduce + AdamW", "global_batch": world * B, "clips_per_gpu": B,
+                          "parallelism": f"dp{world}", "block": "aim", "l2": "flushed between steps (256 MiB memset, its time subtracted)"},
+               "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": host_x.numel() * 4 + host_y.numel() * 8,
+                       "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
+               "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
+               "loss_last": losses[-1] if losses else None}
+        if v_cpu is not None:
+            out["cpu_baseline"] = {"value": v_cpu, "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": "2 training steps x 1 clip of the same model on the oracle port (torch CPU fp32)"}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -6,7 +6,7 @@ weights/clips of oracle/aim_oracle.py.  Run in the build container only:
 
 Outputs (committed):
   tiny_<block>[_nt2].npz : fp64 logits, loss and every trainable gradient of a 2-layer,
-                           width-128 model (full tensors; small)
+                           width-256 model (full tensors; small)
   vitb16_8x224_<block>.npz : cfg1 of BASELINE.json (ViT-B/16, 8x224, batch 1): fp32 and fp64
                            logits of the reference, loss, per-block cls-token taps (frame 0)
                            and per-tensor gradient summaries (L2 norm, sum, first 8 values).
@@ -27,7 +27,7 @@ from oracle import aim_oracle as O  # noqa: E402
 from oracle import ref_loader as R  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-TINY = dict(input_resolution=64, num_frames=4, patch_size=16, width=128, layers=2, heads=2)
+TINY = dict(input_resolution=64, num_frames=4, patch_size=16, width=256, layers=2, heads=4)
 
 
 def _ref(cfg, p, dt):
@@ -66,7 +66,7 @@ def make_tiny(block, nt):
            "feat": feat.detach().numpy(), "labels": labels.numpy()}
     for name, prm in m.named_parameters():
         if prm.requires_grad:
-            out["grad/" + name] = prm.grad.numpy()
+            out["grad/" + name] = prm.grad.numpy().astype(np.float32)
     tag = f"tiny_{block}" + ("_nt2" if nt == 2 else "")
     np.savez_compressed(os.path.join(HERE, tag + ".npz"), **out)
     print(tag, "loss", float(loss), "n_grads", sum(k.startswith("grad/") for k in out))

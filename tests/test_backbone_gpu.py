@@ -1,0 +1,151 @@
+"""Model-level parity on a real B200: aimb200.ViT_CLIP (CUDA path through the C ABI) against
+ (1) the CPU oracle on the same seeded fixture and (2) the committed golden vectors produced by the
+ real reference.  Gates: fp32 mode max|d|/max|ref| <= 1e-3 on logits, bf16 mode
+ <= 2e-2 with identical top-1; gradients of the trainable set: <= 1e-3 (fp32), <= 6e-2 (bf16)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import aimb200
+from oracle import aim_oracle as O
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+TINY = dict(input_resolution=64, num_frames=4, patch_size=16, width=256, layers=2, heads=4)
+
+
+def _build(cfg: O.OracleCfg, mode: str, drop_path_rate=0.0):
+    m = aimb200.build_backbone(dict(type="ViT_CLIP", input_resolution=cfg.input_resolution, num_frames=cfg.num_frames,
+                                    patch_size=cfg.patch_size, width=cfg.width, layers=cfg.layers, heads=cfg.heads,
+                                    drop_path_rate=drop_path_rate, num_tadapter=cfg.num_tadapter,
+                                    adapter_scale=cfg.adapter_scale, compute_dtype=mode))
+    m.init_weights()
+    m.load_state_dict(O.fixture_state_dict(cfg))
+    return m.cuda()
+
+
+def _cuda_logits_and_grads(m, cfg, x, hw, hb, labels):
+    hwc, hbc = hw.cuda().requires_grad_(True), hb.cuda().requires_grad_(True)
+    m.train()   # drop_path_rate=0 -> deterministic; exercises the saved-activation path
+    feat = m(x.cuda())
+    lg = O.head_logits(feat, hwc, hbc)
+    loss = F.cross_entropy(lg, labels.cuda())
+    loss.backward()
+    grads = {k: p.grad.detach().cpu() for k, p in m.named_parameters() if p.requires_grad}
+    return lg.detach().cpu(), float(loss), grads
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("nt", [1, 2])
+def test_tiny_logits_and_all_grads_vs_golden(mode, nt):
+    gold = np.load(os.path.join(G, "tiny_aim" + ("_nt2" if nt == 2 else "") + ".npz"))
+    cfg = O.OracleCfg(**TINY, block="aim", num_tadapter=nt)
+    m = _build(cfg, mode)
+    x = O.fixture_clip(cfg, 2)
+    hw, hb = O.fixture_head(cfg, 16)
+    lg, loss, grads = _cuda_logits_and_grads(m, cfg, x, hw, hb, torch.tensor(gold["labels"]))
+    tol_l, tol_g = (1e-3, 1e-3) if mode == "fp32" else (2e-2, 6e-2)
+    assert O.normalised_max_err(lg, torch.tensor(gold["logits"])) < tol_l
+    assert abs(loss - float(gold["loss"])) < tol_l
+    n = 0
+    for k in gold.files:
+        if k.startswith("grad/"):
+            n += 1
+            assert O.normalised_max_err(grads[k[5:]], torch.tensor(gold[k])) < tol_g, k
+    assert n == len(grads)
+    # eval-mode (inference buffers) forward agrees with the training-mode forward
+    m.eval()
+    with torch.no_grad():
+        lg2 = O.head_logits(m(x.cuda()), hw.cuda(), hb.cuda()).cpu()
+    assert O.normalised_max_err(lg2, lg) < (1e-6 if mode == "fp32" else 5e-3)  # bf16: eval skips the pre-activation rounding
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_vitb16_8x224_logits_vs_golden_and_oracle(mode):
+    """cfg1 of BASELINE.json (the reference correctness fixture): ViT-B/16, 8x224, batch 1."""
+    gold = np.load(os.path.join(G, "vitb16_8x224_aim.npz"))
+    cfg = O.OracleCfg(block="aim")
+    m = _build(cfg, mode)
+    x = O.fixture_clip(cfg, 1)
+    hw, hb = O.fixture_head(cfg, 400)
+    lg, loss, grads = _cuda_logits_and_grads(m, cfg, x, hw, hb, torch.tensor(gold["labels"]))
+    ref = torch.tensor(gold["logits_f64"])
+    err = O.normalised_max_err(lg, ref)
+    print(f"[{mode}] logit err vs reference fp64 = {err:.3e}; loss {loss:.6f} vs {float(gold['loss_f64']):.6f}")
+    assert err < (1e-3 if mode == "fp32" else 2e-2)
+    assert int(lg.argmax()) == int(ref.argmax())
+    # gradient summaries of all 147 trainable tensors + 5 full tensors
+    names = [str(s) for s in gold["grad_names"]]
+    assert sorted(names) == sorted(grads)
+    tol = 1e-3 if mode == "fp32" else 6e-2
+    worst = 0.0
+    for i, k in enumerate(names):
+        g = grads[k].double().reshape(-1)
+        e = abs(float(g.norm()) - gold["grad_norm"][i]) / max(gold["grad_norm"][i], 1e-30)
+        worst = max(worst, e)
+        assert e < tol, (k, e)
+    for k in gold.files:
+        if k.startswith("grad/"):
+            assert O.normalised_max_err(grads[k[5:]], torch.tensor(gold[k])) < tol, k
+    print(f"[{mode}] worst grad-norm rel err over 147 tensors = {worst:.3e}")
+    # the live oracle on this box gives the same answer as the committed golden (oracle not drifting)
+    p = O.fixture_state_dict(cfg)
+    with torch.no_grad():
+        lo = O.logits(p, x, cfg, hw, hb)
+    assert O.normalised_max_err(lo, ref) < 5e-6
+
+
+def test_bf16_top1_identical_batch4():
+    cfg = O.OracleCfg(block="aim")
+    m = _build(cfg, "bf16").eval()
+    x = O.fixture_clip(cfg, 4, seed=5)
+    hw, hb = O.fixture_head(cfg, 400)
+    with torch.no_grad():
+        lg = O.head_logits(m(x.cuda()), hw.cuda(), hb.cuda()).cpu()
+        ref = O.logits(O.fixture_state_dict(cfg), x, cfg, hw, hb)
+    assert O.normalised_max_err(lg, ref) < 2e-2
+    assert torch.equal(lg.argmax(1), ref.argmax(1))
+
+
+def test_droppath_training_matches_oracle_with_same_masks():
+    cfg = O.OracleCfg(**TINY, block="aim")
+    m = _build(cfg, "fp32", drop_path_rate=0.5).train()
+    x = O.fixture_clip(cfg, 2)
+    torch.manual_seed(3)
+    masks = m._drop_masks(m._dims(2), torch.device("cuda"))
+    torch.manual_seed(3)
+    feat = m(x.cuda())
+    om = [(None, None) if a is None else (a.cpu(), b.cpu()) for a, b in masks]
+    ref = O.backbone(O.fixture_state_dict(cfg), x, cfg, drop_masks=om)
+    assert any(a is not None and float(a.min()) == 0.0 for a, _ in masks), "mask with a dropped token expected"
+    assert O.normalised_max_err(feat.detach().cpu(), ref) < 1e-3
+
+
+def test_uint8_input_normalisation_fused():
+    cfg = O.OracleCfg(**TINY, block="aim")
+    m = _build(cfg, "fp32").eval()
+    mean, std = [122.769, 116.74, 104.04], [68.493, 66.63, 70.321]
+    m.set_input_normalization(mean, std)
+    g = torch.Generator().manual_seed(9)
+    xu = torch.randint(0, 256, (2, 3, 4, 64, 64), dtype=torch.uint8, generator=g)
+    with torch.no_grad():
+        feat = m(xu.cuda()).cpu()
+    xf = (xu.float() - torch.tensor(mean).view(1, 3, 1, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1, 1)
+    ref = O.backbone(O.fixture_state_dict(cfg), xf, cfg)
+    assert O.normalised_max_err(feat, ref) < 1e-3
+
+
+def test_edge_shapes_and_errors():
+    cfg = O.OracleCfg(**TINY, block="aim")
+    m = _build(cfg, "bf16").eval()
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 3, 5, 64, 64, device="cuda"))      # T != num_frames (vit_clip.py:344,444)
+    with torch.no_grad():
+        out = m(torch.zeros(0, 3, 4, 64, 64, device="cuda"))  # empty batch
+    assert out.shape == (0, 256, 4, 1, 1)
+    with torch.no_grad():
+        out = m(torch.randn(3, 3, 4, 64, 64, device="cuda"))
+    assert out.shape == (3, 256, 4, 1, 1) and bool(torch.isfinite(out).all())

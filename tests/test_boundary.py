@@ -1,0 +1,89 @@
+"""CPU: the drop-in boundary — registry name, constructor arguments of every vitclip_* config, the
+state_dict layout, freeze rule, error behaviour, and that the C-ABI library exports what include/aimb200.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import aimb200
+from aimb200 import lib
+from oracle import aim_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+# model.backbone dicts of configs/recognition/vit/vitclip_*.py (+ _base_/models/vitclip_base.py), transcribed:
+# the configs are data, not code; `pretrained` overridden to None as the reference's recognizer tests do
+# (tests/test_models/test_recognizers/test_recognizer3d.py:9-10).
+CONFIG_BACKBONES = {
+    "_base_/vitclip_base": dict(type='ViT_CLIP', input_resolution=224, patch_size=16, num_frames=32, width=768, layers=12,
+                                heads=12, drop_path_rate=0.1),
+    "vitclip_base_k400": dict(type='ViT_CLIP', input_resolution=224, patch_size=16, num_frames=32, width=768, layers=12,
+                              heads=12, drop_path_rate=0.2, adapter_scale=0.5, num_tadapter=1, pretrained=None),
+    "vitclip_base_k700": dict(type='ViT_CLIP', input_resolution=224, patch_size=16, num_frames=8, width=768, layers=12,
+                              heads=12, drop_path_rate=0.2, adapter_scale=0.5, num_tadapter=1, pretrained=None),
+    "vitclip_base_sthv2": dict(type='ViT_CLIP', input_resolution=224, patch_size=16, num_frames=8, width=768, layers=12,
+                               heads=12, drop_path_rate=0.2, adapter_scale=0.5, num_tadapter=2, pretrained=None),
+    "vitclip_base_hmdb51": dict(type='ViT_CLIP', input_resolution=224, patch_size=16, num_frames=8, width=768, layers=12,
+                                heads=12, drop_path_rate=0.2, adapter_scale=0.5, pretrained=None, shift=False),
+    "vitclip_large_k400": dict(type='ViT_CLIP', input_resolution=224, patch_size=14, num_frames=8, width=1024, layers=24,
+                               heads=16, drop_path_rate=0.2, adapter_scale=0.5, num_tadapter=1, pretrained=None),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CONFIG_BACKBONES))
+def test_config_backbones_build(name):
+    cfg = dict(CONFIG_BACKBONES[name])
+    if cfg["layers"] == 24:
+        cfg["layers"] = 2            # keep the CPU suite small; the tree per block is what matters
+    m = aimb200.build_backbone(cfg)
+    assert type(m).__name__ == "ViT_CLIP"
+    m.init_weights()                 # called with no arguments by BaseRecognizer (recognizers/base.py:126)
+    ocfg = O.OracleCfg(input_resolution=cfg["input_resolution"], num_frames=cfg["num_frames"], patch_size=cfg["patch_size"],
+                       width=cfg["width"], layers=cfg["layers"], heads=cfg["heads"], num_tadapter=cfg.get("num_tadapter", 1))
+    want = O.param_shapes(ocfg)
+    got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert got == want
+    for k, p in m.named_parameters():
+        assert p.requires_grad == O.is_trainable(k), k
+    for k, p in m.named_parameters():            # zero-init of every adapter's D_fc2 (vit_clip.py:386-411)
+        if "Adapter" in k and "D_fc2" in k:
+            assert float(p.abs().max()) == 0.0
+
+
+def test_registry_and_errors():
+    assert aimb200.BACKBONES.get("ViT_CLIP") is aimb200.ViT_CLIP
+    with pytest.raises(TypeError):
+        aimb200.build_backbone(dict(type='ViT_CLIP', input_resolution=224, patch_size=16, num_frames=8, width=768, layers=1,
+                                    heads=12, drop_path_rate=0.0, bogus=1))
+    m = aimb200.ViT_CLIP(64, 4, 16, 128, 1, 2, 0.0)
+    with pytest.raises(TypeError, match="pretrained must be a str or None"):
+        m.init_weights(pretrained=3)
+    with pytest.raises(NotImplementedError):
+        aimb200.ViT_CLIP(64, 4, 16, 128, 1, 2, 0.0, shift=True)
+    with pytest.raises(lib.AimbError):       # no CPU fallback
+        m(torch.zeros(1, 3, 4, 64, 64))
+    assert m.no_weight_decay() == {'absolute_pos_embed', 'temporal_embedding'}
+
+
+def test_state_dict_roundtrip_with_fixture():
+    cfg = O.OracleCfg(input_resolution=64, num_frames=4, patch_size=16, width=128, layers=2, heads=2)
+    m = aimb200.ViT_CLIP(64, 4, 16, 128, 2, 2, 0.0)
+    sd = O.fixture_state_dict(cfg)
+    res = m.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, sd[k])
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "aimb200.h")).read()
+    declared = set(re.findall(r"\b(aimb_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert os.path.isfile(lib.LIB_PATH), "build the library first (__graft_entry__.build())"
+    so = ctypes.CDLL(lib.LIB_PATH)
+    for sym in sorted(declared):
+        assert hasattr(so, sym), f"{sym} declared in include/aimb200.h but not exported"
+    assert declared - {"aimb_last_error"} <= set(lib.SIGNATURES), "lib.py must bind every declared entry point"
+    assert so.aimb_version() >= 100

@@ -154,6 +154,25 @@ def test_gemm_tc_matches_simt_bitwise_inputs():
     assert _err(o1, o2.double()) < 8e-3
 
 
+@pytest.mark.parametrize("R", [1576, 12608, 100, 64])
+@pytest.mark.parametrize("N,K", [(192, 768), (768, 192), (256, 1024), (1024, 256), (64, 256), (128, 128)])
+def test_wgrad_tc(R, N, K):
+    """tcgen05 wgrad (both operands MN-major, split over the rows, fp32 red.global) vs fp64."""
+    lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(R + N)
+    dy = torch.randn(R, N, device="cuda", generator=g).bfloat16()
+    x = torch.randn(R, K, device="cuda", generator=g).bfloat16()
+    dw = torch.full((N, K), float("nan"), device="cuda")
+    lib.gemm_wgrad(dy, x, dw, alpha=0.5)
+    ref = 0.5 * dy.double().T @ x.double()
+    assert _err(dw, ref) < 1e-4
+    lib.gemm_wgrad(dy, x, dw, alpha=0.5, accumulate=True)
+    assert _err(dw, 2 * ref) < 1e-4
+    dw2 = torch.empty_like(dw)
+    lib.gemm_wgrad(dy, x, dw2, alpha=0.5, impl=lib.IMPL_SIMT)
+    assert _err(dw2, ref) < 1e-4
+
+
 @pytest.mark.parametrize("dt", ["f32", "bf16"])
 def test_wgrad_colsum_transpose(dt):
     lib = _lib()
