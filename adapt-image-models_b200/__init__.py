@@ -9,5 +9,6 @@ __all__ = ["lib"]
 from .registry import BACKBONES, build_backbone  # noqa: E402,F401
 from .backbone import ViT_CLIP  # noqa: E402,F401
 from .parallel import GradSync  # noqa: E402,F401
+from .graphs import GraphedStep  # noqa: E402,F401
 
-__all__ += ["BACKBONES", "build_backbone", "ViT_CLIP", "GradSync"]
+__all__ += ["BACKBONES", "build_backbone", "ViT_CLIP", "GradSync", "GraphedStep"]

@@ -325,7 +325,10 @@ class ViT_CLIP(nn.Module):
         if not self.training or self.drop_path_rate <= 0.0:
             return None
         rates = torch.linspace(0, self.drop_path_rate, self.layers)
-        keep = (1.0 - rates).to(device).view(-1, 1, 1)
+        ck = getattr(self, "_keep_cache", None)
+        if ck is None or ck[0] != (str(device), self.drop_path_rate):
+            self._keep_cache = ((str(device), self.drop_path_rate), (1.0 - rates).to(device).view(-1, 1, 1))
+        keep = self._keep_cache[1]
         # timm DropPath on LND tensors: one Bernoulli draw per token index, shared by all frames;
         # two independent draws per block (temporal branch, MLP-adapter branch)
         m = (torch.rand(self.layers, 2, d.n, device=device) < keep).float() / keep

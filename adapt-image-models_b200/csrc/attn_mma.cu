@@ -370,8 +370,12 @@ int attn_spatial_fwd_mma(const void* qkv, void* o, float* lse, int frames, int n
     if (nwarps * 32 > 576) return AIMB_ERR_UNSUPPORTED;
     size_t smem = (size_t)3 * npad * LDS * 2;
     if (smem > 227 * 1024) return AIMB_ERR_UNSUPPORTED;
-    if (cudaFuncSetAttribute(attn_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-        return AIMB_ERR_CUDA;
+    static bool attr_set = false;   // once: not a stream operation, keeps the launch path capture-safe
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(attn_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+            return AIMB_ERR_CUDA;
+        attr_set = true;
+    }
     attn_fwd_mma_kernel<<<frames * heads, nwarps * 32, smem, s>>>((const bf16*)qkv, (bf16*)o, lse, n, heads);
     AIMB_CHECK_LAUNCH();
     return AIMB_OK;
@@ -384,8 +388,12 @@ int attn_spatial_bwd_mma(const void* qkv, const void* o, const void* d_o, const 
     if (nwarps * 32 > 576) return AIMB_ERR_UNSUPPORTED;
     size_t smem = (size_t)4 * npad * LDS * 2 + (size_t)2 * npad * 4;
     if (smem > 227 * 1024) return AIMB_ERR_UNSUPPORTED;
-    if (cudaFuncSetAttribute(attn_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-        return AIMB_ERR_CUDA;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(attn_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+            return AIMB_ERR_CUDA;
+        attr_set = true;
+    }
     attn_bwd_mma_kernel<<<frames * heads, nwarps * 32, smem, s>>>((const bf16*)qkv, (const bf16*)o, (const bf16*)d_o, lse,
                                                                   (bf16*)d_qkv, n, heads);
     AIMB_CHECK_LAUNCH();

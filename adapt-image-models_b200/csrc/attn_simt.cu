@@ -370,8 +370,12 @@ template <typename T>
 int spatial_fwd_simt_launch(const void* qkv, void* o, float* lse, int frames, int n, int heads, cudaStream_t s) {
     size_t smem = spatial_fwd_smem(n);
     if (smem > 227 * 1024) return AIMB_ERR_UNSUPPORTED;
-    if (cudaFuncSetAttribute(attn_spatial_fwd_simt<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-        return AIMB_ERR_CUDA;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(attn_spatial_fwd_simt<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+            return AIMB_ERR_CUDA;
+        attr_set = true;
+    }
     attn_spatial_fwd_simt<T><<<frames * heads, 256, smem, s>>>((const T*)qkv, (T*)o, lse, n, heads);
     AIMB_CHECK_LAUNCH();
     return AIMB_OK;
@@ -381,8 +385,12 @@ int spatial_bwd_simt_launch(const void* qkv, const void* o, const void* d_o, con
                             int n, int heads, cudaStream_t s) {
     size_t smem = spatial_bwd_smem(n);
     if (smem > 227 * 1024) return AIMB_ERR_UNSUPPORTED;
-    if (cudaFuncSetAttribute(attn_spatial_bwd_simt<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-        return AIMB_ERR_CUDA;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(attn_spatial_bwd_simt<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+            return AIMB_ERR_CUDA;
+        attr_set = true;
+    }
     attn_spatial_bwd_simt<T><<<frames * heads, 256, smem, s>>>((const T*)qkv, (const T*)o, (const T*)d_o, lse, (T*)d_qkv, n,
                                                                heads);
     AIMB_CHECK_LAUNCH();
@@ -414,14 +422,23 @@ extern "C" int aimb_attn_temporal_fwd(const void* qkv, void* o, int32_t B, int32
     size_t smem = (size_t)4 * (3 * T * KS + T * (T + 1)) * 4;
     int64_t probs = (int64_t)B * n * heads;
     unsigned grid = (unsigned)((probs + 3) / 4);
-    cudaError_t e;
+    cudaError_t e = cudaSuccess;
+    (void)e;
     if (dtype == AIMB_BF16) {
-        e = cudaFuncSetAttribute(attn_temporal_fwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return AIMB_ERR_CUDA;
+        static bool once = false;
+        if (!once) {
+            e = cudaFuncSetAttribute(attn_temporal_fwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess) return AIMB_ERR_CUDA;
+            once = true;
+        }
         attn_temporal_fwd_kernel<bf16><<<grid, 128, smem, s>>>((const bf16*)qkv, (bf16*)o, B, T, n, heads);
     } else if (dtype == AIMB_F32) {
-        e = cudaFuncSetAttribute(attn_temporal_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return AIMB_ERR_CUDA;
+        static bool once = false;
+        if (!once) {
+            e = cudaFuncSetAttribute(attn_temporal_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess) return AIMB_ERR_CUDA;
+            once = true;
+        }
         attn_temporal_fwd_kernel<float><<<grid, 128, smem, s>>>((const float*)qkv, (float*)o, B, T, n, heads);
     } else return AIMB_ERR_ARG;
     AIMB_CHECK_LAUNCH();
@@ -436,15 +453,24 @@ extern "C" int aimb_attn_temporal_bwd(const void* qkv, const void* d_o, void* d_
     size_t smem = (size_t)4 * (4 * T * KS + 2 * T * (T + 1)) * 4;
     int64_t probs = (int64_t)B * n * heads;
     unsigned grid = (unsigned)((probs + 3) / 4);
-    cudaError_t e;
+    cudaError_t e = cudaSuccess;
+    (void)e;
     if (dtype == AIMB_BF16) {
-        e = cudaFuncSetAttribute(attn_temporal_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return AIMB_ERR_CUDA;
+        static bool once = false;
+        if (!once) {
+            e = cudaFuncSetAttribute(attn_temporal_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess) return AIMB_ERR_CUDA;
+            once = true;
+        }
         attn_temporal_bwd_kernel<bf16><<<grid, 128, smem, s>>>((const bf16*)qkv, (const bf16*)d_o, (bf16*)d_qkv, B, T, n,
                                                                heads);
     } else if (dtype == AIMB_F32) {
-        e = cudaFuncSetAttribute(attn_temporal_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return AIMB_ERR_CUDA;
+        static bool once = false;
+        if (!once) {
+            e = cudaFuncSetAttribute(attn_temporal_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess) return AIMB_ERR_CUDA;
+            once = true;
+        }
         attn_temporal_bwd_kernel<float><<<grid, 128, smem, s>>>((const float*)qkv, (const float*)d_o, (float*)d_qkv, B, T,
                                                                 n, heads);
     } else return AIMB_ERR_ARG;

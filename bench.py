@@ -156,16 +156,18 @@ class Trainer:
 
     def __init__(self, device, world, dtype="bf16", seed=0):
         import aimb200
-        from oracle import aim_oracle as O   # fixture weights only (deterministic random init); not on the timed path
         self.aimb = aimb200
-        cfg = O.OracleCfg(input_resolution=224, num_frames=8, patch_size=16, width=768, layers=12, heads=12)
+        torch.manual_seed(seed)
         m = aimb200.build_backbone(dict(type="ViT_CLIP", compute_dtype=dtype, **MODEL))
-        m.init_weights()
-        m.load_state_dict(O.fixture_state_dict(cfg, seed=seed))
+        m.init_weights()                                   # random init (no CLIP weights offline) + freeze rule
+        g = torch.Generator().manual_seed(seed + 1)
+        with torch.no_grad():                              # init_weights() zeroes D_fc2 / biases / temporal_embedding:
+            for n, p in m.named_parameters():              # randomise them so the adapter paths do real work
+                if "D_fc2" in n or n.endswith("bias") or "temporal_embedding" in n:
+                    p.copy_(0.02 * torch.randn(p.shape, generator=g))
         self.backbone = m.to(device).train()
-        hw, hb = O.fixture_head(cfg, NUM_CLASSES)
-        self.hw = hw.to(device).requires_grad_(True)
-        self.hb = hb.to(device).requires_grad_(True)
+        self.hw = (0.01 * torch.randn(NUM_CLASSES, MODEL["width"], generator=g)).to(device).requires_grad_(True)
+        self.hb = torch.zeros(NUM_CLASSES).to(device).requires_grad_(True)   # I3DHead init (i3d_head.py:49-51)
         self.world = world
         self.sync = aimb200.GradSync(bucket_blocks=3) if world > 1 else None
         if self.sync is not None:
@@ -173,7 +175,8 @@ class Trainer:
         decay = [p for n, p in self.backbone.named_parameters() if p.requires_grad and "Adapter" in n and n.endswith("weight")]
         nodecay = [p for n, p in self.backbone.named_parameters() if p.requires_grad and not ("Adapter" in n and n.endswith("weight"))]
         self.opt = torch.optim.AdamW([{"params": decay + [self.hw], "weight_decay": 0.05},
-                                      {"params": nodecay + [self.hb], "weight_decay": 0.0}], lr=3e-4, fused=True)
+                                      {"params": nodecay + [self.hb], "weight_decay": 0.0}], lr=3e-4, fused=True,
+                                     capturable=True)
 
     def step(self, x, labels):
         feat = self.backbone(x)
@@ -229,17 +232,32 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
+    use_graph = (world == 1 and not args.no_graph)
+    step_fn = tr.step
+    captured_launches = None
+    if use_graph:
+        l_before = lib.launches
+        graphed = aimb200.GraphedStep(tr.step, [dev_x, dev_y], warmup=3,
+                                      before_capture=lambda: tr.opt.zero_grad(set_to_none=True))
+        # launches recorded while capturing == launches replayed per step
+        captured_launches = (lib.launches - l_before) // 4
+        step_fn = graphed
+
     def step_resident():
         l2_flush.zero_()
-        return tr.step(dev_x, dev_y)
+        return step_fn(dev_x, dev_y)
 
     losses = []
 
     def step_e2e():
         l2_flush.zero_()
-        x = host_x.to(dev, non_blocking=True)
-        y = host_y.to(dev, non_blocking=True)
-        losses.append(float(tr.step(x, y)))       # D2H read of the step's loss
+        if use_graph:      # H2D straight into the graph's static input buffers
+            graphed.static_in[0].copy_(host_x, non_blocking=True)
+            graphed.static_in[1].copy_(host_y, non_blocking=True)
+            loss = graphed(graphed.static_in[0], graphed.static_in[1])
+        else:
+            loss = tr.step(host_x.to(dev, non_blocking=True), host_y.to(dev, non_blocking=True))
+        losses.append(float(loss.detach()))       # D2H read of the step's loss
 
     for _ in range(max(3, args.warmup)):
         step_resident()
@@ -248,7 +266,7 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = lib.launches
     ms = timed(step_resident, args.steps)
-    launches = (lib.launches - l0) // args.steps
+    launches = captured_launches if use_graph else (lib.launches - l0) // args.steps
     clocks = sampler.stop() if sampler else None
     ms_step = ms / args.steps - flush_ms
     ms_e2e = timed(step_e2e, args.steps) / args.steps - flush_ms
@@ -299,7 +317,7 @@ def run_ours(args):
                "dtype": args.dtype, "data": "synthetic",
                "config": {"workload": "AIM ViT-B/16 8x224 K400-shape training step (cfg2): 8 clips/GPU, fwd + I3D head + CE + "
                           "adapter-only bwd + grad all-reduce + AdamW", "global_batch": world * B, "clips_per_gpu": B,
-                          "parallelism": f"dp{world}", "block": "aim", "l2": "flushed between steps (256 MiB memset, its time subtracted)"},
+                          "parallelism": f"dp{world}", "block": "aim", "cuda_graph": use_graph, "l2": "flushed between steps (256 MiB memset, its time subtracted)"},
                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": host_x.numel() * 4 + host_y.numel() * 8,
                        "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
                "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
@@ -319,6 +337,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a captured CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
