@@ -79,6 +79,8 @@ def load():
     lib.aimb_last_error.argtypes = []
     lib.aimb_debug_force_bn.argtypes = [C.c_int]
     lib.aimb_debug_force_bn.restype = None
+    lib.aimb_debug_cta_mode.argtypes = [C.c_int]
+    lib.aimb_debug_cta_mode.restype = None
     _lib = lib
     return lib
 

@@ -115,24 +115,34 @@ def test_gemm_simt_bf16(case):
     assert _gemm_case(lib, "bf16", 333, 192, 128, case, lib.IMPL_SIMT) < 1.5e-2
 
 
+@pytest.mark.parametrize("cta_mode", [2, 1])
 @pytest.mark.parametrize("bn", [64, 128, 192, 256])
-@pytest.mark.parametrize("M,N,K", [(128, 768, 64), (1576, 768, 768), (300, 768, 3072), (12608, 2304, 768)])
-def test_gemm_tc_shapes(bn, M, N, K):
-    """tcgen05 kernel, every N-tile instantiation, ragged M (TMA zero fill + masked rows), deep K."""
+@pytest.mark.parametrize("M,N,K", [(128, 768, 64), (1576, 768, 768), (300, 768, 3072), (12608, 2304, 768), (129, 768, 128),
+                                   (385, 768, 192)])
+def test_gemm_tc_shapes(cta_mode, bn, M, N, K):
+    """tcgen05 kernels (cta_mode 2 = CTA pairs / cta_group::2, 1 = single CTA), every N-tile instantiation,
+    ragged M (TMA zero fill + masked rows, including a pair whose second CTA is entirely out of range), deep K."""
     lib = _lib()
     if N % bn:
         pytest.skip("N not divisible")
     lib.load().aimb_debug_force_bn(bn)
+    lib.load().aimb_debug_cta_mode(cta_mode)
     try:
         assert _gemm_case(lib, "bf16", M, N, K, "bias", lib.IMPL_AUTO, seed=bn) < 1e-2
     finally:
         lib.load().aimb_debug_force_bn(0)
+        lib.load().aimb_debug_cta_mode(0)
 
 
+@pytest.mark.parametrize("cta_mode", [2, 1])
 @pytest.mark.parametrize("case", EPI_CASES)
-def test_gemm_tc_epilogues(case):
+def test_gemm_tc_epilogues(case, cta_mode):
     lib = _lib()
-    assert _gemm_case(lib, "bf16", 1000, 768, 192, case, lib.IMPL_AUTO) < 1.5e-2
+    lib.load().aimb_debug_cta_mode(cta_mode)
+    try:
+        assert _gemm_case(lib, "bf16", 1000, 768, 192, case, lib.IMPL_AUTO) < 1.5e-2
+    finally:
+        lib.load().aimb_debug_cta_mode(0)
 
 
 @pytest.mark.parametrize("N,K", [(192, 768), (768, 192), (3072, 768), (768, 3072), (2304, 768), (256, 1024), (4096, 1024)])
