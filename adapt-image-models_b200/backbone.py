@@ -309,12 +309,18 @@ class ViT_CLIP(nn.Module):
                 t = t.reshape(-1, shape[-1])
             W[name] = t
         if training:
-            for name in self.trainable_names():
-                if name.endswith("D_fc1.weight") or name.endswith("D_fc2.weight"):
-                    w = W[name]
-                    wt = torch.empty(w.shape[1], w.shape[0], dtype=cd, device=w.device)
-                    lib.transpose(w, wt)
-                    WT[name] = wt
+            # dgrad through the (trainable) adapter linears needs W^T: all of them in ONE batched launch
+            wnames = [n for n in self.trainable_names() if n.endswith("D_fc1.weight") or n.endswith("D_fc2.weight")]
+            tb = getattr(self, "_tr_table", None)
+            if tb is None or tb[0] is not self._flat:
+                rows = [[self._offsets[n][0], params[n].shape[0], params[n].shape[1]] for n in wnames]
+                self._tr_table = (self._flat, torch.tensor(rows, dtype=torch.int64, device=self._flat.device))
+            flat_t = torch.empty_like(flat_c)
+            lib.transpose_batched(flat_c, flat_t, self._tr_table[1], len(wnames))
+            for n in wnames:
+                o, k = self._offsets[n]
+                r, c = params[n].shape
+                WT[n] = flat_t[o:o + k].view(c, r)
         if self._input_norm is not None:
             dev = self._flat.device
             W["input_mean"], W["input_std"] = self._input_norm[0].to(dev), self._input_norm[1].to(dev)

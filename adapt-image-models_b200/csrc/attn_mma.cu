@@ -68,7 +68,8 @@ __device__ __forceinline__ void load_tile_async(bf16* dst, const bf16* src, int6
 }
 
 // ------------------------------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(576) attn_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o,
+template <int NW>
+__global__ void __launch_bounds__(NW * 32) attn_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o,
                                                            float* __restrict__ lse, int n, int heads) {
     extern __shared__ __align__(16) uint8_t smraw[];
     const int D = heads * HD, ld = 3 * D;
@@ -177,7 +178,8 @@ __global__ void __launch_bounds__(576) attn_fwd_mma_kernel(const bf16* __restric
 }
 
 // ------------------------------------------------------------------------------------------ backward
-__global__ void __launch_bounds__(576) attn_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o,
+template <int NW>
+__global__ void __launch_bounds__(NW * 32) attn_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o,
                                                            const bf16* __restrict__ d_o, const float* __restrict__ lse,
                                                            bf16* __restrict__ d_qkv, int n, int heads) {
     extern __shared__ __align__(16) uint8_t smraw[];
@@ -229,28 +231,27 @@ __global__ void __launch_bounds__(576) attn_bwd_mma_kernel(const bf16* __restric
             for (int j = 0; j < 4; ++j) dq[i][j] = 0.f;
         const float ls0 = sL[r0 + g], ls1 = sL[r0 + g + 8];
         const float dl0 = sDl[r0 + g], dl1 = sDl[r0 + g + 8];
+        uint32_t qa[4][4], ga[4][4];     // this warp's Q and dO rows as A fragments (invariant over the key loop)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            lda_frag(qa[ks], sQ + r0 * LDS + ks * 16, lane);
+            lda_frag(ga[ks], sG + r0 * LDS + ks * 16, lane);
+        }
         for (int kc = 0; kc < npad; kc += 32) {
             float s[4][4], dp[4][4];
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt)
+            for (int nt = 0; nt < 4; ++nt) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { s[nt][j] = 0.f; dp[nt][j] = 0.f; }
 #pragma unroll
-            for (int kp = 0; kp < 2; ++kp) {
-                uint32_t qa0[4], qa1[4], ga0[4], ga1[4];
-                lda_frag(qa0, sQ + r0 * LDS + kp * 32, lane);
-                lda_frag(qa1, sQ + r0 * LDS + kp * 32 + 16, lane);
-                lda_frag(ga0, sG + r0 * LDS + kp * 32, lane);
-                lda_frag(ga1, sG + r0 * LDS + kp * 32 + 16, lane);
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt) {
+                for (int kp = 0; kp < 2; ++kp) {
                     uint32_t kb[4], vb[4];
                     ldb_frag_nk(kb, sK + (kc + nt * 8) * LDS + kp * 32, lane);
                     ldb_frag_nk(vb, sV + (kc + nt * 8) * LDS + kp * 32, lane);
-                    mma16816(s[nt], qa0, kb[0], kb[1]);
-                    mma16816(s[nt], qa1, kb[2], kb[3]);
-                    mma16816(dp[nt], ga0, vb[0], vb[1]);
-                    mma16816(dp[nt], ga1, vb[2], vb[3]);
+                    mma16816(s[nt], qa[2 * kp], kb[0], kb[1]);
+                    mma16816(s[nt], qa[2 * kp + 1], kb[2], kb[3]);
+                    mma16816(dp[nt], ga[2 * kp], vb[0], vb[1]);
+                    mma16816(dp[nt], ga[2 * kp + 1], vb[2], vb[3]);
                 }
             }
             uint32_t dsa[2][4];
@@ -293,28 +294,27 @@ __global__ void __launch_bounds__(576) attn_bwd_mma_kernel(const bf16* __restric
         for (int i = 0; i < 8; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) { dk[i][j] = 0.f; dv[i][j] = 0.f; }
+        uint32_t ka[4][4], va[4][4];     // this warp's K and V rows as A fragments (invariant over the query loop)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            lda_frag(ka[ks], sK + r0 * LDS + ks * 16, lane);
+            lda_frag(va[ks], sV + r0 * LDS + ks * 16, lane);
+        }
         for (int qc = 0; qc < npad; qc += 32) {
             float s[4][4], dp[4][4];
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt)
+            for (int nt = 0; nt < 4; ++nt) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { s[nt][j] = 0.f; dp[nt][j] = 0.f; }
 #pragma unroll
-            for (int kp = 0; kp < 2; ++kp) {
-                uint32_t ka0[4], ka1[4], va0[4], va1[4];
-                lda_frag(ka0, sK + r0 * LDS + kp * 32, lane);
-                lda_frag(ka1, sK + r0 * LDS + kp * 32 + 16, lane);
-                lda_frag(va0, sV + r0 * LDS + kp * 32, lane);
-                lda_frag(va1, sV + r0 * LDS + kp * 32 + 16, lane);
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt) {
+                for (int kp = 0; kp < 2; ++kp) {
                     uint32_t qb[4], gbf[4];
                     ldb_frag_nk(qb, sQ + (qc + nt * 8) * LDS + kp * 32, lane);
                     ldb_frag_nk(gbf, sG + (qc + nt * 8) * LDS + kp * 32, lane);
-                    mma16816(s[nt], ka0, qb[0], qb[1]);      // S^T[key, q]
-                    mma16816(s[nt], ka1, qb[2], qb[3]);
-                    mma16816(dp[nt], va0, gbf[0], gbf[1]);   // dP^T[key, q]
-                    mma16816(dp[nt], va1, gbf[2], gbf[3]);
+                    mma16816(s[nt], ka[2 * kp], qb[0], qb[1]);      // S^T[key, q]
+                    mma16816(s[nt], ka[2 * kp + 1], qb[2], qb[3]);
+                    mma16816(dp[nt], va[2 * kp], gbf[0], gbf[1]);   // dP^T[key, q]
+                    mma16816(dp[nt], va[2 * kp + 1], gbf[2], gbf[3]);
                 }
             }
             uint32_t pa[2][4], dsa[2][4];
@@ -364,40 +364,54 @@ __global__ void __launch_bounds__(576) attn_bwd_mma_kernel(const bf16* __restric
     }
 }
 
-int attn_spatial_fwd_mma(const void* qkv, void* o, float* lse, int frames, int n, int heads, cudaStream_t s) {
-    int npad = (n + 31) & ~31;
-    int nwarps = (n + 15) / 16;
-    if (nwarps * 32 > 576) return AIMB_ERR_UNSUPPORTED;
-    size_t smem = (size_t)3 * npad * LDS * 2;
-    if (smem > 227 * 1024) return AIMB_ERR_UNSUPPORTED;
+template <int NW>
+static int fwd_launch(const void* qkv, void* o, float* lse, int frames, int n, int heads, size_t smem, cudaStream_t s) {
     static bool attr_set = false;   // once: not a stream operation, keeps the launch path capture-safe
     if (!attr_set) {
-        if (cudaFuncSetAttribute(attn_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+        if (cudaFuncSetAttribute(attn_fwd_mma_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
             return AIMB_ERR_CUDA;
         attr_set = true;
     }
-    attn_fwd_mma_kernel<<<frames * heads, nwarps * 32, smem, s>>>((const bf16*)qkv, (bf16*)o, lse, n, heads);
+    attn_fwd_mma_kernel<NW><<<frames * heads, ((n + 15) / 16) * 32, smem, s>>>((const bf16*)qkv, (bf16*)o, lse, n, heads);
     AIMB_CHECK_LAUNCH();
     return AIMB_OK;
+}
+template <int NW>
+static int bwd_launch(const void* qkv, const void* o, const void* d_o, const float* lse, void* d_qkv, int frames, int n,
+                      int heads, size_t smem, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(attn_bwd_mma_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+            return AIMB_ERR_CUDA;
+        attr_set = true;
+    }
+    attn_bwd_mma_kernel<NW><<<frames * heads, ((n + 15) / 16) * 32, smem, s>>>((const bf16*)qkv, (const bf16*)o, (const bf16*)d_o,
+                                                                            lse, (bf16*)d_qkv, n, heads);
+    AIMB_CHECK_LAUNCH();
+    return AIMB_OK;
+}
+
+// one warp per 16 query (or key) rows; kernels are compiled for the warp counts of the supported token counts
+// (n <= 128: toy sizes, 197 -> 13 warps: ViT-B/16, 257 -> 17 warps: ViT-L/14) so launch bounds fit the registers.
+int attn_spatial_fwd_mma(const void* qkv, void* o, float* lse, int frames, int n, int heads, cudaStream_t s) {
+    int npad = (n + 31) & ~31;
+    int nwarps = (n + 15) / 16;
+    size_t smem = (size_t)3 * npad * LDS * 2;
+    if (smem > 227 * 1024 || nwarps > 17) return AIMB_ERR_UNSUPPORTED;
+    if (nwarps <= 8) return fwd_launch<8>(qkv, o, lse, frames, n, heads, smem, s);
+    if (nwarps <= 13) return fwd_launch<13>(qkv, o, lse, frames, n, heads, smem, s);
+    return fwd_launch<17>(qkv, o, lse, frames, n, heads, smem, s);
 }
 
 int attn_spatial_bwd_mma(const void* qkv, const void* o, const void* d_o, const float* lse, void* d_qkv, int frames, int n,
                          int heads, cudaStream_t s) {
     int npad = (n + 31) & ~31;
     int nwarps = (n + 15) / 16;
-    if (nwarps * 32 > 576) return AIMB_ERR_UNSUPPORTED;
     size_t smem = (size_t)4 * npad * LDS * 2 + (size_t)2 * npad * 4;
-    if (smem > 227 * 1024) return AIMB_ERR_UNSUPPORTED;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(attn_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-            return AIMB_ERR_CUDA;
-        attr_set = true;
-    }
-    attn_bwd_mma_kernel<<<frames * heads, nwarps * 32, smem, s>>>((const bf16*)qkv, (const bf16*)o, (const bf16*)d_o, lse,
-                                                                  (bf16*)d_qkv, n, heads);
-    AIMB_CHECK_LAUNCH();
-    return AIMB_OK;
+    if (smem > 227 * 1024 || nwarps > 17) return AIMB_ERR_UNSUPPORTED;
+    if (nwarps <= 8) return bwd_launch<8>(qkv, o, d_o, lse, d_qkv, frames, n, heads, smem, s);
+    if (nwarps <= 13) return bwd_launch<13>(qkv, o, d_o, lse, d_qkv, frames, n, heads, smem, s);
+    return bwd_launch<17>(qkv, o, d_o, lse, d_qkv, frames, n, heads, smem, s);
 }
 
 }  // namespace aimb

@@ -192,11 +192,41 @@ __global__ void __launch_bounds__(256) attn_spatial_bwd_simt(const T* __restrict
     }
 }
 
-// ------------------------------------------------------------------ temporal forward: warp per (b, token, head)
-template <typename T>
-__global__ void __launch_bounds__(128) attn_temporal_fwd_kernel(const T* __restrict__ qkv, T* __restrict__ o, int B,
-                                                                int T_, int n, int heads) {
-    extern __shared__ float sm[];
+// ------------------------------------------------------------------ temporal attention: warp per (b, token, head)
+// T_ (frames) is a template parameter (4/8/16/32).  Per warp: Q/K/V (and dO) rows of the sequence are staged in
+// shared memory as fp32 [T][68] (16-byte aligned rows, 128-byte coalesced global reads of each row-head slice),
+// the T x T scores are produced by lanes owning (i, j) pairs with float4 dot products, and the P.V products by
+// lanes owning two head-dim columns.
+constexpr int TKS = DH + 4;   // smem row stride (floats): keeps float4 alignment, conflict-free for the patterns used
+
+template <typename T> __device__ __forceinline__ float2 ld_pair(const T* p);
+template <> __device__ __forceinline__ float2 ld_pair<float>(const float* p) { return *reinterpret_cast<const float2*>(p); }
+template <> __device__ __forceinline__ float2 ld_pair<bf16>(const bf16* p) {
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+}
+template <typename T> __device__ __forceinline__ void st_pair(T* p, float a, float b);
+template <> __device__ __forceinline__ void st_pair<float>(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+template <> __device__ __forceinline__ void st_pair<bf16>(bf16* p, float a, float b) {
+    *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+}
+__device__ __forceinline__ float dot64(const float* a, const float* b) {
+    float acc = 0.f;
+#pragma unroll
+    for (int d = 0; d < DH; d += 4) {
+        float4 x = *reinterpret_cast<const float4*>(a + d), y = *reinterpret_cast<const float4*>(b + d);
+        acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+    }
+    return acc;
+}
+
+template <typename T, int T_>
+__global__ void __launch_bounds__(128) attn_temporal_fwd_kernel(const T* __restrict__ qkv, T* __restrict__ o, int B, int n,
+                                                                int heads) {
+    extern __shared__ __align__(16) float sm[];
+    constexpr int PS = T_ + 4;
+    constexpr int UI = T_ <= 8 ? T_ : 2;      // outer-loop unroll: full only for short sequences (register pressure)
+    constexpr int UP = T_ <= 8 ? (T_ * T_ + 31) / 32 : 1;
+    constexpr int PER_WARP = 3 * T_ * TKS + T_ * PS;
     const int D = heads * DH, ld = 3 * D;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t prob = (int64_t)blockIdx.x * 4 + warp;
@@ -204,56 +234,67 @@ __global__ void __launch_bounds__(128) attn_temporal_fwd_kernel(const T* __restr
     const int h = (int)(prob % heads);
     const int tok = (int)((prob / heads) % n);
     const int b = (int)(prob / ((int64_t)heads * n));
-    const int per_warp = 3 * T_ * KS + T_ * (T_ + 1);
-    float* sQ = sm + warp * per_warp;
-    float* sK = sQ + T_ * KS;
-    float* sV = sK + T_ * KS;
-    float* sS = sV + T_ * KS;
+    float* sQ = sm + warp * PER_WARP;
+    float* sK = sQ + T_ * TKS;
+    float* sV = sK + T_ * TKS;
+    float* sS = sV + T_ * TKS;
     const int64_t row0 = (int64_t)b * T_ * n + tok;   // row of frame t: row0 + t*n
-    const T* base = qkv + row0 * ld + h * DH;
+    const T* base = qkv + row0 * ld + h * DH + 2 * lane;
     const int64_t rs = (int64_t)n * ld;
+#pragma unroll
     for (int t = 0; t < T_; ++t) {
         const T* r = base + t * rs;
-        sQ[t * KS + lane] = ldf<T>(r + lane);           sQ[t * KS + lane + 32] = ldf<T>(r + lane + 32);
-        sK[t * KS + lane] = ldf<T>(r + D + lane);       sK[t * KS + lane + 32] = ldf<T>(r + D + lane + 32);
-        sV[t * KS + lane] = ldf<T>(r + 2 * D + lane);   sV[t * KS + lane + 32] = ldf<T>(r + 2 * D + lane + 32);
+        *reinterpret_cast<float2*>(sQ + t * TKS + 2 * lane) = ld_pair<T>(r);
+        *reinterpret_cast<float2*>(sK + t * TKS + 2 * lane) = ld_pair<T>(r + D);
+        *reinterpret_cast<float2*>(sV + t * TKS + 2 * lane) = ld_pair<T>(r + 2 * D);
     }
     __syncwarp();
+#pragma unroll UP
     for (int p = lane; p < T_ * T_; p += 32) {
-        int i = p / T_, j = p % T_;
-        float acc = 0.f;
-#pragma unroll 16
-        for (int d = 0; d < DH; ++d) acc = fmaf(sQ[i * KS + d], sK[j * KS + d], acc);
-        sS[i * (T_ + 1) + j] = acc * ATT_SCALE;
+        const int i = p / T_, j = p % T_;
+        sS[i * PS + j] = dot64(sQ + i * TKS, sK + j * TKS) * ATT_SCALE;
     }
     __syncwarp();
     if (lane < T_) {
-        float* row = sS + lane * (T_ + 1);
+        float* row = sS + lane * PS;
         float mx = -INFINITY;
+#pragma unroll
         for (int j = 0; j < T_; ++j) mx = fmaxf(mx, row[j]);
         float sum = 0.f;
+#pragma unroll
         for (int j = 0; j < T_; ++j) { float e = __expf(row[j] - mx); row[j] = e; sum += e; }
-        float inv = 1.f / sum;
+        const float inv = 1.f / sum;
+#pragma unroll
         for (int j = 0; j < T_; ++j) row[j] *= inv;
     }
     __syncwarp();
-    T* obase = o + row0 * D + h * DH;
+    float2 vr[T_];
+#pragma unroll
+    for (int j = 0; j < T_; ++j) vr[j] = *reinterpret_cast<const float2*>(sV + j * TKS + 2 * lane);
+    T* obase = o + row0 * D + h * DH + 2 * lane;
+#pragma unroll UI
     for (int i = 0; i < T_; ++i) {
         float o0 = 0.f, o1 = 0.f;
-        for (int j = 0; j < T_; ++j) {
-            float p = sS[i * (T_ + 1) + j];
-            o0 = fmaf(p, sV[j * KS + lane], o0);
-            o1 = fmaf(p, sV[j * KS + lane + 32], o1);
+#pragma unroll
+        for (int j = 0; j < T_; j += 4) {
+            const float4 p = *reinterpret_cast<const float4*>(sS + i * PS + j);
+            o0 = fmaf(p.x, vr[j].x, o0); o1 = fmaf(p.x, vr[j].y, o1);
+            o0 = fmaf(p.y, vr[j + 1].x, o0); o1 = fmaf(p.y, vr[j + 1].y, o1);
+            o0 = fmaf(p.z, vr[j + 2].x, o0); o1 = fmaf(p.z, vr[j + 2].y, o1);
+            o0 = fmaf(p.w, vr[j + 3].x, o0); o1 = fmaf(p.w, vr[j + 3].y, o1);
         }
-        stf<T>(obase + (int64_t)i * n * D + lane, o0);
-        stf<T>(obase + (int64_t)i * n * D + lane + 32, o1);
+        st_pair<T>(obase + (int64_t)i * n * D, o0, o1);
     }
 }
 
-template <typename T>
+template <typename T, int T_>
 __global__ void __launch_bounds__(128) attn_temporal_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ d_o,
-                                                                T* __restrict__ d_qkv, int B, int T_, int n, int heads) {
-    extern __shared__ float sm[];
+                                                                T* __restrict__ d_qkv, int B, int n, int heads) {
+    extern __shared__ __align__(16) float sm[];
+    constexpr int PS = T_ + 4;
+    constexpr int UI = T_ <= 8 ? T_ : 2;      // outer-loop unroll: full only for short sequences (register pressure)
+    constexpr int UP = T_ <= 8 ? (T_ * T_ + 31) / 32 : 1;
+    constexpr int PER_WARP = 4 * T_ * TKS + 2 * T_ * PS;
     const int D = heads * DH, ld = 3 * D;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t prob = (int64_t)blockIdx.x * 4 + warp;
@@ -261,70 +302,143 @@ __global__ void __launch_bounds__(128) attn_temporal_bwd_kernel(const T* __restr
     const int h = (int)(prob % heads);
     const int tok = (int)((prob / heads) % n);
     const int b = (int)(prob / ((int64_t)heads * n));
-    const int per_warp = 4 * T_ * KS + 2 * T_ * (T_ + 1);
-    float* sQ = sm + warp * per_warp;
-    float* sK = sQ + T_ * KS;
-    float* sV = sK + T_ * KS;
-    float* sG = sV + T_ * KS;            // dO
-    float* sP = sG + T_ * KS;            // probabilities
-    float* sD = sP + T_ * (T_ + 1);      // dP then dS
+    float* sQ = sm + warp * PER_WARP;
+    float* sK = sQ + T_ * TKS;
+    float* sV = sK + T_ * TKS;
+    float* sG = sV + T_ * TKS;            // dO
+    float* sP = sG + T_ * TKS;            // probabilities
+    float* sD = sP + T_ * PS;             // dP then dS
     const int64_t row0 = (int64_t)b * T_ * n + tok;
-    const T* base = qkv + row0 * ld + h * DH;
-    const T* gbase = d_o + row0 * D + h * DH;
+    const T* base = qkv + row0 * ld + h * DH + 2 * lane;
+    const T* gbase = d_o + row0 * D + h * DH + 2 * lane;
     const int64_t rs = (int64_t)n * ld;
+#pragma unroll
     for (int t = 0; t < T_; ++t) {
         const T* r = base + t * rs;
-        const T* g = gbase + (int64_t)t * n * D;
-        sQ[t * KS + lane] = ldf<T>(r + lane);           sQ[t * KS + lane + 32] = ldf<T>(r + lane + 32);
-        sK[t * KS + lane] = ldf<T>(r + D + lane);       sK[t * KS + lane + 32] = ldf<T>(r + D + lane + 32);
-        sV[t * KS + lane] = ldf<T>(r + 2 * D + lane);   sV[t * KS + lane + 32] = ldf<T>(r + 2 * D + lane + 32);
-        sG[t * KS + lane] = ldf<T>(g + lane);           sG[t * KS + lane + 32] = ldf<T>(g + lane + 32);
+        *reinterpret_cast<float2*>(sQ + t * TKS + 2 * lane) = ld_pair<T>(r);
+        *reinterpret_cast<float2*>(sK + t * TKS + 2 * lane) = ld_pair<T>(r + D);
+        *reinterpret_cast<float2*>(sV + t * TKS + 2 * lane) = ld_pair<T>(r + 2 * D);
+        *reinterpret_cast<float2*>(sG + t * TKS + 2 * lane) = ld_pair<T>(gbase + (int64_t)t * n * D);
     }
     __syncwarp();
-    const int TS = T_ + 1;
+#pragma unroll UP
     for (int p = lane; p < T_ * T_; p += 32) {
-        int i = p / T_, j = p % T_;
-        float sc = 0.f, dp = 0.f;
-#pragma unroll 16
-        for (int d = 0; d < DH; ++d) {
-            sc = fmaf(sQ[i * KS + d], sK[j * KS + d], sc);
-            dp = fmaf(sG[i * KS + d], sV[j * KS + d], dp);
-        }
-        sP[i * TS + j] = sc * ATT_SCALE;
-        sD[i * TS + j] = dp;
+        const int i = p / T_, j = p % T_;
+        sP[i * PS + j] = dot64(sQ + i * TKS, sK + j * TKS) * ATT_SCALE;
+        sD[i * PS + j] = dot64(sG + i * TKS, sV + j * TKS);
     }
     __syncwarp();
     if (lane < T_) {
-        float* row = sP + lane * TS;
-        float* drow = sD + lane * TS;
+        float* row = sP + lane * PS;
+        float* drow = sD + lane * PS;
         float mx = -INFINITY;
+#pragma unroll
         for (int j = 0; j < T_; ++j) mx = fmaxf(mx, row[j]);
         float sum = 0.f;
+#pragma unroll
         for (int j = 0; j < T_; ++j) { float e = __expf(row[j] - mx); row[j] = e; sum += e; }
-        float inv = 1.f / sum, delta = 0.f;
+        const float inv = 1.f / sum;
+        float delta = 0.f;
+#pragma unroll
         for (int j = 0; j < T_; ++j) { row[j] *= inv; delta = fmaf(row[j], drow[j], delta); }
+#pragma unroll
         for (int j = 0; j < T_; ++j) drow[j] = row[j] * (drow[j] - delta) * ATT_SCALE;
     }
     __syncwarp();
-    T* dbase = d_qkv + row0 * ld + h * DH;
+    T* dbase = d_qkv + row0 * ld + h * DH + 2 * lane;
+    float2 reg[T_];
+    // dQ_i = sum_j dS_ij K_j     (rows of dS)
+#pragma unroll
+    for (int j = 0; j < T_; ++j) reg[j] = *reinterpret_cast<const float2*>(sK + j * TKS + 2 * lane);
+#pragma unroll UI
     for (int i = 0; i < T_; ++i) {
-        float q0 = 0.f, q1 = 0.f, k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
-        for (int j = 0; j < T_; ++j) {
-            float ds_ij = sD[i * TS + j];   // row i: dQ_i += dS_ij K_j
-            q0 = fmaf(ds_ij, sK[j * KS + lane], q0);
-            q1 = fmaf(ds_ij, sK[j * KS + lane + 32], q1);
-            float ds_ji = sD[j * TS + i];   // column i: dK_i += dS_ji Q_j ; dV_i += P_ji dO_j
-            float p_ji = sP[j * TS + i];
-            k0 = fmaf(ds_ji, sQ[j * KS + lane], k0);
-            k1 = fmaf(ds_ji, sQ[j * KS + lane + 32], k1);
-            v0 = fmaf(p_ji, sG[j * KS + lane], v0);
-            v1 = fmaf(p_ji, sG[j * KS + lane + 32], v1);
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < T_; j += 4) {
+            const float4 c = *reinterpret_cast<const float4*>(sD + i * PS + j);
+            a0 = fmaf(c.x, reg[j].x, a0); a1 = fmaf(c.x, reg[j].y, a1);
+            a0 = fmaf(c.y, reg[j + 1].x, a0); a1 = fmaf(c.y, reg[j + 1].y, a1);
+            a0 = fmaf(c.z, reg[j + 2].x, a0); a1 = fmaf(c.z, reg[j + 2].y, a1);
+            a0 = fmaf(c.w, reg[j + 3].x, a0); a1 = fmaf(c.w, reg[j + 3].y, a1);
         }
-        T* r = dbase + i * rs;
-        stf<T>(r + lane, q0);            stf<T>(r + lane + 32, q1);
-        stf<T>(r + D + lane, k0);        stf<T>(r + D + lane + 32, k1);
-        stf<T>(r + 2 * D + lane, v0);    stf<T>(r + 2 * D + lane + 32, v1);
+        st_pair<T>(dbase + i * rs, a0, a1);
     }
+    // dK_i = sum_j dS_ji Q_j     (columns of dS)
+#pragma unroll
+    for (int j = 0; j < T_; ++j) reg[j] = *reinterpret_cast<const float2*>(sQ + j * TKS + 2 * lane);
+#pragma unroll UI
+    for (int i = 0; i < T_; ++i) {
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < T_; ++j) {
+            const float c = sD[j * PS + i];
+            a0 = fmaf(c, reg[j].x, a0); a1 = fmaf(c, reg[j].y, a1);
+        }
+        st_pair<T>(dbase + i * rs + D, a0, a1);
+    }
+    // dV_i = sum_j P_ji dO_j     (columns of P)
+#pragma unroll
+    for (int j = 0; j < T_; ++j) reg[j] = *reinterpret_cast<const float2*>(sG + j * TKS + 2 * lane);
+#pragma unroll UI
+    for (int i = 0; i < T_; ++i) {
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < T_; ++j) {
+            const float c = sP[j * PS + i];
+            a0 = fmaf(c, reg[j].x, a0); a1 = fmaf(c, reg[j].y, a1);
+        }
+        st_pair<T>(dbase + i * rs + 2 * D, a0, a1);
+    }
+}
+
+template <typename T, int T_>
+static int temporal_fwd_launch(const void* qkv, void* o, int B, int n, int heads, cudaStream_t s) {
+    constexpr size_t smem = (size_t)4 * (3 * T_ * TKS + T_ * (T_ + 4)) * 4;
+    static bool once = false;
+    if (!once) {
+        if (cudaFuncSetAttribute(attn_temporal_fwd_kernel<T, T_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return AIMB_ERR_CUDA;
+        once = true;
+    }
+    int64_t probs = (int64_t)B * n * heads;
+    attn_temporal_fwd_kernel<T, T_><<<(unsigned)((probs + 3) / 4), 128, smem, s>>>((const T*)qkv, (T*)o, B, n, heads);
+    AIMB_CHECK_LAUNCH();
+    return AIMB_OK;
+}
+template <typename T, int T_>
+static int temporal_bwd_launch(const void* qkv, const void* d_o, void* d_qkv, int B, int n, int heads, cudaStream_t s) {
+    constexpr size_t smem = (size_t)4 * (4 * T_ * TKS + 2 * T_ * (T_ + 4)) * 4;
+    static bool once = false;
+    if (!once) {
+        if (cudaFuncSetAttribute(attn_temporal_bwd_kernel<T, T_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return AIMB_ERR_CUDA;
+        once = true;
+    }
+    int64_t probs = (int64_t)B * n * heads;
+    attn_temporal_bwd_kernel<T, T_><<<(unsigned)((probs + 3) / 4), 128, smem, s>>>((const T*)qkv, (const T*)d_o, (T*)d_qkv, B, n,
+                                                                                   heads);
+    AIMB_CHECK_LAUNCH();
+    return AIMB_OK;
+}
+template <typename T>
+static int temporal_fwd_T(const void* qkv, void* o, int B, int T_, int n, int heads, cudaStream_t s) {
+    switch (T_) {
+        case 4: return temporal_fwd_launch<T, 4>(qkv, o, B, n, heads, s);
+        case 8: return temporal_fwd_launch<T, 8>(qkv, o, B, n, heads, s);
+        case 16: return temporal_fwd_launch<T, 16>(qkv, o, B, n, heads, s);
+        case 32: return temporal_fwd_launch<T, 32>(qkv, o, B, n, heads, s);
+    }
+    return AIMB_ERR_UNSUPPORTED;
+}
+template <typename T>
+static int temporal_bwd_T(const void* qkv, const void* d_o, void* d_qkv, int B, int T_, int n, int heads, cudaStream_t s) {
+    switch (T_) {
+        case 4: return temporal_bwd_launch<T, 4>(qkv, d_o, d_qkv, B, n, heads, s);
+        case 8: return temporal_bwd_launch<T, 8>(qkv, d_o, d_qkv, B, n, heads, s);
+        case 16: return temporal_bwd_launch<T, 16>(qkv, d_o, d_qkv, B, n, heads, s);
+        case 32: return temporal_bwd_launch<T, 32>(qkv, d_o, d_qkv, B, n, heads, s);
+    }
+    return AIMB_ERR_UNSUPPORTED;
 }
 
 // ------------------------------------------------------------------ fork block weights (vit_clip.py:147-151,182-186)
@@ -416,66 +530,22 @@ using namespace aimb;
 
 extern "C" int aimb_attn_temporal_fwd(const void* qkv, void* o, int32_t B, int32_t T, int32_t n, int32_t heads,
                                       int32_t dtype, void* stream) {
-    if (!qkv || !o || B < 0 || T <= 0 || T > 32 || n <= 0 || heads <= 0) return AIMB_ERR_ARG;
+    if (!qkv || !o || B < 0 || T <= 0 || n <= 0 || heads <= 0) return AIMB_ERR_ARG;
     if (B == 0) return AIMB_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    size_t smem = (size_t)4 * (3 * T * KS + T * (T + 1)) * 4;
-    int64_t probs = (int64_t)B * n * heads;
-    unsigned grid = (unsigned)((probs + 3) / 4);
-    cudaError_t e = cudaSuccess;
-    (void)e;
-    if (dtype == AIMB_BF16) {
-        static bool once = false;
-        if (!once) {
-            e = cudaFuncSetAttribute(attn_temporal_fwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            if (e != cudaSuccess) return AIMB_ERR_CUDA;
-            once = true;
-        }
-        attn_temporal_fwd_kernel<bf16><<<grid, 128, smem, s>>>((const bf16*)qkv, (bf16*)o, B, T, n, heads);
-    } else if (dtype == AIMB_F32) {
-        static bool once = false;
-        if (!once) {
-            e = cudaFuncSetAttribute(attn_temporal_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            if (e != cudaSuccess) return AIMB_ERR_CUDA;
-            once = true;
-        }
-        attn_temporal_fwd_kernel<float><<<grid, 128, smem, s>>>((const float*)qkv, (float*)o, B, T, n, heads);
-    } else return AIMB_ERR_ARG;
-    AIMB_CHECK_LAUNCH();
-    return AIMB_OK;
+    if (dtype == AIMB_BF16) return temporal_fwd_T<bf16>(qkv, o, B, T, n, heads, s);
+    if (dtype == AIMB_F32) return temporal_fwd_T<float>(qkv, o, B, T, n, heads, s);
+    return AIMB_ERR_ARG;
 }
 
 extern "C" int aimb_attn_temporal_bwd(const void* qkv, const void* d_o, void* d_qkv, int32_t B, int32_t T, int32_t n,
                                       int32_t heads, int32_t dtype, void* stream) {
-    if (!qkv || !d_o || !d_qkv || B < 0 || T <= 0 || T > 32 || n <= 0 || heads <= 0) return AIMB_ERR_ARG;
+    if (!qkv || !d_o || !d_qkv || B < 0 || T <= 0 || n <= 0 || heads <= 0) return AIMB_ERR_ARG;
     if (B == 0) return AIMB_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    size_t smem = (size_t)4 * (4 * T * KS + 2 * T * (T + 1)) * 4;
-    int64_t probs = (int64_t)B * n * heads;
-    unsigned grid = (unsigned)((probs + 3) / 4);
-    cudaError_t e = cudaSuccess;
-    (void)e;
-    if (dtype == AIMB_BF16) {
-        static bool once = false;
-        if (!once) {
-            e = cudaFuncSetAttribute(attn_temporal_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            if (e != cudaSuccess) return AIMB_ERR_CUDA;
-            once = true;
-        }
-        attn_temporal_bwd_kernel<bf16><<<grid, 128, smem, s>>>((const bf16*)qkv, (const bf16*)d_o, (bf16*)d_qkv, B, T, n,
-                                                               heads);
-    } else if (dtype == AIMB_F32) {
-        static bool once = false;
-        if (!once) {
-            e = cudaFuncSetAttribute(attn_temporal_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            if (e != cudaSuccess) return AIMB_ERR_CUDA;
-            once = true;
-        }
-        attn_temporal_bwd_kernel<float><<<grid, 128, smem, s>>>((const float*)qkv, (const float*)d_o, (float*)d_qkv, B, T,
-                                                                n, heads);
-    } else return AIMB_ERR_ARG;
-    AIMB_CHECK_LAUNCH();
-    return AIMB_OK;
+    if (dtype == AIMB_BF16) return temporal_bwd_T<bf16>(qkv, d_o, d_qkv, B, T, n, heads, s);
+    if (dtype == AIMB_F32) return temporal_bwd_T<float>(qkv, d_o, d_qkv, B, T, n, heads, s);
+    return AIMB_ERR_ARG;
 }
 
 extern "C" int aimb_fork_weights(const void* qkv, const void* kc, float* w_o, float* w_c, int32_t frames, int32_t n,

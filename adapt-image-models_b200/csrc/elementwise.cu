@@ -309,29 +309,67 @@ __global__ void __launch_bounds__(128) tail_bwd_kernel(const float* __restrict__
 }
 
 // ------------------------------------------------------------------ column sums (bias grads, temporal-embedding grad)
-// block = 32 (columns) x 8 (row lanes); each block reduces ROWS rows of 32 columns, then one atomicAdd per column.
+// block = 32 lanes (each a 16-byte column vector) x 8 row lanes; every block reduces `rows_per_block` rows of
+// 32 column vectors, then one atomicAdd per column.
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, int64_t ld,
                                                      const float* __restrict__ row_scale, int row_mod, float alpha,
                                                      float* __restrict__ out, int64_t R, int C, int rows_per_block) {
-    __shared__ float red[8][33];
-    int c = blockIdx.x * 32 + threadIdx.x;
+    constexpr int V = VecIO<T>::N;
+    __shared__ float red[8][32][V + 1];
+    const int c = (blockIdx.x * 32 + threadIdx.x) * V;
     int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
     int64_t r1 = r0 + rows_per_block < R ? r0 + rows_per_block : R;
-    float s = 0.f;
+    float s[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) s[j] = 0.f;
     if (c < C)
         for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
-            float v = ldf<T>(x + r * ld + c);
-            if (row_scale) v *= row_scale[r % row_mod];
-            s += v;
+            float v[V];
+            VecIO<T>::ld(x + r * ld + c, v);
+            float w = row_scale ? row_scale[r % row_mod] : 1.f;
+#pragma unroll
+            for (int j = 0; j < V; ++j) s[j] = fmaf(v[j], w, s[j]);
         }
-    red[threadIdx.y][threadIdx.x] = s;
+#pragma unroll
+    for (int j = 0; j < V; ++j) red[threadIdx.y][threadIdx.x][j] = s[j];
     __syncthreads();
     if (threadIdx.y == 0 && c < C) {
-        float t = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
-        atomicAdd(out + c, alpha * t);
+        for (int j = 0; j < V; ++j) {
+            float t = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x][j];
+            atomicAdd(out + c + j, alpha * t);
+        }
+    }
+}
+
+// Batched 2-D transposes in one launch: matrix b (blockIdx.z) is src + table[3b] of shape [table[3b+1], table[3b+2]],
+// written transposed at the same element offset in dst.  (All adapter weights of a step: 6 per block.)
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_batched_kernel(const T* __restrict__ src, T* __restrict__ dst,
+                                                                const int64_t* __restrict__ table) {
+    __shared__ T tile[32][33];
+    const int64_t off = table[3 * blockIdx.z];
+    const int R = (int)table[3 * blockIdx.z + 1], C = (int)table[3 * blockIdx.z + 2];
+    const T* in = src + off;
+    T* out = dst + off;
+    const int tiles_c = (C + 31) / 32, tiles_r = (R + 31) / 32;
+    for (int tidx = blockIdx.x; tidx < tiles_c * tiles_r; tidx += gridDim.x) {
+        const int bx = tidx % tiles_c, by = tidx / tiles_c;
+        int c = bx * 32 + threadIdx.x;
+        for (int i = threadIdx.y; i < 32; i += 8) {
+            int r = by * 32 + i;
+            if (r < R && c < C) tile[i][threadIdx.x] = in[(int64_t)r * C + c];
+        }
+        __syncthreads();
+        int r = by * 32 + threadIdx.x;
+        for (int i = threadIdx.y; i < 32; i += 8) {
+            int cc = bx * 32 + i;
+            if (r < R && cc < C) out[(int64_t)cc * R + r] = tile[threadIdx.x][i];
+        }
+        __syncthreads();
     }
 }
 
@@ -508,15 +546,34 @@ extern "C" int aimb_tail_bwd(const float* dfeat, const void* x, const float* mea
 extern "C" int aimb_colsum(const void* x, int64_t ld, const float* row_scale, int32_t row_mod, float alpha, float* out,
                            int64_t R, int32_t C, int32_t accumulate, int32_t dtype, void* stream) {
     if (!x || !out || R < 0 || C <= 0 || ld < C || (row_scale && row_mod <= 0)) return AIMB_ERR_ARG;
+    const int V = dtype == AIMB_BF16 ? 8 : 4;
+    if (C % V || ld % V || ((uintptr_t)x & 15)) return AIMB_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     if (!accumulate && cudaMemsetAsync(out, 0, (size_t)C * 4, s) != cudaSuccess) return AIMB_ERR_CUDA;
     if (R == 0) return AIMB_OK;
-    const int rpb = 256;
-    dim3 grid((C + 31) / 32, (unsigned)((R + rpb - 1) / rpb)), block(32, 8);
+    const int gx = (C / V + 31) / 32;
+    int rpb = 128;
+    while (rpb > 16 && (int64_t)gx * ((R + rpb - 1) / rpb) < 296) rpb >>= 1;   // >= 2 waves of blocks
+    dim3 grid(gx, (unsigned)((R + rpb - 1) / rpb)), block(32, 8);
     if (dtype == AIMB_BF16)
         colsum_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)x, ld, row_scale, row_mod, alpha, out, R, C, rpb);
     else if (dtype == AIMB_F32)
         colsum_kernel<float><<<grid, block, 0, s>>>((const float*)x, ld, row_scale, row_mod, alpha, out, R, C, rpb);
+    else return AIMB_ERR_ARG;
+    AIMB_CHECK_LAUNCH();
+    return AIMB_OK;
+}
+
+extern "C" int aimb_transpose_batched(const void* src, void* dst, const int64_t* table, int32_t nmat, int32_t dtype,
+                                      void* stream) {
+    if (!src || !dst || !table || nmat < 0) return AIMB_ERR_ARG;
+    if (nmat == 0) return AIMB_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    dim3 grid(48, 1, nmat), block(32, 8);
+    if (dtype == AIMB_BF16)
+        transpose_batched_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)src, (bf16*)dst, table);
+    else if (dtype == AIMB_F32)
+        transpose_batched_kernel<float><<<grid, block, 0, s>>>((const float*)src, (float*)dst, table);
     else return AIMB_ERR_ARG;
     AIMB_CHECK_LAUNCH();
     return AIMB_OK;

@@ -690,7 +690,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
     constexpr int TCOLS = NS <= 64 ? 64 : NS <= 128 ? 128 : 256;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a __shared__ pointer
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STG);
+    float* wstg = reinterpret_cast<float*>(smem + STAGES * STG);                 // 4 warps x [32][33] fp32
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STG + 4 * 32 * 33 * 4);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* done_bar = empty_bar + STAGES;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done_bar + 1);
@@ -759,9 +760,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
             if (transposed_out) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) atomicAdd(out + (int64_t)(c + j) * ldo + m, alpha * __uint_as_float(r[j]));
-            } else {
+            } else {    // rows of the result are contiguous: transpose through smem so each red covers 32 floats of a row
+                float* st = wstg + quad * (32 * 33);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) atomicAdd(out + (int64_t)m * ldo + c + j, alpha * __uint_as_float(r[j]));
+                for (int j = 0; j < 32; ++j) st[lane * 33 + j] = alpha * __uint_as_float(r[j]);
+                __syncwarp();
+                const int64_t m0 = (int64_t)mt * 128 + quad * 32;
+#pragma unroll 4
+                for (int rr = 0; rr < 32; ++rr) atomicAdd(out + (m0 + rr) * ldo + c + lane, st[rr * 33 + lane]);
+                __syncwarp();
             }
         }
     }
@@ -779,7 +786,7 @@ static int launch_wgrad(const CUtensorMap& tp, const CUtensorMap& tq, float* out
     constexpr int BOX = 64 * 64 * 2;
     constexpr int STG = 2 * BOX + (NS / 64) * BOX;
     constexpr int STAGES = (200 * 1024) / STG > 6 ? 6 : (200 * 1024) / STG;
-    constexpr int SMEM = STAGES * STG + 1024 + 256;
+    constexpr int SMEM = STAGES * STG + 4 * 32 * 33 * 4 + 1024 + 256;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(wgrad_tc_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess)

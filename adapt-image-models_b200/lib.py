@@ -51,6 +51,7 @@ SIGNATURES = {
     "aimb_gemm_wgrad": [_P, _L, _P, _L, _P, _L, _I, _I, _F, _I, _I, _I, _P],
     "aimb_colsum": [_P, _L, _P, _I, _F, _P, _L, _I, _I, _I, _P],
     "aimb_transpose": [_P, _P, _I, _I, _I, _P],
+    "aimb_transpose_batched": [_P, _P, _P, _I, _I, _P],
     "aimb_attn_spatial_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "aimb_attn_spatial_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "aimb_attn_temporal_fwd": [_P, _P, _I, _I, _I, _I, _I, _P],
@@ -233,6 +234,14 @@ def transpose(src, dst):
     _count()
     _chk(load().aimb_transpose(_ptr(_c(src)), _ptr(_c(dst)), R, Cn, dt_code(src), _stream()), "transpose")
     return dst
+
+
+def transpose_batched(src_flat, dst_flat, table_dev, nmat):
+    """table_dev: int64 CUDA tensor [nmat, 3] = (element offset, rows, cols) into src_flat / dst_flat."""
+    assert table_dev.dtype == torch.int64 and table_dev.is_cuda and src_flat.dtype == dst_flat.dtype
+    _count()
+    _chk(load().aimb_transpose_batched(_ptr(_c(src_flat)), _ptr(_c(dst_flat)), _ptr(table_dev), nmat, dt_code(src_flat),
+                                       _stream()), "transpose_batched")
 
 
 def attn_spatial_fwd(qkv, o, lse, frames, n, heads, impl=IMPL_AUTO):

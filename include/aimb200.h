@@ -123,6 +123,10 @@ int aimb_gemm_wgrad(const void* dY, int64_t ldy, const void* X, int64_t ldx, flo
 int aimb_colsum(const void* x, int64_t ld, const float* row_scale, int32_t row_mod, float alpha, float* out,
                 int64_t R, int32_t C, int32_t accumulate, int32_t dtype, void* stream);
 int aimb_transpose(const void* in, void* out, int32_t R, int32_t C, int32_t dtype, void* stream);
+/* One launch for many transposes (the per-step transposes of the trainable adapter weights for dgrad):
+ * matrix b = src + table[3b] (elements), shape [table[3b+1], table[3b+2]], written transposed at dst + table[3b].
+ * `table` is a DEVICE array of 3*nmat int64. */
+int aimb_transpose_batched(const void* src, void* dst, const int64_t* table, int32_t nmat, int32_t dtype, void* stream);
 
 /* ---- attention cores: vit_clip.py:140-156 (the part between the QKV and out_proj GEMMs) ------ */
 /* Spatial: one softmax(q k^T / 8) v problem per (frame, head); n tokens, head_dim 64.
