@@ -55,7 +55,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
-                                          "100", "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "20", "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -232,16 +232,26 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
-    use_graph = (world == 1 and not args.no_graph)
+    use_graph = not args.no_graph
     step_fn = tr.step
     captured_launches = None
     if use_graph:
         l_before = lib.launches
-        graphed = aimb200.GraphedStep(tr.step, [dev_x, dev_y], warmup=3,
-                                      before_capture=lambda: tr.opt.zero_grad(set_to_none=True))
-        # launches recorded while capturing == launches replayed per step
-        captured_launches = (lib.launches - l_before) // 4
-        step_fn = graphed
+        try:     # the whole step (incl. the bucketed NCCL all-reduces at N>1) replayed as one CUDA graph
+            graphed = aimb200.GraphedStep(tr.step, [dev_x, dev_y], warmup=3,
+                                          before_capture=lambda: tr.opt.zero_grad(set_to_none=True))
+            # launches recorded while capturing == launches replayed per step
+            captured_launches = (lib.launches - l_before) // 4
+            step_fn = graphed
+        except Exception as e:   # noqa: BLE001  (capture unsupported by this NCCL/driver combination -> eager launches)
+            if rank == 0:
+                print(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
+            use_graph = False
+    if world > 1:                # every rank must take the same path
+        flag = torch.tensor([1 if use_graph else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag) == 0 and use_graph:
+            use_graph, step_fn = False, tr.step
 
     def step_resident():
         l2_flush.zero_()
@@ -326,8 +336,20 @@ def run_ours(args):
             out["cpu_baseline"] = {"value": v_cpu, "unit": UNIT, "cores": cores, "kind": "port",
                                    "sample": "2 training steps x 1 clip of the same model on the oracle port (torch CPU fp32)"}
         print(json.dumps(out), flush=True)
+    # Teardown: a captured graph that contains NCCL kernels must be destroyed before the communicator, and a
+    # stuck communicator teardown must never hang the launcher: hard-exit after a grace period.
+    sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
+        import threading as _th
+        _th.Timer(20.0, lambda: os._exit(0)).start()
+        step_fn = None
+        if use_graph:
+            graphed.graph.reset()
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
+        os._exit(0)
 
 
 def main():
