@@ -313,8 +313,12 @@ def run_ours(args):
     gemm_fl = sum(f for _, _, f in recs)
     prof_ms = e0.elapsed_time(e1)
     achieved = gemm_fl / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
+    if os.path.isfile(tp):      # dram__bytes_read+write per GEMM launch from the committed ncu --set full capture
+        traffic = json.load(open(tp)).get("avg_dram_bytes_per_launch")
     roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (TMA + tcgen05/TMEM bf16 GEMM)", "achieved": achieved,
-                "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic, "peak_source": peak_src,
                 "launches_per_step": len(recs) // nprof, "avg_launch_us": gemm_ms * 1e3 / max(1, len(recs)),
                 "share_of_step": gemm_ms / prof_ms,
                 "step_tflops_algorithmic": TFLOP_PER_CLIP_STEP * B / (ms_step / 1e3),

@@ -1,0 +1,55 @@
+"""Summaries of ncu outputs for profiles/.
+  python bench_tools/summarize_ncu.py list gpurun_out/launches_r1.csv > profiles/r1_launch_list.md
+  python bench_tools/summarize_ncu.py full gpurun_out/gemm_r1_final.ncu-rep > profiles/r1_gemm_full.md"""
+import collections
+import csv
+import re
+import subprocess
+import sys
+
+
+def launch_list(path):
+    rows = list(csv.reader(open(path)))
+    hi = [i for i, r in enumerate(rows) if 'Kernel Name' in r][0]
+    hdr = rows[hi]
+    ix = {h: i for i, h in enumerate(hdr)}
+    data = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+    agg = collections.OrderedDict()
+    for r in data:
+        name = re.sub(r'\(.*', '', r[ix['Kernel Name']]).replace('void ', '').replace('aimb::', '')
+        v = float(r[ix['Metric Value']].replace(',', '')) / 1e3   # ns -> us
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    tot = sum(a[1] for a in agg.values())
+    print(f"# ncu launch list: {len(data)} launches, {tot / 1e3:.1f} ms total (cold-cache, serialised: compare SHARES)\n")
+    print("| kernel | launches | total us | share |\n|---|---:|---:|---:|")
+    for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        if t / tot < 0.0005:
+            continue
+        print(f"| `{k[:90]}` | {n} | {t:.1f} | {100 * t / tot:.1f}% |")
+
+
+WANT = ['gpu__time_duration.sum', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+        'dram__bytes_read.sum', 'dram__bytes_write.sum', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__m_xbar2l1tex_read_bytes.sum', 'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',
+        'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum']
+
+
+def full(path):
+    out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    ix = {h: i for i, h in enumerate(hdr)}
+    cols = [c for c in WANT if c in ix]
+    print("# ncu --set full, selected raw metrics per launch\n")
+    print("| kernel | " + " | ".join(c.replace('.avg', '').replace('pct_of_peak_sustained_', '%') for c in cols) + " |")
+    print("|---|" + "---:|" * len(cols))
+    for r in data:
+        name = re.sub(r'\(.*', '', r[ix['Kernel Name']]).replace('void ', '').replace('aimb::', '')
+        print(f"| `{name}` | " + " | ".join(f"{r[ix[c]]} {units[ix[c]]}" for c in cols) + " |")
+
+
+if __name__ == "__main__":
+    {"list": launch_list, "full": full}[sys.argv[1]](sys.argv[2])
