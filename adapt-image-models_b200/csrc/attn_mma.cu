@@ -1,11 +1,15 @@
-// Fused flash-style spatial attention for bf16 (vit_clip.py:140-156): one CTA per (frame, head),
-// the whole K/V (n = 197 or 257 tokens, head_dim 64) resident in shared memory, scores never leave
-// registers.  Tensor-core path: mma.sync m16n8k16 bf16 with fp32 accumulation and fp32 softmax
-// statistics.  Q/K/V are read in place from the fused QKV buffer [M, 3D]; O is written head-major
-// into [M, D] (== permute(2,0,1,3).flatten(2) of the reference) so out_proj consumes it directly.
+// Fused flash-style spatial attention for bf16 (vit_clip.py:140-156).  One (frame, head) problem = n tokens
+// (197 / 257) x head_dim 64; the score matrix never leaves registers.  Tensor-core path: mma.sync m16n8k16 bf16,
+// fp32 accumulation and fp32 softmax statistics.  Q/K/V are read in place from the fused QKV buffer [M, 3D]; O is
+// written head-major into [M, D] (== permute(2,0,1,3).flatten(2) of the reference) so out_proj consumes it directly.
 //
-// Backward runs in the same residency: phase 1 (warp = 16 query rows) recomputes P and produces dQ,
-// phase 2 (warp = 16 key rows) recomputes P^T and produces dK, dV — no atomics, no score matrix in HBM.
+// Work decomposition (round-1 tuning, see profiles/):
+//   forward : a CTA owns up to 8 row tiles (16 query rows each, one warp per tile) of one (frame, head); only K and V
+//             live in shared memory (64.5 KB for n = 197), the warp's own 16 query rows are loaded straight from
+//             global into MMA A-fragments -> 2 CTAs resident per SM, one CTA's load phase overlaps another's math.
+//   backward: one CTA per (frame, head) with Q, K, V, dO in shared memory; phase 1 (warp = 16 query rows) recomputes P
+//             from the saved LSE and produces dQ, phase 2 (warp = 16 key rows) produces dK, dV.  No atomics, no score
+//             matrix in HBM.  (Splitting the phases into separate 2-matrix CTAs was measured slower: 2x smem fills.)
 #include "common.cuh"
 
 namespace aimb {
@@ -38,6 +42,9 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ float2 unpack_bf16(uint32_t v) {
+    return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v));
+}
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_u32(smem)), "l"(gmem));
 }
@@ -45,10 +52,6 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
-// A fragment (16 rows x 16 k) of a row-major [row][k] smem tile; p -> element (row0, k0)
-__device__ __forceinline__ void lda_frag(uint32_t (&a)[4], const bf16* p, int lane) {
-    ldsm_x4(a, p + (lane & 15) * LDS + (lane >> 4) * 8);
-}
 // B fragments for TWO k-steps (k0..k0+31) of an [n][k] smem tile (8 n rows): r0,r1 = k-step 0; r2,r3 = k-step 1
 __device__ __forceinline__ void ldb_frag_nk(uint32_t (&r)[4], const bf16* p, int lane) {
     ldsm_x4(r, p + (lane & 7) * LDS + (lane >> 3) * 8);
@@ -56,6 +59,22 @@ __device__ __forceinline__ void ldb_frag_nk(uint32_t (&r)[4], const bf16* p, int
 // B fragments for TWO n-tiles (n0..n0+15) of a [k][n] smem tile (16 k rows): r0,r1 = n-tile 0; r2,r3 = n-tile 1
 __device__ __forceinline__ void ldb_frag_kn(uint32_t (&r)[4], const bf16* p, int lane) {
     ldsm_x4_t(r, p + ((lane & 7) + ((lane >> 3) & 1) * 8) * LDS + (lane >> 4) * 8);
+}
+
+// A fragments (4 k-steps covering the 64 head dims) of 16 rows read straight from global memory.
+// p -> (row0, col 0) of the warp's tile, `ld` = row stride in elements; rows >= rows_valid read as zero.
+__device__ __forceinline__ void lda_frags_global(uint32_t (&a)[4][4], const bf16* p, int64_t ld, int rows_valid, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    const bool v0 = g < rows_valid, v1 = g + 8 < rows_valid;
+    const bf16* r0 = p + (int64_t)g * ld + 2 * t;
+    const bf16* r1 = r0 + 8 * ld;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        a[ks][0] = v0 ? *reinterpret_cast<const uint32_t*>(r0 + ks * 16) : 0u;
+        a[ks][1] = v1 ? *reinterpret_cast<const uint32_t*>(r1 + ks * 16) : 0u;
+        a[ks][2] = v0 ? *reinterpret_cast<const uint32_t*>(r0 + ks * 16 + 8) : 0u;
+        a[ks][3] = v1 ? *reinterpret_cast<const uint32_t*>(r1 + ks * 16 + 8) : 0u;
+    }
 }
 
 // Load `n` rows x 64 bf16 (row stride `ld` elements in global) into smem [npad][LDS], zero the pad rows.
@@ -68,30 +87,25 @@ __device__ __forceinline__ void load_tile_async(bf16* dst, const bf16* src, int6
 }
 
 // ------------------------------------------------------------------------------------------ forward
-template <int NW>
-__global__ void __launch_bounds__(NW * 32) attn_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o,
-                                                           float* __restrict__ lse, int n, int heads) {
+__global__ void __launch_bounds__(256, 2) attn_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o,
+                                                              float* __restrict__ lse, int n, int heads, int wpc) {
     extern __shared__ __align__(16) uint8_t smraw[];
     const int D = heads * HD, ld = 3 * D;
     const int f = blockIdx.x / heads, h = blockIdx.x % heads;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int npad = (n + 31) & ~31;
-    bf16* sQ = reinterpret_cast<bf16*>(smraw);
-    bf16* sK = sQ + npad * LDS;
+    bf16* sK = reinterpret_cast<bf16*>(smraw);
     bf16* sV = sK + npad * LDS;
     const bf16* base = qkv + (int64_t)f * n * ld + h * HD;
-    load_tile_async(sQ, base, ld, n, npad, tid, blockDim.x);
     load_tile_async(sK, base + D, ld, n, npad, tid, blockDim.x);
     load_tile_async(sV, base + 2 * D, ld, n, npad, tid, blockDim.x);
+    const int q0 = (blockIdx.y * wpc + warp) * 16;
+    uint32_t qa[4][4];
+    if (q0 < n) lda_frags_global(qa, base + (int64_t)q0 * ld, ld, n - q0, lane);
     cp_async_wait_all();
     __syncthreads();
-
-    const int q0 = warp * 16;
     if (q0 >= n) return;
     const int g = lane >> 2, t = lane & 3;
-    uint32_t qa[4][4];
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) lda_frag(qa[ks], sQ + q0 * LDS + ks * 16, lane);
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
     float oacc[8][4];
 #pragma unroll
@@ -177,7 +191,15 @@ __global__ void __launch_bounds__(NW * 32) attn_fwd_mma_kernel(const bf16* __res
     }
 }
 
+// A fragment (16 rows x 16 k) of a row-major [row][k] smem tile; p -> element (row0, k0)
+__device__ __forceinline__ void lda_frag(uint32_t (&a)[4], const bf16* p, int lane) {
+    ldsm_x4(a, p + (lane & 15) * LDS + (lane >> 4) * 8);
+}
+
 // ------------------------------------------------------------------------------------------ backward
+// One CTA per (frame, head) holding Q, K, V, dO in shared memory (129 KB at n = 197): phase 1 (warp = 16 query
+// rows) recomputes P and produces dQ, phase 2 (warp = 16 key rows) recomputes P^T and produces dK, dV.  Measured
+// faster than splitting the phases into separate 2-matrix CTAs (which doubles the shared-memory fills).
 template <int NW>
 __global__ void __launch_bounds__(NW * 32) attn_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o,
                                                            const bf16* __restrict__ d_o, const float* __restrict__ lse,
@@ -364,18 +386,31 @@ __global__ void __launch_bounds__(NW * 32) attn_bwd_mma_kernel(const bf16* __res
     }
 }
 
-template <int NW>
-static int fwd_launch(const void* qkv, void* o, float* lse, int frames, int n, int heads, size_t smem, cudaStream_t s) {
+// row tiles of 16 are spread over ceil(tiles / 8) CTAs with an equal number of warps each
+static void split_rows(int n, int& nsplit, int& wpc) {
+    const int tiles = (n + 15) / 16;
+    nsplit = (tiles + 7) / 8;
+    wpc = (tiles + nsplit - 1) / nsplit;
+}
+
+int attn_spatial_fwd_mma(const void* qkv, void* o, float* lse, int frames, int n, int heads, cudaStream_t s) {
+    const int npad = (n + 31) & ~31;
+    int nsplit, wpc;
+    split_rows(n, nsplit, wpc);
+    const size_t smem = (size_t)2 * npad * LDS * 2;
+    if (smem > 200 * 1024) return AIMB_ERR_UNSUPPORTED;
     static bool attr_set = false;   // once: not a stream operation, keeps the launch path capture-safe
     if (!attr_set) {
-        if (cudaFuncSetAttribute(attn_fwd_mma_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+        if (cudaFuncSetAttribute(attn_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
             return AIMB_ERR_CUDA;
         attr_set = true;
     }
-    attn_fwd_mma_kernel<NW><<<frames * heads, ((n + 15) / 16) * 32, smem, s>>>((const bf16*)qkv, (bf16*)o, lse, n, heads);
+    dim3 grid(frames * heads, nsplit);
+    attn_fwd_mma_kernel<<<grid, wpc * 32, smem, s>>>((const bf16*)qkv, (bf16*)o, lse, n, heads, wpc);
     AIMB_CHECK_LAUNCH();
     return AIMB_OK;
 }
+
 template <int NW>
 static int bwd_launch(const void* qkv, const void* o, const void* d_o, const float* lse, void* d_qkv, int frames, int n,
                       int heads, size_t smem, cudaStream_t s) {
@@ -391,18 +426,8 @@ static int bwd_launch(const void* qkv, const void* o, const void* d_o, const flo
     return AIMB_OK;
 }
 
-// one warp per 16 query (or key) rows; kernels are compiled for the warp counts of the supported token counts
-// (n <= 128: toy sizes, 197 -> 13 warps: ViT-B/16, 257 -> 17 warps: ViT-L/14) so launch bounds fit the registers.
-int attn_spatial_fwd_mma(const void* qkv, void* o, float* lse, int frames, int n, int heads, cudaStream_t s) {
-    int npad = (n + 31) & ~31;
-    int nwarps = (n + 15) / 16;
-    size_t smem = (size_t)3 * npad * LDS * 2;
-    if (smem > 227 * 1024 || nwarps > 17) return AIMB_ERR_UNSUPPORTED;
-    if (nwarps <= 8) return fwd_launch<8>(qkv, o, lse, frames, n, heads, smem, s);
-    if (nwarps <= 13) return fwd_launch<13>(qkv, o, lse, frames, n, heads, smem, s);
-    return fwd_launch<17>(qkv, o, lse, frames, n, heads, smem, s);
-}
-
+// kernels are compiled for the warp counts of the supported token counts (n <= 128: toy sizes, 197 -> 13 warps:
+// ViT-B/16, 257 -> 17 warps: ViT-L/14) so the launch bounds fit the registers.
 int attn_spatial_bwd_mma(const void* qkv, const void* o, const void* d_o, const float* lse, void* d_qkv, int frames, int n,
                          int heads, cudaStream_t s) {
     int npad = (n + 31) & ~31;

@@ -87,6 +87,7 @@ struct EpiParams {
     int32_t out_f32;      // out is float regardless of T (wgrad accumulators)
     int32_t accumulate;   // out += v (only with out_f32)
     int64_t ldo;          // leading dim of out/out_pre/res1/res2/dact_src (elements)
+    float* colsum_out;    // [N] fp32: column sums of the stored values (atomically accumulated; zeroed by the host side)
 };
 
 inline EpiParams make_epi(const aimb_epilogue_t* e, int64_t ld_default) {
@@ -96,6 +97,7 @@ inline EpiParams make_epi(const aimb_epilogue_t* e, int64_t ld_default) {
     p.row_mod = e->row_mod > 0 ? e->row_mod : 1; p.act = e->act; p.dact = e->dact;
     p.bias_rowscaled = e->bias_rowscaled; p.out_f32 = e->out_f32; p.accumulate = e->accumulate;
     p.ldo = e->ldo > 0 ? e->ldo : ld_default;
+    p.colsum_out = e->colsum_out;
     return p;
 }
 

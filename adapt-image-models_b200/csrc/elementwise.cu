@@ -112,53 +112,90 @@ __global__ void __launch_bounds__(128) layernorm_fwd_kernel(const T* __restrict_
 }
 
 // ------------------------------------------------------------------ LayerNorm backward (input grad only)
-template <typename T>
+// One warp per row, RPW rows per warp.  Optionally accumulates cs_out[c] += alpha * w[row] * dx[row, c] (the bias
+// gradient of the adapter fed by dx) from the values already in registers: per-lane column partials over the
+// warp's rows, reduced across the 4 warps through smem, one atomicAdd per column per block.
+template <typename T, int RPW>
 __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                                             const float* __restrict__ mean_i,
                                                             const float* __restrict__ rstd_i,
                                                             const T* __restrict__ gamma, const T* dres, T* dx,
-                                                            int64_t rows, int D) {
+                                                            const float* __restrict__ cs_w, int cs_mod, float cs_alpha,
+                                                            float* __restrict__ cs_out, int64_t rows, int D) {
     constexpr int V = RowRegs<T>::V, NIT = RowRegs<T>::NIT;
-    int lane = threadIdx.x & 31;
-    int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (row >= rows) return;
-    RowRegs<T> g, xh;
-    g.load(dy + row * D, D, lane);
-    xh.load(x + row * D, D, lane);
-    float mean = mean_i[row], rstd = rstd_i[row];
-    float s1 = 0.f, s2 = 0.f;
+    constexpr int NWARP = 4;
+    __shared__ float red[RPW > 1 ? NWARP * MAXD : 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float cs[NIT][V];
 #pragma unroll
-    for (int it = 0; it < NIT; ++it) {
-        int c = (it * 32 + lane) * V;
-        if (c < D) {
-            float gm[V];
-            VecIO<T>::ld(gamma + c, gm);
+    for (int it = 0; it < NIT; ++it)
 #pragma unroll
-            for (int j = 0; j < V; ++j) {
-                float gg = g.v[it][j] * gm[j];
-                float h = (xh.v[it][j] - mean) * rstd;
-                g.v[it][j] = gg;
-                xh.v[it][j] = h;
-                s1 += gg;
-                s2 += gg * h;
+        for (int j = 0; j < V; ++j) cs[it][j] = 0.f;
+    // each warp handles RPW consecutive rows; with the fused column sums a block flushes one atomic per column
+    // for its 4*RPW rows (measured: fewer, fatter persistent blocks lose more in memory parallelism than they save)
+#pragma unroll 1
+    for (int k = 0; k < RPW; ++k) {
+        const int64_t row = ((int64_t)blockIdx.x * NWARP + warp) * RPW + k;
+        if (row >= rows) break;
+        RowRegs<T> g, xh;
+        g.load(dy + row * D, D, lane);
+        xh.load(x + row * D, D, lane);
+        const float mean = mean_i[row], rstd = rstd_i[row];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            int c = (it * 32 + lane) * V;
+            if (c < D) {
+                float gm[V];
+                VecIO<T>::ld(gamma + c, gm);
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    float gg = g.v[it][j] * gm[j];
+                    float h = (xh.v[it][j] - mean) * rstd;
+                    g.v[it][j] = gg;
+                    xh.v[it][j] = h;
+                    s1 += gg;
+                    s2 += gg * h;
+                }
+            }
+        }
+        s1 = warp_sum(s1) / D;
+        s2 = warp_sum(s2) / D;
+        const float w = (RPW > 1 && cs_w) ? cs_w[row % cs_mod] : 1.f;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            int c = (it * 32 + lane) * V;
+            if (c < D) {
+                float o[V];
+                if (dres) VecIO<T>::ld(dres + row * D + c, o);
+                else {
+#pragma unroll
+                    for (int j = 0; j < V; ++j) o[j] = 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    o[j] += rstd * (g.v[it][j] - s1 - xh.v[it][j] * s2);
+                    if (RPW > 1) cs[it][j] = fmaf(w, o[j], cs[it][j]);
+                }
+                VecIO<T>::st(dx + row * D + c, o);
             }
         }
     }
-    s1 = warp_sum(s1) / D;
-    s2 = warp_sum(s2) / D;
+    if (RPW > 1) {
 #pragma unroll
-    for (int it = 0; it < NIT; ++it) {
-        int c = (it * 32 + lane) * V;
-        if (c < D) {
-            float o[V];
-            if (dres) VecIO<T>::ld(dres + row * D + c, o);
-            else {
+        for (int it = 0; it < NIT; ++it) {
+            int c = (it * 32 + lane) * V;
+            if (c < D) {
 #pragma unroll
-                for (int j = 0; j < V; ++j) o[j] = 0.f;
+                for (int j = 0; j < V; ++j) red[warp * MAXD + c + j] = cs[it][j];
             }
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < D; c += 128) {
+            float t = 0.f;
 #pragma unroll
-            for (int j = 0; j < V; ++j) o[j] += rstd * (g.v[it][j] - s1 - xh.v[it][j] * s2);
-            VecIO<T>::st(dx + row * D + c, o);
+            for (int w = 0; w < NWARP; ++w) t += red[w * MAXD + c];
+            atomicAdd(cs_out + c, cs_alpha * t);
         }
     }
 }
@@ -435,21 +472,51 @@ extern "C" int aimb_layernorm_fwd(const void* x, const void* gamma, const void* 
     return AIMB_OK;
 }
 
-extern "C" int aimb_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma,
-                                  const void* dres, void* dx, int64_t rows, int32_t D, int32_t dtype, void* stream) {
+static int ln_bwd_launch(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma,
+                         const void* dres, void* dx, const float* cs_w, int cs_mod, float cs_alpha, float* cs_out,
+                         int64_t rows, int D, int dtype, cudaStream_t s) {
     if (!dy || !x || !mean || !rstd || !gamma || !dx || rows < 0 || !vec_ok(D, dtype)) return AIMB_ERR_ARG;
+    if (cs_out && cudaMemsetAsync(cs_out, 0, (size_t)D * 4, s) != cudaSuccess) return AIMB_ERR_CUDA;
     if (rows == 0) return AIMB_OK;
-    cudaStream_t s = (cudaStream_t)stream;
-    unsigned grid = (unsigned)((rows + 3) / 4);
-    if (dtype == AIMB_BF16)
-        layernorm_bwd_kernel<bf16><<<grid, 128, 0, s>>>((const bf16*)dy, (const bf16*)x, mean, rstd, (const bf16*)gamma,
-                                                        (const bf16*)dres, (bf16*)dx, rows, D);
-    else if (dtype == AIMB_F32)
-        layernorm_bwd_kernel<float><<<grid, 128, 0, s>>>((const float*)dy, (const float*)x, mean, rstd,
-                                                         (const float*)gamma, (const float*)dres, (float*)dx, rows, D);
-    else return AIMB_ERR_ARG;
+    if (cs_out) {
+        constexpr int RPW = 8;
+        unsigned grid = (unsigned)((rows + 4 * RPW - 1) / (4 * RPW));
+        if (dtype == AIMB_BF16)
+            layernorm_bwd_kernel<bf16, RPW><<<grid, 128, 0, s>>>((const bf16*)dy, (const bf16*)x, mean, rstd, (const bf16*)gamma,
+                                                                 (const bf16*)dres, (bf16*)dx, cs_w, cs_mod > 0 ? cs_mod : 1,
+                                                                 cs_alpha, cs_out, rows, D);
+        else if (dtype == AIMB_F32)
+            layernorm_bwd_kernel<float, RPW><<<grid, 128, 0, s>>>((const float*)dy, (const float*)x, mean, rstd,
+                                                                  (const float*)gamma, (const float*)dres, (float*)dx, cs_w,
+                                                                  cs_mod > 0 ? cs_mod : 1, cs_alpha, cs_out, rows, D);
+        else return AIMB_ERR_ARG;
+    } else {
+        unsigned grid = (unsigned)((rows + 3) / 4);
+        if (dtype == AIMB_BF16)
+            layernorm_bwd_kernel<bf16, 1><<<grid, 128, 0, s>>>((const bf16*)dy, (const bf16*)x, mean, rstd, (const bf16*)gamma,
+                                                               (const bf16*)dres, (bf16*)dx, nullptr, 1, 1.f, nullptr, rows, D);
+        else if (dtype == AIMB_F32)
+            layernorm_bwd_kernel<float, 1><<<grid, 128, 0, s>>>((const float*)dy, (const float*)x, mean, rstd,
+                                                                (const float*)gamma, (const float*)dres, (float*)dx, nullptr, 1,
+                                                                1.f, nullptr, rows, D);
+        else return AIMB_ERR_ARG;
+    }
     AIMB_CHECK_LAUNCH();
     return AIMB_OK;
+}
+
+extern "C" int aimb_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma,
+                                  const void* dres, void* dx, int64_t rows, int32_t D, int32_t dtype, void* stream) {
+    return ln_bwd_launch(dy, x, mean, rstd, gamma, dres, dx, nullptr, 1, 1.f, nullptr, rows, D, dtype, (cudaStream_t)stream);
+}
+
+extern "C" int aimb_layernorm_bwd_colsum(const void* dy, const void* x, const float* mean, const float* rstd,
+                                         const void* gamma, const void* dres, void* dx, const float* cs_row_scale,
+                                         int32_t cs_row_mod, float cs_alpha, float* cs_out, int64_t rows, int32_t D,
+                                         int32_t dtype, void* stream) {
+    if (!cs_out || (cs_row_scale && cs_row_mod <= 0)) return AIMB_ERR_ARG;
+    return ln_bwd_launch(dy, x, mean, rstd, gamma, dres, dx, cs_row_scale, cs_row_mod, cs_alpha, cs_out, rows, D, dtype,
+                         (cudaStream_t)stream);
 }
 
 extern "C" int aimb_stem_assemble_ln(const void* tok, const void* cls, const void* pos, const void* temb,

@@ -19,6 +19,7 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& e, int64_t m, in
     if (e.row_scale && !e.bias_rowscaled) v *= rs;
     if (e.res1) v += ldf<T>((const T*)e.res1 + off);
     if (e.res2) v += ldf<T>((const T*)e.res2 + off);
+    if (e.colsum_out) atomicAdd(e.colsum_out + n, v);
     if (e.out_f32) {
         float* o = (float*)e.out + off;
         *o = e.accumulate ? *o + v : v;

@@ -24,7 +24,7 @@ constexpr int TC_THREADS = 192;          // wgrad kernel: 1 producer + 1 MMA + 4
 constexpr int GEMM_THREADS = 320;        // GEMM: 1 producer + 1 MMA + 8 epilogue warps
 constexpr int EPI_WARPS = 8;
 constexpr int STG_WARP_FLOATS = 32 * 33 + 128;     // per-warp 32x32 fp32 transpose buffer (padded) + bias slice
-constexpr int STG_BYTES = EPI_WARPS * STG_WARP_FLOATS * 4;
+constexpr int STG_BYTES = EPI_WARPS * STG_WARP_FLOATS * 4 + 1024;   // + scol[256]: per-CTA column-sum partials
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 
 template <int BN> struct TileCfg {
@@ -144,8 +144,8 @@ __device__ __forceinline__ void epilogue_vec8(const EpiParams& e, int64_t m, int
 // 8 rows x 64 B per instruction.  `wait_acc` blocks until the accumulator is ready (called after the first
 // chunk's operand prefetch has been issued).
 template <int NCOLS, int ACT, int DACT, int EXT, typename WaitFn>
-__device__ __forceinline__ void epilogue_warp_t(const EpiParams& epi, float* stg, uint32_t taddr, int64_t row_base,
-                                                int n_base, int M, int lane, WaitFn wait_acc) {
+__device__ __forceinline__ void epilogue_warp_t(const EpiParams& epi, float* stg, float* scol, int col_in_tile, uint32_t taddr,
+                                                int64_t row_base, int n_base, int M, int lane, WaitFn wait_acc) {
     // Latency plan: everything that does not depend on the accumulator (bias -> smem, the first chunk's
     // residual / saved-activation operands) is requested BEFORE the accumulator-ready wait; inside the loop the
     // TMEM load of chunk c+1 and the operand loads of chunk c+1 are in flight while chunk c is processed.
@@ -177,6 +177,9 @@ __device__ __forceinline__ void epilogue_warp_t(const EpiParams& epi, float* stg
             *reinterpret_cast<float4*>(bias8) = *reinterpret_cast<const float4*>(sbias + c + c0);
             *reinterpret_cast<float4*>(bias8 + 4) = *reinterpret_cast<const float4*>(sbias + c + c0 + 4);
         }
+        float cs8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cs8[j] = 0.f;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int rl = i * 8 + row_l;
@@ -185,7 +188,21 @@ __device__ __forceinline__ void epilogue_warp_t(const EpiParams& epi, float* stg
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = stg[rl * 33 + c0 + j];
             if (dbg == 2) { if (v[0] == 1.2345e-30f && v[7] == 3.3e-31f) stg[lane * 33] = v[3]; continue; }
-            if (row < M) epilogue_vec8<ACT, DACT, EXT>(epi, row, n0, v, bias8, cur, i);
+            if (row < M) {
+                epilogue_vec8<ACT, DACT, EXT>(epi, row, n0, v, bias8, cur, i);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) cs8[j] += v[j];
+            }
+        }
+        if (epi.colsum_out) {      // bias gradient of the consumer: reduce the 8 row-lanes that share these columns,
+#pragma unroll                     // then the 4 quadrant warps through shared memory (flushed once per tile)
+            for (int j = 0; j < 8; ++j) {
+                float t = cs8[j];
+                t += __shfl_xor_sync(0xffffffffu, t, 4);
+                t += __shfl_xor_sync(0xffffffffu, t, 8);
+                t += __shfl_xor_sync(0xffffffffu, t, 16);
+                if (lane < 4) atomicAdd(scol + col_in_tile + c + c0 + j, t);
+            }
         }
         __syncwarp();
         if (DB) cur = nxt;
@@ -222,8 +239,8 @@ static int pick_variant(const EpiParams& e) {
 }
 
 template <int NCOLS, int V, typename WaitFn>
-__device__ __forceinline__ void epilogue_warp(const EpiParams& epi, float* stg, uint32_t taddr, int64_t row_base, int n_base,
-                                              int M, int lane, WaitFn wait_acc) {
+__device__ __forceinline__ void epilogue_warp(const EpiParams& epi, float* stg, float* scol, int col_in_tile, uint32_t taddr,
+                                              int64_t row_base, int n_base, int M, int lane, WaitFn wait_acc) {
     if (g_dbg_skip_epilogue == 1) {
         wait_acc();
         for (int c = 0; c < NCOLS; c += 32) {
@@ -235,7 +252,7 @@ __device__ __forceinline__ void epilogue_warp(const EpiParams& epi, float* stg, 
         return;
     }
     using EV = EpiVariant<V>;
-    epilogue_warp_t<NCOLS, EV::ACT, EV::DACT, EV::EXT>(epi, stg, taddr, row_base, n_base, M, lane, wait_acc);
+    epilogue_warp_t<NCOLS, EV::ACT, EV::DACT, EV::EXT>(epi, stg, scol, col_in_tile, taddr, row_base, n_base, M, lane, wait_acc);
 }
 
 template <int BN, int V>
@@ -247,6 +264,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a __shared__ pointer
     float* stg_all = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+    float* scol = stg_all + EPI_WARPS * STG_WARP_FLOATS;
+    if (threadIdx.x < 256) scol[threadIdx.x] = 0.f;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + STG_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;     // [2] accumulator ready
@@ -327,12 +346,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t aphase = (it >> 1) & 1;
             const int64_t row_base = (int64_t)m_blk * BM + quad * 32;
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN + half * (BN / 2);
-            epilogue_warp<BN / 2, V>(epi, stg, taddr, row_base, n_blk * BN + half * (BN / 2), M, lane, [&]() {
+            epilogue_warp<BN / 2, V>(epi, stg, scol, half * (BN / 2), taddr, row_base, n_blk * BN + half * (BN / 2), M, lane, [&]() {
                 ptx::mbar_wait(&tfull_bar[as], aphase);
                 ptx::tc_fence_after();
             });
             ptx::tc_fence_before();
             __syncwarp();
+            if (epi.colsum_out) {      // one global atomic per column per tile (the 8 epilogue warps meet on named barrier 1)
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const int te = threadIdx.x - 64;
+                if (te < BN) { atomicAdd(epi.colsum_out + n_blk * BN + te, scol[te]); scol[te] = 0.f; }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
             if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
         }
     }
@@ -369,6 +394,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a __shared__ pointer
     float* stg_all = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+    float* scol = stg_all + EPI_WARPS * STG_WARP_FLOATS;
+    if (threadIdx.x < 256) scol[threadIdx.x] = 0.f;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + STG_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
@@ -449,12 +476,18 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t aphase = (it >> 1) & 1;
             const int64_t row_base = (int64_t)m_blk * 2 * BM + (int64_t)rank * BM + quad * 32;
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN + half * (BN / 2);
-            epilogue_warp<BN / 2, V>(epi, stg, taddr, row_base, n_blk * BN + half * (BN / 2), M, lane, [&]() {
+            epilogue_warp<BN / 2, V>(epi, stg, scol, half * (BN / 2), taddr, row_base, n_blk * BN + half * (BN / 2), M, lane, [&]() {
                 ptx::mbar_wait(&tfull_bar[as], aphase);
                 ptx::tc_fence_after();
             });
             ptx::tc_fence_before();
             __syncwarp();
+            if (epi.colsum_out) {      // one global atomic per column per tile (the 8 epilogue warps meet on named barrier 1)
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const int te = threadIdx.x - 64;
+                if (te < BN) { atomicAdd(epi.colsum_out + n_blk * BN + te, scol[te]); scol[te] = 0.f; }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
             if (lane == 0) ptx::mbar_arrive_cluster(&tempty_bar[as], 0);   // the leader's MMA warp waits for both CTAs
         }
     }
@@ -848,6 +881,7 @@ extern "C" int aimb_gemm_nt(const void* A, int64_t lda, const void* W, int64_t l
     if (M == 0) return AIMB_OK;
     EpiParams p = make_epi(epi, N);
     cudaStream_t s = (cudaStream_t)stream;
+    if (p.colsum_out && cudaMemsetAsync(p.colsum_out, 0, (size_t)N * 4, s) != cudaSuccess) return AIMB_ERR_CUDA;
     // tcgen05 kernel for every shape it tiles (all ViT-B/16 and ViT-L/14 GEMMs); shapes it cannot tile
     // (N or K not a multiple of 64 — toy widths only) run on the SIMT kernel, still on the GPU.
     const bool tc_ok = (K % BK == 0) && (N % 64 == 0) && (lda % 8 == 0) && (ldw % 8 == 0) && (p.ldo % 8 == 0);

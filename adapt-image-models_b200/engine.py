@@ -203,7 +203,8 @@ class Engine:
         if on_block_done:
             on_block_done(d.L)
         for i in reversed(range(d.L)):
-            dx = self._block_bwd(i, dx, W, WT, grads, d, sv["blocks"][i])
+            prev_mask_m = sv["blocks"][i - 1]["masks"][1] if i > 0 else None
+            dx = self._block_bwd(i, dx, W, WT, grads, d, sv["blocks"][i], prev_mask_m)
             if on_block_done:
                 on_block_done(i)
         # ln_pre backward -> dz ; temporal_embedding grad = sum over (b, token)   (vit_clip.py:443-447)
@@ -215,24 +216,25 @@ class Engine:
             on_block_done(-1)
         self.saved = None
 
-    def _adapter_bwd(self, name, pre, dy, a, h, g, W, WT, grads, d, rs, alpha, d_a_out, d_a_res):
+    def _adapter_bwd(self, name, pre, dy, a, h, g, W, WT, grads, d, rs, alpha, d_a_out, d_a_res, db2_fused=False):
         """y = alpha * rs * (fc2(gelu(fc1(a)))).  Given dy: adapter weight/bias grads, and
-        d_a_out = d_a_res + d(a) (d_a_res may be None)."""
+        d_a_out = d_a_res + d(a) (d_a_res may be None).  db2_fused: the fc2 bias gradient (a weighted column sum
+        of dy) was already produced by the kernel that wrote dy."""
         M, r, D = d.M, d.r, d.D
         k1w, k1b = pre + name + ".D_fc1.weight", pre + name + ".D_fc1.bias"
         k2w, k2b = pre + name + ".D_fc2.weight", pre + name + ".D_fc2.bias"
         # fc2: g' = rs*gelu(h) was stored, so dW2 = alpha * dy^T g' ; db2 = alpha * sum_m rs[m] dy[m]
         lib.gemm_wgrad(dy, g, grads[k2w], alpha=alpha)
-        lib.colsum(dy, grads[k2b], row_scale=rs, alpha=alpha)
-        # d_h = rs * alpha * (dy W2) * gelu'(h)
+        if not db2_fused:
+            lib.colsum(dy, grads[k2b], row_scale=rs, alpha=alpha)
+        # d_h = rs * alpha * (dy W2) * gelu'(h) ; db1 = column sums of d_h, taken in the same epilogue
         d_h = self.buf("d_h", (M, r))
-        self.gemm(dy, WT[k2w], d_h, dact_src=h, dact=lib.ACT_GELU, alpha=alpha, row_scale=rs)
+        self.gemm(dy, WT[k2w], d_h, dact_src=h, dact=lib.ACT_GELU, alpha=alpha, row_scale=rs, colsum_out=grads[k1b])
         lib.gemm_wgrad(d_h, a, grads[k1w])
-        lib.colsum(d_h, grads[k1b])
         self.gemm(d_h, WT[k1w], d_a_out, res1=d_a_res)
         return d_a_out
 
-    def _block_bwd(self, i, dx, W, WT, grads, d, S):
+    def _block_bwd(self, i, dx, W, WT, grads, d, S, prev_mask_m=None):
         M, D, n = d.M, d.D, d.n
         pre = f"transformer.resblocks.{i}."
         mask_t, mask_m = S["masks"]
@@ -241,14 +243,17 @@ class Engine:
         self.gemm(dx, WT[pre + "mlp.c_proj.weight"], d_hf, dact_src=S["hf"], dact=lib.ACT_QUICKGELU)
         d_xn2 = self.buf("d_xn", (M, D))
         self.gemm(d_hf, WT[pre + "mlp.c_fc.weight"], d_xn2)
+        # (for i < L-1 the MLP-adapter fc2 bias grad was fused into the LN backward of block i+1 that produced dx)
         self._adapter_bwd("MLP_Adapter", pre, dx, S["xn2"], S["h_m"], S["g_m"], W, WT, grads, d, mask_m, d.scale,
-                          d_xn2, d_xn2)
+                          d_xn2, d_xn2, db2_fused=(i < d.L - 1))
         m3, r3 = S["ln2"]
         dx2 = dx                                              # residual grads accumulate in place in `dx`
-        lib.layernorm_bwd(d_xn2, S["x2"], m3, r3, W[pre + "ln_2.weight"], dx, dx2)
+        lib.layernorm_bwd(d_xn2, S["x2"], m3, r3, W[pre + "ln_2.weight"], dx, dx2,
+                          colsum_out=grads[pre + "S_Adapter.D_fc2.bias"])
         # ---------------- spatial: x2 = x1 + a_s + S_Adapter_noskip(a_s)
         d_as = self.buf("d_a", (M, D))
-        self._adapter_bwd("S_Adapter", pre, dx2, S["a_s"], S["h_s"], S["g_s"], W, WT, grads, d, None, 1.0, d_as, dx2)
+        self._adapter_bwd("S_Adapter", pre, dx2, S["a_s"], S["h_s"], S["g_s"], W, WT, grads, d, None, 1.0, d_as, dx2,
+                          db2_fused=True)
         d_os = self.buf("d_o", (M, D))
         self.gemm(d_as, WT[pre + "attn.out_proj.weight"], d_os)
         d_qkv = self.buf("d_qkv", (M, 3 * D))
@@ -257,20 +262,30 @@ class Engine:
         self.gemm(d_qkv, WT[pre + "attn.in_proj_weight"], d_xn1)
         m2, r2 = S["ln1s"]
         dx1 = dx
-        lib.layernorm_bwd(d_xn1, S["x1"], m2, r2, W[pre + "ln_1.weight"], dx2, dx1)
+        lib.layernorm_bwd(d_xn1, S["x1"], m2, r2, W[pre + "ln_1.weight"], dx2, dx1,
+                          colsum_out=grads[pre + "T_Adapter.D_fc2.bias"], colsum_row_scale=mask_t)
         # ---------------- temporal: x1 = x + mask_t * T_Adapter(attn(ln_1(x)))
         d_at = self.buf("d_a", (M, D))
-        self._adapter_bwd("T_Adapter", pre, dx1, S["a_t"], S["h_t"], S["g_t"], W, WT, grads, d, mask_t, 1.0, d_at, None)
+        self._adapter_bwd("T_Adapter", pre, dx1, S["a_t"], S["h_t"], S["g_t"], W, WT, grads, d, mask_t, 1.0, d_at, None,
+                          db2_fused=True)
         d_ot = self.buf("d_o", (M, D))
         self.gemm(d_at, WT[pre + "attn.out_proj.weight"], d_ot)
         lib.attn_temporal_bwd(S["qkv_t"], d_ot, d_qkv, d.B, d.T, n, d.heads)
         d_xn1t = self.buf("d_xn", (M, D))
-        self.gemm(d_qkv, WT[pre + "attn.in_proj_weight"], d_xn1t)
         if d.num_tadapter == 2:
+            self.gemm(d_qkv, WT[pre + "attn.in_proj_weight"], d_xn1t, colsum_out=grads[pre + "T_Adapter_in.D_fc2.bias"])
             xn, hi, gi = S["tin"]
             d_xn_tot = self.buf("d_xn_b", (M, D))
-            self._adapter_bwd("T_Adapter_in", pre, d_xn1t, xn, hi, gi, W, WT, grads, d, None, 1.0, d_xn_tot, d_xn1t)
+            self._adapter_bwd("T_Adapter_in", pre, d_xn1t, xn, hi, gi, W, WT, grads, d, None, 1.0, d_xn_tot, d_xn1t,
+                              db2_fused=True)
             d_xn1t = d_xn_tot
+        else:
+            self.gemm(d_qkv, WT[pre + "attn.in_proj_weight"], d_xn1t)
         m1, r1 = S["ln1t"]
-        lib.layernorm_bwd(d_xn1t, S["x"], m1, r1, W[pre + "ln_1.weight"], dx1, dx)
+        if i > 0:   # dx is the output gradient of block i-1: its MLP-adapter fc2 bias grad = scale * sum_m mask_m[m] dx[m]
+            lib.layernorm_bwd(d_xn1t, S["x"], m1, r1, W[pre + "ln_1.weight"], dx1, dx,
+                              colsum_out=grads[f"transformer.resblocks.{i - 1}.MLP_Adapter.D_fc2.bias"],
+                              colsum_row_scale=prev_mask_m, colsum_alpha=d.scale)
+        else:
+            lib.layernorm_bwd(d_xn1t, S["x"], m1, r1, W[pre + "ln_1.weight"], dx1, dx)
         return dx

@@ -31,7 +31,7 @@ class Epilogue(C.Structure):
     _fields_ = [("bias", C.c_void_p), ("row_scale", C.c_void_p), ("res1", C.c_void_p), ("res2", C.c_void_p),
                 ("dact_src", C.c_void_p), ("out", C.c_void_p), ("out_pre", C.c_void_p), ("alpha", C.c_float),
                 ("row_mod", C.c_int32), ("act", C.c_int32), ("dact", C.c_int32), ("bias_rowscaled", C.c_int32),
-                ("out_f32", C.c_int32), ("accumulate", C.c_int32), ("ldo", C.c_int64)]
+                ("out_f32", C.c_int32), ("accumulate", C.c_int32), ("ldo", C.c_int64), ("colsum_out", C.c_void_p)]
 
 
 # name -> argtypes; every function returns int except where noted.  Must list EVERY symbol of aimb200.h.
@@ -44,6 +44,7 @@ SIGNATURES = {
     "aimb_temb_grad": [_P, _P, _I, _I, _I, _I, _I, _P],
     "aimb_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _L, _I, _F, _I, _P],
     "aimb_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P],
+    "aimb_layernorm_bwd_colsum": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _F, _P, _L, _I, _I, _P],
     "aimb_tail_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P],
     "aimb_tail_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "aimb_gemm_nt": [_P, _L, _P, _L, C.POINTER(Epilogue), _L, _I, _I, _I, _I, _P],
@@ -133,11 +134,19 @@ def layernorm_fwd(x, gamma, beta, y, mean=None, rstd=None, eps=1e-5):
     return y
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, dres, dx):
+def layernorm_bwd(dy, x, mean, rstd, gamma, dres, dx, colsum_out=None, colsum_row_scale=None, colsum_alpha=1.0):
+    """dx = dres + LN'(dy); optionally colsum_out[c] = colsum_alpha * sum_r dx[r,c] * row_scale[r % len] (fused)."""
     rows, D = x.numel() // x.shape[-1], x.shape[-1]
     _count()
-    _chk(load().aimb_layernorm_bwd(_ptr(_c(dy)), _ptr(_c(x)), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dres),
-                                   _ptr(_c(dx)), rows, D, dt_code(x), _stream()), "layernorm_bwd")
+    if colsum_out is None:
+        _chk(load().aimb_layernorm_bwd(_ptr(_c(dy)), _ptr(_c(x)), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dres),
+                                       _ptr(_c(dx)), rows, D, dt_code(x), _stream()), "layernorm_bwd")
+    else:
+        assert colsum_out.dtype == torch.float32 and colsum_out.numel() == D
+        rs = colsum_row_scale
+        _chk(load().aimb_layernorm_bwd_colsum(_ptr(_c(dy)), _ptr(_c(x)), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dres),
+                                              _ptr(_c(dx)), _ptr(rs), rs.numel() if rs is not None else 0, colsum_alpha,
+                                              _ptr(colsum_out), rows, D, dt_code(x), _stream()), "layernorm_bwd_colsum")
     return dx
 
 
@@ -177,7 +186,7 @@ def tail_bwd(dfeat, x, mean, rstd, gamma, dx, dgamma, dbeta, B, T, n):
 
 
 def make_epilogue(out, bias=None, row_scale=None, res1=None, res2=None, dact_src=None, out_pre=None, alpha=1.0, act=0,
-                  dact=0, bias_rowscaled=False, out_f32=False, accumulate=False, ldo=0) -> Epilogue:
+                  dact=0, bias_rowscaled=False, out_f32=False, accumulate=False, ldo=0, colsum_out=None) -> Epilogue:
     e = Epilogue()
     e.bias, e.row_scale, e.res1, e.res2 = _ptr(bias), _ptr(row_scale), _ptr(res1), _ptr(res2)
     e.dact_src, e.out, e.out_pre = _ptr(dact_src), _ptr(out), _ptr(out_pre)
@@ -186,6 +195,7 @@ def make_epilogue(out, bias=None, row_scale=None, res1=None, res2=None, dact_src
     e.act, e.dact = act, dact
     e.bias_rowscaled, e.out_f32, e.accumulate = int(bias_rowscaled), int(out_f32), int(accumulate)
     e.ldo = ldo
+    e.colsum_out = _ptr(colsum_out)
     return e
 
 

@@ -50,6 +50,8 @@ extern "C" {
  *   if (row_scale && !bias_rowscaled) v *= row_scale[m % row_mod]   (DropPath per-token multiplier)
  *   v += res1[m,n] + res2[m,n]
  *   out[m,n] = v          (or out[m,n] += v when accumulate && out_f32)
+ *   if (colsum_out) colsum_out[n] = sum_m v               (fp32; the bias gradient of the layer that consumes `out`,
+ *                                                         produced while the tile is still in registers)
  * NULL pointers disable the corresponding term. */
 typedef struct aimb_epilogue {
     const void* bias;       /* [N], dtype */
@@ -67,6 +69,7 @@ typedef struct aimb_epilogue {
     int32_t out_f32;
     int32_t accumulate;
     int64_t ldo; /* 0 -> N */
+    float* colsum_out; /* [N] fp32, overwritten */
 } aimb_epilogue_t;
 
 int aimb_version(void);
@@ -96,6 +99,13 @@ int aimb_layernorm_fwd(const void* x, const void* gamma, const void* beta, void*
 /* dx = dres + LN'(dy) ; dres may be NULL; dx may alias dres or dy. */
 int aimb_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma,
                        const void* dres, void* dx, int64_t rows, int32_t D, int32_t dtype, void* stream);
+
+/* Same, and additionally cs_out[c] = cs_alpha * sum_r dx[r,c] * (cs_row_scale ? cs_row_scale[r % cs_row_mod] : 1)
+ * (fp32 [D], overwritten): the bias gradient of the adapter whose output gradient is `dx`, fused into the pass
+ * that produces `dx` instead of re-reading it. */
+int aimb_layernorm_bwd_colsum(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma,
+                              const void* dres, void* dx, const float* cs_row_scale, int32_t cs_row_mod, float cs_alpha,
+                              float* cs_out, int64_t rows, int32_t D, int32_t dtype, void* stream);
 
 /* ---- tail: vit_clip.py:450-456 (ln_post on the cls rows only, '(b t) d -> b d t') ----------- */
 /* feat is fp32 [B, D, T]. mean/rstd [B*T] saved for backward. */

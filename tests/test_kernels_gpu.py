@@ -50,6 +50,14 @@ def test_layernorm_fwd_bwd(dt, rows, D):
     assert _err(dx, xr.grad + dres.double()) < _tol(dt)
     lib.layernorm_bwd(dy, x, mean, rstd, w, None, dx)
     assert _err(dx, xr.grad) < _tol(dt)
+    # fused weighted column sum of the produced gradient (bias grad of the adapter that consumes it)
+    rs = torch.rand(7, device="cuda", generator=g)
+    cs = torch.full((D,), float("nan"), device="cuda")
+    lib.layernorm_bwd(dy, x, mean, rstd, w, dres, dx, colsum_out=cs, colsum_row_scale=rs, colsum_alpha=0.5)
+    tot = xr.grad + dres.double()
+    assert _err(dx, tot) < _tol(dt)
+    refc = 0.5 * (tot * rs.double()[torch.arange(rows, device="cuda") % 7][:, None]).sum(0)
+    assert _err(cs, refc) < (1e-4 if dt == "f32" else 5e-3)
 
 
 EPI_CASES = ["plain", "bias", "bias_qgelu_pre", "bias_gelu_rowscale", "res2", "dact", "bias_rowscaled_alpha"]
@@ -88,10 +96,12 @@ def _gemm_case(lib, dt, M, N, K, case, impl, seed=0):
         kw = dict(bias=bias, res1=r1, res2=r2)
         ref = acc + bias.double() + r1.double() + r2.double()
     elif case == "dact":
-        kw = dict(dact_src=pre, dact=lib.ACT_GELU, row_scale=rs, alpha=0.5)
+        cs = torch.full((N,), float("nan"), device="cuda")
+        kw = dict(dact_src=pre, dact=lib.ACT_GELU, row_scale=rs, alpha=0.5, colsum_out=cs)
         u = pre.double().requires_grad_(True)
         F.gelu(u).sum().backward()
         ref = acc * u.grad * 0.5 * rsm
+        extra = (cs, ref.sum(0))
     elif case == "bias_rowscaled_alpha":
         kw = dict(bias=bias, row_scale=rs, bias_rowscaled=True, alpha=0.5, res1=r1)
         ref = (acc + bias.double() * rsm) * 0.5 + r1.double()
