@@ -102,8 +102,8 @@ class ViT_CLIP(nn.Module):
         block = os.environ.get("AIMB200_BLOCK", block or "aim")
         if block not in ("aim", "fork"):
             raise ValueError("block must be 'aim' (upstream AIM math, vitclip_aim.py:196-211) or 'fork' (vit_clip.py:199-288)")
-        if block == "fork":
-            raise NotImplementedError("block='fork' (vit_clip.py:199-288) is not built yet; see DESIGN.md")
+        if block == "fork" and num_tadapter != 1:
+            raise ValueError("num_tadapter==2 is only defined for block='aim' (the in-tree fork has no T_Adapter_in)")
         if shift:
             raise NotImplementedError("shift=True (PatchShift, vit_clip.py:15-49,233-254) is outside the built path")
         if width % heads or width // heads != 64:
@@ -224,7 +224,7 @@ class ViT_CLIP(nn.Module):
         K = 3 * p * p
         return Dims(B=B, T=self.num_frames, n=(res // p) ** 2 + 1, D=self.width, heads=self.heads, L=self.layers,
                     r=int(self.width * 0.25), patch=p, res=res, kpad=(K + 63) // 64 * 64, num_tadapter=self.num_tadapter,
-                    scale=self.adapter_scale)
+                    scale=self.adapter_scale, block=self.block)
 
     def trainable_names(self) -> List[str]:
         """Flat-buffer order: temporal_embedding, block 0 .. L-1 adapters, ln_post — so that the gradient

@@ -446,6 +446,69 @@ __global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ in
     }
 }
 
+
+// ------------------------------------------------------------------ fork block (vit_clip.py:264-275) combine
+// out[f,i,:] = x[f,i,:] + (1 - lam[f]) * a_o[f,i,:] + rs[i] * s[f,:]      (s = scale * S_Adapter(lam * a_c), one row per frame)
+template <typename T>
+__global__ void __launch_bounds__(128) fork_combine_kernel(const T* __restrict__ x, const T* __restrict__ a_o,
+                                                           const T* __restrict__ sfr, const float* __restrict__ lam,
+                                                           const float* __restrict__ rs, T* __restrict__ out, int BT, int n,
+                                                           int D) {
+    constexpr int V = VecIO<T>::N;
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (row >= (int64_t)BT * n) return;
+    const int f = (int)(row / n), i = (int)(row % n);
+    const float w = 1.f - lam[f], m = rs ? rs[i] : 1.f;
+    for (int c = lane * V; c < D; c += 32 * V) {
+        float a[V], b[V], cc[V], o[V];
+        VecIO<T>::ld(x + row * D + c, a);
+        VecIO<T>::ld(a_o + row * D + c, b);
+        VecIO<T>::ld(sfr + (int64_t)f * D + c, cc);
+#pragma unroll
+        for (int j = 0; j < V; ++j) o[j] = a[j] + w * b[j] + m * cc[j];
+        VecIO<T>::st(out + row * D + c, o);
+    }
+}
+// d_ao[f,i,:] = (1 - lam[f]) * dx[f,i,:] ;  d_s[f,:] = sum_i rs[i] * dx[f,i,:]     (block = one frame x 32*V columns)
+template <typename T>
+__global__ void __launch_bounds__(256) fork_combine_bwd_kernel(const T* __restrict__ dx, const float* __restrict__ lam,
+                                                               const float* __restrict__ rs, T* __restrict__ d_ao,
+                                                               T* __restrict__ d_s, int n, int D) {
+    constexpr int V = VecIO<T>::N;
+    __shared__ float red[8][32][V + 1];
+    const int f = blockIdx.y;
+    const int c = (blockIdx.x * 32 + threadIdx.x) * V;
+    const float w = 1.f - lam[f];
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.f;
+    if (c < D)
+        for (int i = threadIdx.y; i < n; i += 8) {
+            const int64_t off = ((int64_t)f * n + i) * D + c;
+            float v[V], o[V];
+            VecIO<T>::ld(dx + off, v);
+            const float m = rs ? rs[i] : 1.f;
+#pragma unroll
+            for (int j = 0; j < V; ++j) { o[j] = w * v[j]; acc[j] = fmaf(m, v[j], acc[j]); }
+            VecIO<T>::st(d_ao + off, o);
+        }
+#pragma unroll
+    for (int j = 0; j < V; ++j) red[threadIdx.y][threadIdx.x][j] = acc[j];
+    __syncthreads();
+    if (threadIdx.y == 0 && c < D) {
+        float o[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            float t = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x][j];
+            o[j] = t;
+        }
+        VecIO<T>::st(d_s + (int64_t)f * D + c, o);
+    }
+}
+
 static inline bool vec_ok(int D, int dtype) {
     int v = dtype == AIMB_BF16 ? 8 : 4;
     return D > 0 && D % v == 0 && D <= MAXD;
@@ -666,6 +729,39 @@ extern "C" int aimb_transpose(const void* in, void* out, int32_t R, int32_t C, i
     dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
     if (dtype == AIMB_BF16) transpose_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)in, (bf16*)out, R, C);
     else if (dtype == AIMB_F32) transpose_kernel<float><<<grid, block, 0, s>>>((const float*)in, (float*)out, R, C);
+    else return AIMB_ERR_ARG;
+    AIMB_CHECK_LAUNCH();
+    return AIMB_OK;
+}
+
+extern "C" int aimb_fork_combine(const void* x, const void* a_o, const void* s_frame, const float* lam, const float* rs,
+                                 void* out, int32_t BT, int32_t n, int32_t D, int32_t dtype, void* stream) {
+    if (!x || !a_o || !s_frame || !lam || !out || BT < 0 || n <= 0 || !vec_ok(D, dtype)) return AIMB_ERR_ARG;
+    if (BT == 0) return AIMB_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned grid = (unsigned)(((int64_t)BT * n + 3) / 4);
+    if (dtype == AIMB_BF16)
+        fork_combine_kernel<bf16><<<grid, 128, 0, s>>>((const bf16*)x, (const bf16*)a_o, (const bf16*)s_frame, lam, rs, (bf16*)out,
+                                                       BT, n, D);
+    else if (dtype == AIMB_F32)
+        fork_combine_kernel<float><<<grid, 128, 0, s>>>((const float*)x, (const float*)a_o, (const float*)s_frame, lam, rs,
+                                                        (float*)out, BT, n, D);
+    else return AIMB_ERR_ARG;
+    AIMB_CHECK_LAUNCH();
+    return AIMB_OK;
+}
+
+extern "C" int aimb_fork_combine_bwd(const void* dx, const float* lam, const float* rs, void* d_ao, void* d_s, int32_t BT,
+                                     int32_t n, int32_t D, int32_t dtype, void* stream) {
+    if (!dx || !lam || !d_ao || !d_s || BT < 0 || n <= 0 || !vec_ok(D, dtype)) return AIMB_ERR_ARG;
+    if (BT == 0) return AIMB_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int V = dtype == AIMB_BF16 ? 8 : 4;
+    dim3 grid((D / V + 31) / 32, BT), block(32, 8);
+    if (dtype == AIMB_BF16)
+        fork_combine_bwd_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)dx, lam, rs, (bf16*)d_ao, (bf16*)d_s, n, D);
+    else if (dtype == AIMB_F32)
+        fork_combine_bwd_kernel<float><<<grid, block, 0, s>>>((const float*)dx, lam, rs, (float*)d_ao, (float*)d_s, n, D);
     else return AIMB_ERR_ARG;
     AIMB_CHECK_LAUNCH();
     return AIMB_OK;

@@ -884,7 +884,8 @@ extern "C" int aimb_gemm_nt(const void* A, int64_t lda, const void* W, int64_t l
     if (p.colsum_out && cudaMemsetAsync(p.colsum_out, 0, (size_t)N * 4, s) != cudaSuccess) return AIMB_ERR_CUDA;
     // tcgen05 kernel for every shape it tiles (all ViT-B/16 and ViT-L/14 GEMMs); shapes it cannot tile
     // (N or K not a multiple of 64 — toy widths only) run on the SIMT kernel, still on the GPU.
-    const bool tc_ok = (K % BK == 0) && (N % 64 == 0) && (lda % 8 == 0) && (ldw % 8 == 0) && (p.ldo % 8 == 0);
+    // (also M < 128: the per-frame [B*T, D] GEMMs of the fork block — a TMA box may not exceed the tensor)
+    const bool tc_ok = (K % BK == 0) && (N % 64 == 0) && (lda % 8 == 0) && (ldw % 8 == 0) && (p.ldo % 8 == 0) && M >= BM;
     if (dtype == AIMB_BF16 && impl == AIMB_IMPL_AUTO && !p.out_f32 && tc_ok)
         return gemm_tc_launch(A, lda, W, ldw, p, M, N, K, g_force_bn, g_cta_mode, s);
     if (dtype != AIMB_BF16 && dtype != AIMB_F32) return AIMB_ERR_ARG;
@@ -895,7 +896,7 @@ extern "C" int aimb_gemm_wgrad(const void* dY, int64_t ldy, const void* X, int64
                                int32_t K, float alpha, int32_t accumulate, int32_t dtype, int32_t impl, void* stream) {
     if (!dY || !X || !dW || R < 0 || N <= 0 || K <= 0 || ldy < N || ldx < K) return AIMB_ERR_ARG;
     cudaStream_t s0 = (cudaStream_t)stream;
-    if (dtype == AIMB_BF16 && impl == AIMB_IMPL_AUTO && R > 0) {
+    if (dtype == AIMB_BF16 && impl == AIMB_IMPL_AUTO && R >= 64) {
         const bool shape_ok = (N % 128 == 0 && K % 64 == 0 && K <= 256) || (K % 128 == 0 && N % 64 == 0 && N <= 256);
         if (shape_ok && ldy % 8 == 0 && ldx % 8 == 0) {
             if (!accumulate && cudaMemsetAsync(dW, 0, (size_t)N * K * 4, s0) != cudaSuccess) return AIMB_ERR_CUDA;

@@ -39,6 +39,7 @@ class Dims:
     kpad: int
     num_tadapter: int
     scale: float
+    block: str = "aim"
 
     @property
     def BT(self):
@@ -103,7 +104,10 @@ class Engine:
             sv["z"], sv["ln_pre"] = z, (mean0, rstd0)
         for i in range(d.L):
             masks = drop_masks[i] if (drop_masks is not None) else (None, None)
-            xcur = self._block_fwd(i, xcur, W, d, training, masks, sv)
+            if d.block == "fork":
+                xcur = self._block_fwd_fork(i, xcur, W, d, training, masks, sv)
+            else:
+                xcur = self._block_fwd(i, xcur, W, d, training, masks, sv)
         # ---- tail
         feat = torch.empty(d.B, D, d.T, device=self.device, dtype=torch.float32)
         tm = self.buf("tail_mean", (BT,), torch.float32, key)
@@ -116,7 +120,7 @@ class Engine:
 
     def _adapter_fwd(self, name, pre, a, W, d, bk, training, rs, alpha, res1, res2, out):
         """out = res1 + res2 + alpha * rs * (fc2(gelu(fc1(a))))   (rs folded into the hidden, see backward)."""
-        M, r = d.M, d.r
+        M, r = a.shape[0], d.r
         h = self.buf(name + "_h", (M, r), key=bk) if training else None
         g = self.buf(name + "_g", (M, r), key=bk)
         self.gemm(a, W[pre + name + ".D_fc1.weight"], g, bias=W[pre + name + ".D_fc1.bias"], act=lib.ACT_GELU,
@@ -124,6 +128,38 @@ class Engine:
         self.gemm(g, W[pre + name + ".D_fc2.weight"], out, bias=W[pre + name + ".D_fc2.bias"], row_scale=rs,
                   bias_rowscaled=rs is not None, alpha=alpha, res1=res1, res2=res2)
         return h, g
+
+    def _mlp_fwd(self, i, x2, W, d, training, mask_m, bk):
+        """joint adaptation (vitclip_aim.py:210-211 == vit_clip.py:285-286):
+        x_out = x2 + c_proj(QuickGELU(c_fc(ln_2(x2)))) + drop_path(scale * MLP_Adapter(ln_2(x2)))"""
+        M, D = d.M, d.D
+        pre = f"transformer.resblocks.{i}."
+        f32 = torch.float32
+        xn2 = self.buf("xn2", (M, D), key=bk)
+        m3, r3 = self.buf("ln2_m", (M,), f32, bk), self.buf("ln2_r", (M,), f32, bk)
+        lib.layernorm_fwd(x2, W[pre + "ln_2.weight"], W[pre + "ln_2.bias"], xn2, m3, r3)
+        tmp = self.buf("tmp", (M, D))
+        h_m, g_m = self._adapter_fwd("MLP_Adapter", pre, xn2, W, d, bk, training, mask_m, d.scale, x2, None, tmp)
+        hf = self.buf("hf", (M, 4 * D), key=bk) if training else None
+        gf = self.buf("gf", (M, 4 * D))
+        self.gemm(xn2, W[pre + "mlp.c_fc.weight"], gf, bias=W[pre + "mlp.c_fc.bias"], act=lib.ACT_QUICKGELU, out_pre=hf)
+        xo = self.buf("x", (M, D), key=("train", i + 1) if training else ("eval", (i + 1) % 2))
+        self.gemm(gf, W[pre + "mlp.c_proj.weight"], xo, bias=W[pre + "mlp.c_proj.bias"], res1=tmp)
+        return xo, dict(ln2=(m3, r3), xn2=xn2, h_m=h_m, g_m=g_m, hf=hf)
+
+    def _mlp_bwd(self, i, dx, W, WT, grads, d, S, mask_m, db2_fused, colsum_for=None):
+        """backward of _mlp_fwd: returns dx2 = d(x2) (accumulated in place in `dx`)."""
+        M, D = d.M, d.D
+        pre = f"transformer.resblocks.{i}."
+        d_hf = self.buf("d_big", (M, 4 * D))
+        self.gemm(dx, WT[pre + "mlp.c_proj.weight"], d_hf, dact_src=S["hf"], dact=lib.ACT_QUICKGELU)
+        d_xn2 = self.buf("d_xn", (M, D))
+        self.gemm(d_hf, WT[pre + "mlp.c_fc.weight"], d_xn2)
+        self._adapter_bwd("MLP_Adapter", pre, dx, S["xn2"], S["h_m"], S["g_m"], W, WT, grads, d, mask_m, d.scale,
+                          d_xn2, d_xn2, db2_fused=db2_fused)
+        m3, r3 = S["ln2"]
+        lib.layernorm_bwd(d_xn2, S["x2"], m3, r3, W[pre + "ln_2.weight"], dx, dx, colsum_out=colsum_for)
+        return dx
 
     def _block_fwd(self, i, x, W, d, training, masks, sv):
         M, D, r, n = d.M, d.D, d.r, d.n
@@ -167,23 +203,111 @@ class Engine:
         self.gemm(o_s, Wo, a_s, bias=bo)
         x2 = self.buf("x2", (M, D), key=bk)
         h_s, g_s = self._adapter_fwd("S_Adapter", pre, a_s, W, d, bk, training, None, 1.0, x1, a_s, x2)
-        # ---------------- joint adaptation (:210-211)
-        xn2 = self.buf("xn2", (M, D), key=bk)
-        m3, r3 = self.buf("ln2_m", (M,), f32, bk), self.buf("ln2_r", (M,), f32, bk)
-        lib.layernorm_fwd(x2, W[pre + "ln_2.weight"], W[pre + "ln_2.bias"], xn2, m3, r3)
-        tmp = self.buf("tmp", (M, D))
-        h_m, g_m = self._adapter_fwd("MLP_Adapter", pre, xn2, W, d, bk, training, mask_m, d.scale, x2, None, tmp)
-        hf = self.buf("hf", (M, 4 * D), key=bk) if training else None
-        gf = self.buf("gf", (M, 4 * D))
-        self.gemm(xn2, W[pre + "mlp.c_fc.weight"], gf, bias=W[pre + "mlp.c_fc.bias"], act=lib.ACT_QUICKGELU, out_pre=hf)
-        xo = self.buf("x", (M, D), key=("train", i + 1) if training else ("eval", (i + 1) % 2))
-        self.gemm(gf, W[pre + "mlp.c_proj.weight"], xo, bias=W[pre + "mlp.c_proj.bias"], res1=tmp)
+        xo, mlp_saved = self._mlp_fwd(i, x2, W, d, training, mask_m, bk)
         if training:
             S.update(x=x, ln1t=(m1, r1), qkv_t=qkv_t, o_t=o_t, a_t=a_t, h_t=h_t, g_t=g_t, x1=x1, ln1s=(m2, r2),
-                     qkv_s=qkv_s, o_s=o_s, lse=lse, a_s=a_s, h_s=h_s, g_s=g_s, x2=x2, ln2=(m3, r3), xn2=xn2, h_m=h_m,
-                     g_m=g_m, hf=hf, masks=masks)
+                     qkv_s=qkv_s, o_s=o_s, lse=lse, a_s=a_s, h_s=h_s, g_s=g_s, x2=x2, masks=masks, **mlp_saved)
             sv["blocks"].append(S)
         return xo
+
+
+    # ------------------------------------------------------------------ block 'fork' (vit_clip.py:199-288, shift=False)
+    def _block_fwd_fork(self, i, x, W, d, training, masks, sv):
+        """cls-only temporal attention kept aside as xt; spatial self-attention a_o; cross attention of every token to the
+        single key xt_f (softmax == 1 -> a_c is one row per frame); lambda_f = w_c / (w_c + w_o) (no grad);
+        x += (1 - lambda) a_o + drop_path(scale * S_Adapter(lambda a_c)); then the shared MLP half."""
+        M, D, n, BT = d.M, d.D, d.n, d.BT
+        pre = f"transformer.resblocks.{i}."
+        bk = ("train", i) if training else "eval"
+        mask_s, mask_m = masks
+        f32 = torch.float32
+        Wqkv, bqkv = W[pre + "attn.in_proj_weight"], W[pre + "attn.in_proj_bias"]
+        Wo, bo = W[pre + "attn.out_proj.weight"], W[pre + "attn.out_proj.bias"]
+        xn = self.buf("xn", (M, D))
+        m1, r1 = self.buf("ln1s_m", (M,), f32, bk), self.buf("ln1s_r", (M,), f32, bk)
+        lib.layernorm_fwd(x, W[pre + "ln_1.weight"], W[pre + "ln_1.bias"], xn, m1, r1)
+        # ---- temporal attention over the T cls tokens of each clip (:218-229); ln_1 is row-wise, so ln_1(cls) = cls rows of xn
+        ct = xn.view(BT, n, D)[:, 0, :]                                    # [BT, D], row stride n*D (read in place)
+        qkv_c = self.buf("qkv_c", (BT, 3 * D), key=bk)
+        self.gemm(ct, Wqkv, qkv_c, bias=bqkv)
+        o_c = self.buf("o_c", (BT, D), key=bk)
+        lib.attn_temporal_fwd(qkv_c, o_c, d.B, d.T, 1, d.heads)
+        a_ct = self.buf("a_ct", (BT, D), key=bk)
+        self.gemm(o_c, Wo, a_ct, bias=bo)
+        xt = self.buf("xt", (BT, D), key=bk)
+        h_t, g_t = self._adapter_fwd("T_Adapter", pre, a_ct, W, d, bk, training, None, 1.0, None, None, xt)
+        # ---- spatial self attention (:264, :128-162)
+        qkv_s = self.buf("qkv_s", (M, 3 * D), key=bk)
+        self.gemm(xn, Wqkv, qkv_s, bias=bqkv)
+        o_s = self.buf("o_s", (M, D), key=bk)
+        lse = self.buf("lse_s", (BT, d.heads, n), f32, bk) if training else None
+        lib.attn_spatial_fwd(qkv_s, o_s, lse, BT, n, d.heads, impl=self.attn_impl)
+        a_o = self.buf("a_s", (M, D))
+        self.gemm(o_s, Wo, a_o, bias=bo)
+        # ---- cross attention to xt (:265, :164-197): k, v from the raw xt; one key -> softmax == 1 -> a_c = out_proj(v_c)
+        k_c = self.buf("k_c", (BT, D))
+        v_c = self.buf("v_c", (BT, D))
+        self.gemm(xt, Wqkv[D:2 * D], k_c, bias=bqkv[D:2 * D])
+        self.gemm(xt, Wqkv[2 * D:], v_c, bias=bqkv[2 * D:])
+        a_c = self.buf("a_c", (BT, D), key=bk)
+        self.gemm(v_c, Wo, a_c, bias=bo)
+        # ---- lambda from the un-normalised attention masses (:147-151, :182-186), fp32, no max subtraction
+        w_o = self.buf("w_o", (BT,), f32)
+        w_c = self.buf("w_c", (BT,), f32)
+        lib.fork_weights(qkv_s, k_c, w_o, w_c, BT, n, D)
+        lam = self.buf("lam", (BT,), f32, bk)
+        torch.div(w_c, w_c + w_o, out=lam)
+        # ---- S_Adapter (no skip in the fork) on one row per frame
+        u = self.buf("u", (BT, D), key=bk)
+        u.copy_(a_c.float() * lam.unsqueeze(1))
+        s_fr = self.buf("s_fr", (BT, D))
+        h_s, g_s = self._adapter_fwd("S_Adapter", pre, u, W, d, bk, training, None, d.scale, None, None, s_fr)
+        x2 = self.buf("x2", (M, D), key=bk)
+        lib.fork_combine(x, a_o, s_fr, lam, mask_s, x2, BT, n)
+        xo, mlp_saved = self._mlp_fwd(i, x2, W, d, training, mask_m, bk)
+        if training:
+            sv["blocks"].append(dict(x=x, ln1s=(m1, r1), qkv_c=qkv_c, a_ct=a_ct, h_t=h_t, g_t=g_t, qkv_s=qkv_s, o_s=o_s,
+                                     lse=lse, lam=lam, u=u, h_s=h_s, g_s=g_s, x2=x2, masks=masks, **mlp_saved))
+        return xo
+
+    def _block_bwd_fork(self, i, dx, W, WT, grads, d, S):
+        M, D, n, BT = d.M, d.D, d.n, d.BT
+        pre = f"transformer.resblocks.{i}."
+        mask_s, mask_m = S["masks"]
+        lam = S["lam"]
+        WqkvT, WoT = WT[pre + "attn.in_proj_weight"], WT[pre + "attn.out_proj.weight"]   # [D, 3D], [D, D]
+        dx2 = self._mlp_bwd(i, dx, W, WT, grads, d, S, mask_m, db2_fused=False)
+        # x2 = x + (1 - lam) a_o + mask_s * s_fr   (lam carries no gradient: computed under no_grad in the reference)
+        d_ao = self.buf("d_a", (M, D))
+        d_s = self.buf("d_s", (BT, D))
+        lib.fork_combine_bwd(dx2, lam, mask_s, d_ao, d_s, BT, n)
+        d_u = self.buf("d_u", (BT, D))
+        self._adapter_bwd("S_Adapter", pre, d_s, S["u"], S["h_s"], S["g_s"], W, WT, grads, d, None, d.scale, d_u, None)
+        d_ac = self.buf("d_ac", (BT, D))
+        d_ac.copy_(d_u.float() * lam.unsqueeze(1))
+        d_vc = self.buf("d_vc", (BT, D))
+        self.gemm(d_ac, WoT, d_vc)                                         # a_c = out_proj(v_c)
+        d_xt = self.buf("d_xt", (BT, D))
+        self.gemm(d_vc, WqkvT[:, 2 * D:], d_xt)                            # v_c = xt W_v^T + b_v ; k_c feeds only lam
+        d_act = self.buf("d_act", (BT, D))
+        self._adapter_bwd("T_Adapter", pre, d_xt, S["a_ct"], S["h_t"], S["g_t"], W, WT, grads, d, None, 1.0, d_act, None)
+        d_oc = self.buf("d_oc", (BT, D))
+        self.gemm(d_act, WoT, d_oc)
+        d_qkv_c = self.buf("d_qkv_c", (BT, 3 * D))
+        lib.attn_temporal_bwd(S["qkv_c"], d_oc, d_qkv_c, d.B, d.T, 1, d.heads)
+        d_ct = self.buf("d_ct", (BT, D))
+        self.gemm(d_qkv_c, WqkvT, d_ct)                                    # grad wrt ln_1(x) at the cls rows
+        # spatial self attention
+        d_os = self.buf("d_o", (M, D))
+        self.gemm(d_ao, WoT, d_os)
+        d_qkv = self.buf("d_qkv", (M, 3 * D))
+        lib.attn_spatial_bwd(S["qkv_s"], S["o_s"], d_os, S["lse"], d_qkv, BT, n, d.heads, impl=self.attn_impl)
+        d_xn = self.buf("d_xn", (M, D))
+        self.gemm(d_qkv, WqkvT, d_xn)
+        d_xn.view(BT, n, D)[:, 0, :].add_(d_ct)
+        m1, r1 = S["ln1s"]
+        lib.layernorm_bwd(d_xn, S["x"], m1, r1, W[pre + "ln_1.weight"], dx2, dx)
+        return dx
 
     # ------------------------------------------------------------------ backward
     def backward(self, dfeat: torch.Tensor, W: Dict[str, torch.Tensor], WT: Dict[str, torch.Tensor],
@@ -204,7 +328,10 @@ class Engine:
             on_block_done(d.L)
         for i in reversed(range(d.L)):
             prev_mask_m = sv["blocks"][i - 1]["masks"][1] if i > 0 else None
-            dx = self._block_bwd(i, dx, W, WT, grads, d, sv["blocks"][i], prev_mask_m)
+            if d.block == "fork":
+                dx = self._block_bwd_fork(i, dx, W, WT, grads, d, sv["blocks"][i])
+            else:
+                dx = self._block_bwd(i, dx, W, WT, grads, d, sv["blocks"][i], prev_mask_m)
             if on_block_done:
                 on_block_done(i)
         # ln_pre backward -> dz ; temporal_embedding grad = sum over (b, token)   (vit_clip.py:443-447)
@@ -220,7 +347,7 @@ class Engine:
         """y = alpha * rs * (fc2(gelu(fc1(a)))).  Given dy: adapter weight/bias grads, and
         d_a_out = d_a_res + d(a) (d_a_res may be None).  db2_fused: the fc2 bias gradient (a weighted column sum
         of dy) was already produced by the kernel that wrote dy."""
-        M, r, D = d.M, d.r, d.D
+        M, r, D = dy.shape[0], d.r, d.D
         k1w, k1b = pre + name + ".D_fc1.weight", pre + name + ".D_fc1.bias"
         k2w, k2b = pre + name + ".D_fc2.weight", pre + name + ".D_fc2.bias"
         # fc2: g' = rs*gelu(h) was stored, so dW2 = alpha * dy^T g' ; db2 = alpha * sum_m rs[m] dy[m]
@@ -239,17 +366,10 @@ class Engine:
         pre = f"transformer.resblocks.{i}."
         mask_t, mask_m = S["masks"]
         # ---------------- joint adaptation: x_out = x2 + mlp(xn2) + scale*mask_m*MLP_Adapter(xn2)
-        d_hf = self.buf("d_big", (M, 4 * D))
-        self.gemm(dx, WT[pre + "mlp.c_proj.weight"], d_hf, dact_src=S["hf"], dact=lib.ACT_QUICKGELU)
-        d_xn2 = self.buf("d_xn", (M, D))
-        self.gemm(d_hf, WT[pre + "mlp.c_fc.weight"], d_xn2)
-        # (for i < L-1 the MLP-adapter fc2 bias grad was fused into the LN backward of block i+1 that produced dx)
-        self._adapter_bwd("MLP_Adapter", pre, dx, S["xn2"], S["h_m"], S["g_m"], W, WT, grads, d, mask_m, d.scale,
-                          d_xn2, d_xn2, db2_fused=(i < d.L - 1))
-        m3, r3 = S["ln2"]
-        dx2 = dx                                              # residual grads accumulate in place in `dx`
-        lib.layernorm_bwd(d_xn2, S["x2"], m3, r3, W[pre + "ln_2.weight"], dx, dx2,
-                          colsum_out=grads[pre + "S_Adapter.D_fc2.bias"])
+        # (for i < L-1 the MLP-adapter fc2 bias grad was fused into the LN backward of block i+1 that produced dx;
+        #  the LN2 backward below produces dx2 and, fused, the S_Adapter fc2 bias grad = column sums of dx2)
+        dx2 = self._mlp_bwd(i, dx, W, WT, grads, d, S, mask_m, db2_fused=(i < d.L - 1),
+                            colsum_for=grads[pre + "S_Adapter.D_fc2.bias"])
         # ---------------- spatial: x2 = x1 + a_s + S_Adapter_noskip(a_s)
         d_as = self.buf("d_a", (M, D))
         self._adapter_bwd("S_Adapter", pre, dx2, S["a_s"], S["h_s"], S["g_s"], W, WT, grads, d, None, 1.0, d_as, dx2,

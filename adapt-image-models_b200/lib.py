@@ -58,6 +58,8 @@ SIGNATURES = {
     "aimb_attn_temporal_fwd": [_P, _P, _I, _I, _I, _I, _I, _P],
     "aimb_attn_temporal_bwd": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "aimb_fork_weights": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "aimb_fork_combine": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "aimb_fork_combine_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
 }
 
 _lib = None
@@ -282,3 +284,15 @@ def fork_weights(qkv, kc, w_o, w_c, frames, n, D):
     _count()
     _chk(load().aimb_fork_weights(_ptr(_c(qkv)), _ptr(_c(kc)), _ptr(w_o), _ptr(w_c), frames, n, D, dt_code(qkv),
                                   _stream()), "fork_weights")
+
+
+def fork_combine(x, a_o, s_frame, lam, rs, out, BT, n):
+    _count()
+    _chk(load().aimb_fork_combine(_ptr(_c(x)), _ptr(_c(a_o)), _ptr(_c(s_frame)), _ptr(lam), _ptr(rs), _ptr(_c(out)), BT, n,
+                                  x.shape[-1], dt_code(x), _stream()), "fork_combine")
+
+
+def fork_combine_bwd(dx, lam, rs, d_ao, d_s, BT, n):
+    _count()
+    _chk(load().aimb_fork_combine_bwd(_ptr(_c(dx)), _ptr(lam), _ptr(rs), _ptr(_c(d_ao)), _ptr(_c(d_s)), BT, n, dx.shape[-1],
+                                      dt_code(dx), _stream()), "fork_combine_bwd")

@@ -159,6 +159,14 @@ int aimb_attn_temporal_bwd(const void* qkv, const void* d_o, void* d_qkv, int32_
 int aimb_fork_weights(const void* qkv, const void* kc, float* w_o, float* w_c, int32_t frames, int32_t n,
                       int32_t D, int32_t dtype, void* stream);
 
+/* out[f,i,:] = x[f,i,:] + (1 - lam[f]) * a_o[f,i,:] + rs[i] * s_frame[f,:]   (vit_clip.py:275; s_frame = scale *
+ * S_Adapter(lam * a_c) is constant over the tokens of a frame because the cross attention has a single key). */
+int aimb_fork_combine(const void* x, const void* a_o, const void* s_frame, const float* lam, const float* rs, void* out,
+                      int32_t BT, int32_t n, int32_t D, int32_t dtype, void* stream);
+/* d_ao[f,i,:] = (1 - lam[f]) * dx[f,i,:] ;  d_s[f,:] = sum_i rs[i] * dx[f,i,:] */
+int aimb_fork_combine_bwd(const void* dx, const float* lam, const float* rs, void* d_ao, void* d_s, int32_t BT, int32_t n,
+                          int32_t D, int32_t dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,7 +21,7 @@ def _build(cfg: O.OracleCfg, mode: str, drop_path_rate=0.0):
     m = aimb200.build_backbone(dict(type="ViT_CLIP", input_resolution=cfg.input_resolution, num_frames=cfg.num_frames,
                                     patch_size=cfg.patch_size, width=cfg.width, layers=cfg.layers, heads=cfg.heads,
                                     drop_path_rate=drop_path_rate, num_tadapter=cfg.num_tadapter,
-                                    adapter_scale=cfg.adapter_scale, compute_dtype=mode))
+                                    adapter_scale=cfg.adapter_scale, compute_dtype=mode, block=cfg.block))
     m.init_weights()
     m.load_state_dict(O.fixture_state_dict(cfg))
     return m.cuda()
@@ -39,10 +39,10 @@ def _cuda_logits_and_grads(m, cfg, x, hw, hb, labels):
 
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
-@pytest.mark.parametrize("nt", [1, 2])
-def test_tiny_logits_and_all_grads_vs_golden(mode, nt):
-    gold = np.load(os.path.join(G, "tiny_aim" + ("_nt2" if nt == 2 else "") + ".npz"))
-    cfg = O.OracleCfg(**TINY, block="aim", num_tadapter=nt)
+@pytest.mark.parametrize("block,nt", [("aim", 1), ("aim", 2), ("fork", 1)])
+def test_tiny_logits_and_all_grads_vs_golden(mode, block, nt):
+    gold = np.load(os.path.join(G, f"tiny_{block}" + ("_nt2" if nt == 2 else "") + ".npz"))
+    cfg = O.OracleCfg(**TINY, block=block, num_tadapter=nt)
     m = _build(cfg, mode)
     x = O.fixture_clip(cfg, 2)
     hw, hb = O.fixture_head(cfg, 16)
@@ -64,10 +64,13 @@ def test_tiny_logits_and_all_grads_vs_golden(mode, nt):
 
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
-def test_vitb16_8x224_logits_vs_golden_and_oracle(mode):
-    """cfg1 of BASELINE.json (the reference correctness fixture): ViT-B/16, 8x224, batch 1."""
-    gold = np.load(os.path.join(G, "vitb16_8x224_aim.npz"))
-    cfg = O.OracleCfg(block="aim")
+@pytest.mark.parametrize("block", ["aim", "fork"])
+def test_vitb16_8x224_logits_vs_golden_and_oracle(mode, block):
+    """cfg1 of BASELINE.json (the reference correctness fixture): ViT-B/16, 8x224, batch 1.
+    block='aim' is checked against the reference class AIM (vitclip_aim.py), block='fork' against the in-tree
+    ViT_CLIP (vit_clip.py) — goldens generated from each."""
+    gold = np.load(os.path.join(G, f"vitb16_8x224_{block}.npz"))
+    cfg = O.OracleCfg(block=block)
     m = _build(cfg, mode)
     x = O.fixture_clip(cfg, 1)
     hw, hb = O.fixture_head(cfg, 400)
@@ -110,8 +113,9 @@ def test_bf16_top1_identical_batch4():
     assert torch.equal(lg.argmax(1), ref.argmax(1))
 
 
-def test_droppath_training_matches_oracle_with_same_masks():
-    cfg = O.OracleCfg(**TINY, block="aim")
+@pytest.mark.parametrize("block", ["aim", "fork"])
+def test_droppath_training_matches_oracle_with_same_masks(block):
+    cfg = O.OracleCfg(**TINY, block=block)
     m = _build(cfg, "fp32", drop_path_rate=0.5).train()
     x = O.fixture_clip(cfg, 2)
     torch.manual_seed(3)
