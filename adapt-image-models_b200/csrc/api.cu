@@ -11,7 +11,11 @@ int attn_spatial_bwd_mma(const void* qkv, const void* o, const void* d_o, const 
                          int heads, cudaStream_t s);
 }  // namespace aimb
 
+namespace aimb { int g_pdl_enabled = 1; }
+
 using namespace aimb;
+
+extern "C" void aimb_debug_set_pdl(int on) { g_pdl_enabled = on; }
 
 extern "C" int aimb_version(void) { return 100; }
 

@@ -89,6 +89,7 @@ __device__ __forceinline__ void load_tile_async(bf16* dst, const bf16* src, int6
 // ------------------------------------------------------------------------------------------ forward
 __global__ void __launch_bounds__(256, 2) attn_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o,
                                                               float* __restrict__ lse, int n, int heads, int wpc) {
+    pdl_grid_sync();
     extern __shared__ __align__(16) uint8_t smraw[];
     const int D = heads * HD, ld = 3 * D;
     const int f = blockIdx.x / heads, h = blockIdx.x % heads;
@@ -204,6 +205,7 @@ template <int NW>
 __global__ void __launch_bounds__(NW * 32) attn_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o,
                                                            const bf16* __restrict__ d_o, const float* __restrict__ lse,
                                                            bf16* __restrict__ d_qkv, int n, int heads) {
+    pdl_grid_sync();
     extern __shared__ __align__(16) uint8_t smraw[];
     const int D = heads * HD, ld = 3 * D;
     const int f = blockIdx.x / heads, h = blockIdx.x % heads;
@@ -406,7 +408,7 @@ int attn_spatial_fwd_mma(const void* qkv, void* o, float* lse, int frames, int n
         attr_set = true;
     }
     dim3 grid(frames * heads, nsplit);
-    attn_fwd_mma_kernel<<<grid, wpc * 32, smem, s>>>((const bf16*)qkv, (bf16*)o, lse, n, heads, wpc);
+    launch_k((attn_fwd_mma_kernel), dim3(grid), dim3(wpc * 32), smem, s, (const bf16*)qkv, (bf16*)o, lse, n, heads, wpc);
     AIMB_CHECK_LAUNCH();
     return AIMB_OK;
 }
@@ -420,7 +422,7 @@ static int bwd_launch(const void* qkv, const void* o, const void* d_o, const flo
             return AIMB_ERR_CUDA;
         attr_set = true;
     }
-    attn_bwd_mma_kernel<NW><<<frames * heads, ((n + 15) / 16) * 32, smem, s>>>((const bf16*)qkv, (const bf16*)o, (const bf16*)d_o,
+    launch_k((attn_bwd_mma_kernel<NW>), dim3(frames * heads), dim3(((n + 15) / 16) * 32), smem, s, (const bf16*)qkv, (const bf16*)o, (const bf16*)d_o,
                                                                             lse, (bf16*)d_qkv, n, heads);
     AIMB_CHECK_LAUNCH();
     return AIMB_OK;

@@ -25,6 +25,7 @@ __device__ __forceinline__ void load_rows_to_smem(float* dst, const T* src, int6
 template <typename T>
 __global__ void __launch_bounds__(256) attn_spatial_fwd_simt(const T* __restrict__ qkv, T* __restrict__ o,
                                                              float* __restrict__ lse, int n, int heads) {
+    pdl_grid_sync();
     extern __shared__ float sm[];
     const int D = heads * DH, ld = 3 * D;
     const int f = blockIdx.x / heads, h = blockIdx.x % heads;
@@ -87,6 +88,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) attn_spatial_bwd_simt(const T* __restrict__ qkv, const T* __restrict__ o,
                                                              const T* __restrict__ d_o, const float* __restrict__ lse,
                                                              T* __restrict__ d_qkv, int n, int heads) {
+    pdl_grid_sync();
     extern __shared__ float sm[];
     const int D = heads * DH, ld = 3 * D;
     const int f = blockIdx.x / heads, h = blockIdx.x % heads;
@@ -222,6 +224,7 @@ __device__ __forceinline__ float dot64(const float* a, const float* b) {
 template <typename T, int T_>
 __global__ void __launch_bounds__(128) attn_temporal_fwd_kernel(const T* __restrict__ qkv, T* __restrict__ o, int B, int n,
                                                                 int heads) {
+    pdl_grid_sync();
     extern __shared__ __align__(16) float sm[];
     constexpr int PS = T_ + 4;
     constexpr int UI = T_ <= 8 ? T_ : 2;      // outer-loop unroll: full only for short sequences (register pressure)
@@ -290,6 +293,7 @@ __global__ void __launch_bounds__(128) attn_temporal_fwd_kernel(const T* __restr
 template <typename T, int T_>
 __global__ void __launch_bounds__(128) attn_temporal_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ d_o,
                                                                 T* __restrict__ d_qkv, int B, int n, int heads) {
+    pdl_grid_sync();
     extern __shared__ __align__(16) float sm[];
     constexpr int PS = T_ + 4;
     constexpr int UI = T_ <= 8 ? T_ : 2;      // outer-loop unroll: full only for short sequences (register pressure)
@@ -401,7 +405,7 @@ static int temporal_fwd_launch(const void* qkv, void* o, int B, int n, int heads
         once = true;
     }
     int64_t probs = (int64_t)B * n * heads;
-    attn_temporal_fwd_kernel<T, T_><<<(unsigned)((probs + 3) / 4), 128, smem, s>>>((const T*)qkv, (T*)o, B, n, heads);
+    launch_k((attn_temporal_fwd_kernel<T, T_>), dim3((unsigned)((probs + 3) / 4)), dim3(128), smem, s, (const T*)qkv, (T*)o, B, n, heads);
     AIMB_CHECK_LAUNCH();
     return AIMB_OK;
 }
@@ -415,7 +419,7 @@ static int temporal_bwd_launch(const void* qkv, const void* d_o, void* d_qkv, in
         once = true;
     }
     int64_t probs = (int64_t)B * n * heads;
-    attn_temporal_bwd_kernel<T, T_><<<(unsigned)((probs + 3) / 4), 128, smem, s>>>((const T*)qkv, (const T*)d_o, (T*)d_qkv, B, n,
+    launch_k((attn_temporal_bwd_kernel<T, T_>), dim3((unsigned)((probs + 3) / 4)), dim3(128), smem, s, (const T*)qkv, (const T*)d_o, (T*)d_qkv, B, n,
                                                                                    heads);
     AIMB_CHECK_LAUNCH();
     return AIMB_OK;
@@ -448,6 +452,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) fork_weights_kernel(const T* __restrict__ qkv, const T* __restrict__ kc,
                                                            float* __restrict__ w_o, float* __restrict__ w_c, int n,
                                                            int D) {
+    pdl_grid_sync();
     extern __shared__ float sm[];
     const int f = blockIdx.x, i0 = blockIdx.y * 8;   // 8 query rows per block (one per warp)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -490,7 +495,7 @@ int spatial_fwd_simt_launch(const void* qkv, void* o, float* lse, int frames, in
             return AIMB_ERR_CUDA;
         attr_set = true;
     }
-    attn_spatial_fwd_simt<T><<<frames * heads, 256, smem, s>>>((const T*)qkv, (T*)o, lse, n, heads);
+    launch_k((attn_spatial_fwd_simt<T>), dim3(frames * heads), dim3(256), smem, s, (const T*)qkv, (T*)o, lse, n, heads);
     AIMB_CHECK_LAUNCH();
     return AIMB_OK;
 }
@@ -505,7 +510,7 @@ int spatial_bwd_simt_launch(const void* qkv, const void* o, const void* d_o, con
             return AIMB_ERR_CUDA;
         attr_set = true;
     }
-    attn_spatial_bwd_simt<T><<<frames * heads, 256, smem, s>>>((const T*)qkv, (const T*)o, (const T*)d_o, lse, (T*)d_qkv, n,
+    launch_k((attn_spatial_bwd_simt<T>), dim3(frames * heads), dim3(256), smem, s, (const T*)qkv, (const T*)o, (const T*)d_o, lse, (T*)d_qkv, n,
                                                                heads);
     AIMB_CHECK_LAUNCH();
     return AIMB_OK;
@@ -558,9 +563,9 @@ extern "C" int aimb_fork_weights(const void* qkv, const void* kc, float* w_o, fl
     dim3 grid(frames, (n + 7) / 8);
     size_t smem = (size_t)8 * D * 4;
     if (dtype == AIMB_BF16)
-        fork_weights_kernel<bf16><<<grid, 256, smem, s>>>((const bf16*)qkv, (const bf16*)kc, w_o, w_c, n, D);
+        launch_k((fork_weights_kernel<bf16>), dim3(grid), dim3(256), smem, s, (const bf16*)qkv, (const bf16*)kc, w_o, w_c, n, D);
     else if (dtype == AIMB_F32)
-        fork_weights_kernel<float><<<grid, 256, smem, s>>>((const float*)qkv, (const float*)kc, w_o, w_c, n, D);
+        launch_k((fork_weights_kernel<float>), dim3(grid), dim3(256), smem, s, (const float*)qkv, (const float*)kc, w_o, w_c, n, D);
     else return AIMB_ERR_ARG;
     AIMB_CHECK_LAUNCH();
     return AIMB_OK;

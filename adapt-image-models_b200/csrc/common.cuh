@@ -15,6 +15,33 @@ namespace aimb {
 
 typedef __nv_bfloat16 bf16;
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------------
+// Every kernel of the library is launched with programmaticStreamSerialization allowed: the next kernel's CTAs may be
+// scheduled (and run their prologue) while the previous kernel drains.  Protocol, identical in every kernel:
+//   pdl_trigger()  - as early as possible: lets the dependent grid start launching once all CTAs have started
+//   pdl_wait()     - before the FIRST access to global memory: blocks until the previous grid has fully completed and
+//                    its writes are visible.  Safe transitively (a grid cannot complete before its own wait returns).
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_grid_sync() { pdl_trigger(); pdl_wait(); }
+
+extern int g_pdl_enabled;   // host side (api.cu); 0 disables the launch attribute (debug)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = g_pdl_enabled ? 1 : 0;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 template <typename T> struct DT;
 template <> struct DT<float> {
     static __device__ __forceinline__ float ld(const float* p) { return *p; }

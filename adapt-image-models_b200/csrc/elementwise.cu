@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(128) layernorm_fwd_kernel(const T* __restrict_
                                                             const T* __restrict__ beta, T* __restrict__ y,
                                                             float* __restrict__ mean_o, float* __restrict__ rstd_o,
                                                             int64_t rows, int D, float eps) {
+    pdl_grid_sync();
     int lane = threadIdx.x & 31;
     int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -122,6 +123,7 @@ __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const T* __restrict_
                                                             const T* __restrict__ gamma, const T* dres, T* dx,
                                                             const float* __restrict__ cs_w, int cs_mod, float cs_alpha,
                                                             float* __restrict__ cs_out, int64_t rows, int D) {
+    pdl_grid_sync();
     constexpr int V = RowRegs<T>::V, NIT = RowRegs<T>::NIT;
     constexpr int NWARP = 4;
     __shared__ float red[RPW > 1 ? NWARP * MAXD : 1];
@@ -208,6 +210,7 @@ __global__ void __launch_bounds__(128) stem_assemble_ln_kernel(const T* __restri
                                                                T* __restrict__ z, T* __restrict__ xo,
                                                                float* __restrict__ mean_o, float* __restrict__ rstd_o,
                                                                int BT, int T_, int n, int D, float eps) {
+    pdl_grid_sync();
     constexpr int V = RowRegs<T>::V, NIT = RowRegs<T>::NIT;
     int lane = threadIdx.x & 31;
     int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -246,6 +249,7 @@ template <typename TI, typename T>
 __global__ void __launch_bounds__(256) im2col_kernel(const TI* __restrict__ x, const float* __restrict__ mean,
                                                      const float* __restrict__ std_, T* __restrict__ cols, int B,
                                                      int T_, int H, int W, int p, int kpad) {
+    pdl_grid_sync();
     int G = W / p, Gy = H / p;
     int64_t total = (int64_t)B * T_ * 3 * Gy * p * G;  // one thread per (b, t, c, gy, ky, gx): p contiguous pixels
     int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -272,6 +276,7 @@ __global__ void __launch_bounds__(128) tail_fwd_kernel(const T* __restrict__ x, 
                                                        const T* __restrict__ beta, float* __restrict__ feat,
                                                        float* __restrict__ mean_o, float* __restrict__ rstd_o, int BT,
                                                        int T_, int n, int D, float eps) {
+    pdl_grid_sync();
     constexpr int V = RowRegs<T>::V, NIT = RowRegs<T>::NIT;
     int lane = threadIdx.x & 31;
     int f = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -302,6 +307,7 @@ __global__ void __launch_bounds__(128) tail_bwd_kernel(const float* __restrict__
                                                        const float* __restrict__ rstd_i, const T* __restrict__ gamma,
                                                        T* __restrict__ dx, float* __restrict__ dgamma,
                                                        float* __restrict__ dbeta, int BT, int T_, int n, int D) {
+    pdl_grid_sync();
     constexpr int V = RowRegs<T>::V, NIT = RowRegs<T>::NIT;
     int lane = threadIdx.x & 31;
     int f = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -352,6 +358,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, int64_t ld,
                                                      const float* __restrict__ row_scale, int row_mod, float alpha,
                                                      float* __restrict__ out, int64_t R, int C, int rows_per_block) {
+    pdl_grid_sync();
     constexpr int V = VecIO<T>::N;
     __shared__ float red[8][32][V + 1];
     const int c = (blockIdx.x * 32 + threadIdx.x) * V;
@@ -387,6 +394,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, in
 template <typename T>
 __global__ void __launch_bounds__(256) transpose_batched_kernel(const T* __restrict__ src, T* __restrict__ dst,
                                                                 const int64_t* __restrict__ table) {
+    pdl_grid_sync();
     __shared__ T tile[32][33];
     const int64_t off = table[3 * blockIdx.z];
     const int R = (int)table[3 * blockIdx.z + 1], C = (int)table[3 * blockIdx.z + 2];
@@ -414,6 +422,7 @@ __global__ void __launch_bounds__(256) transpose_batched_kernel(const T* __restr
 template <typename T>
 __global__ void __launch_bounds__(256) temb_grad_kernel(const T* __restrict__ dz, float* __restrict__ out, int T_, int n,
                                                         int D) {
+    pdl_grid_sync();
     __shared__ float red[8][33];
     int c = blockIdx.x * 32 + threadIdx.x;
     int f = blockIdx.y;
@@ -432,6 +441,7 @@ __global__ void __launch_bounds__(256) temb_grad_kernel(const T* __restrict__ dz
 
 template <typename T>
 __global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ in, T* __restrict__ out, int R, int C) {
+    pdl_grid_sync();
     __shared__ T tile[32][33];
     int c = blockIdx.x * 32 + threadIdx.x;
     for (int i = threadIdx.y; i < 32; i += 8) {
@@ -454,6 +464,7 @@ __global__ void __launch_bounds__(128) fork_combine_kernel(const T* __restrict__
                                                            const T* __restrict__ sfr, const float* __restrict__ lam,
                                                            const float* __restrict__ rs, T* __restrict__ out, int BT, int n,
                                                            int D) {
+    pdl_grid_sync();
     constexpr int V = VecIO<T>::N;
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -475,6 +486,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) fork_combine_bwd_kernel(const T* __restrict__ dx, const float* __restrict__ lam,
                                                                const float* __restrict__ rs, T* __restrict__ d_ao,
                                                                T* __restrict__ d_s, int n, int D) {
+    pdl_grid_sync();
     constexpr int V = VecIO<T>::N;
     __shared__ float red[8][32][V + 1];
     const int f = blockIdx.y;
@@ -525,10 +537,10 @@ extern "C" int aimb_layernorm_fwd(const void* x, const void* gamma, const void* 
     cudaStream_t s = (cudaStream_t)stream;
     unsigned grid = (unsigned)((rows + 3) / 4);
     if (dtype == AIMB_BF16)
-        layernorm_fwd_kernel<bf16><<<grid, 128, 0, s>>>((const bf16*)x, (const bf16*)gamma, (const bf16*)beta, (bf16*)y,
+        launch_k((layernorm_fwd_kernel<bf16>), dim3(grid), dim3(128), 0, s, (const bf16*)x, (const bf16*)gamma, (const bf16*)beta, (bf16*)y,
                                                         mean, rstd, rows, D, eps);
     else if (dtype == AIMB_F32)
-        layernorm_fwd_kernel<float><<<grid, 128, 0, s>>>((const float*)x, (const float*)gamma, (const float*)beta,
+        launch_k((layernorm_fwd_kernel<float>), dim3(grid), dim3(128), 0, s, (const float*)x, (const float*)gamma, (const float*)beta,
                                                          (float*)y, mean, rstd, rows, D, eps);
     else return AIMB_ERR_ARG;
     AIMB_CHECK_LAUNCH();
@@ -545,21 +557,21 @@ static int ln_bwd_launch(const void* dy, const void* x, const float* mean, const
         constexpr int RPW = 8;
         unsigned grid = (unsigned)((rows + 4 * RPW - 1) / (4 * RPW));
         if (dtype == AIMB_BF16)
-            layernorm_bwd_kernel<bf16, RPW><<<grid, 128, 0, s>>>((const bf16*)dy, (const bf16*)x, mean, rstd, (const bf16*)gamma,
+            launch_k((layernorm_bwd_kernel<bf16, RPW>), dim3(grid), dim3(128), 0, s, (const bf16*)dy, (const bf16*)x, mean, rstd, (const bf16*)gamma,
                                                                  (const bf16*)dres, (bf16*)dx, cs_w, cs_mod > 0 ? cs_mod : 1,
                                                                  cs_alpha, cs_out, rows, D);
         else if (dtype == AIMB_F32)
-            layernorm_bwd_kernel<float, RPW><<<grid, 128, 0, s>>>((const float*)dy, (const float*)x, mean, rstd,
+            launch_k((layernorm_bwd_kernel<float, RPW>), dim3(grid), dim3(128), 0, s, (const float*)dy, (const float*)x, mean, rstd,
                                                                   (const float*)gamma, (const float*)dres, (float*)dx, cs_w,
                                                                   cs_mod > 0 ? cs_mod : 1, cs_alpha, cs_out, rows, D);
         else return AIMB_ERR_ARG;
     } else {
         unsigned grid = (unsigned)((rows + 3) / 4);
         if (dtype == AIMB_BF16)
-            layernorm_bwd_kernel<bf16, 1><<<grid, 128, 0, s>>>((const bf16*)dy, (const bf16*)x, mean, rstd, (const bf16*)gamma,
+            launch_k((layernorm_bwd_kernel<bf16, 1>), dim3(grid), dim3(128), 0, s, (const bf16*)dy, (const bf16*)x, mean, rstd, (const bf16*)gamma,
                                                                (const bf16*)dres, (bf16*)dx, nullptr, 1, 1.f, nullptr, rows, D);
         else if (dtype == AIMB_F32)
-            layernorm_bwd_kernel<float, 1><<<grid, 128, 0, s>>>((const float*)dy, (const float*)x, mean, rstd,
+            launch_k((layernorm_bwd_kernel<float, 1>), dim3(grid), dim3(128), 0, s, (const float*)dy, (const float*)x, mean, rstd,
                                                                 (const float*)gamma, (const float*)dres, (float*)dx, nullptr, 1,
                                                                 1.f, nullptr, rows, D);
         else return AIMB_ERR_ARG;
@@ -592,11 +604,11 @@ extern "C" int aimb_stem_assemble_ln(const void* tok, const void* cls, const voi
     int64_t rows = (int64_t)B * T * n;
     unsigned grid = (unsigned)((rows + 3) / 4);
     if (dtype == AIMB_BF16)
-        stem_assemble_ln_kernel<bf16><<<grid, 128, 0, s>>>((const bf16*)tok, (const bf16*)cls, (const bf16*)pos,
+        launch_k((stem_assemble_ln_kernel<bf16>), dim3(grid), dim3(128), 0, s, (const bf16*)tok, (const bf16*)cls, (const bf16*)pos,
                                                            (const bf16*)temb, (const bf16*)gamma, (const bf16*)beta,
                                                            (bf16*)z, (bf16*)x, mean, rstd, B * T, T, n, D, eps);
     else if (dtype == AIMB_F32)
-        stem_assemble_ln_kernel<float><<<grid, 128, 0, s>>>((const float*)tok, (const float*)cls, (const float*)pos,
+        launch_k((stem_assemble_ln_kernel<float>), dim3(grid), dim3(128), 0, s, (const float*)tok, (const float*)cls, (const float*)pos,
                                                             (const float*)temb, (const float*)gamma, (const float*)beta,
                                                             (float*)z, (float*)x, mean, rstd, B * T, T, n, D, eps);
     else return AIMB_ERR_ARG;
@@ -610,9 +622,9 @@ static int im2col_dispatch(const void* x, const float* mean, const float* std_, 
     int64_t total = (int64_t)B * T * 3 * (H / p) * p * (W / p);
     unsigned grid = (unsigned)((total + 255) / 256);
     if (dtype == AIMB_BF16)
-        im2col_kernel<TI, bf16><<<grid, 256, 0, s>>>((const TI*)x, mean, std_, (bf16*)cols, B, T, H, W, p, kpad);
+        launch_k((im2col_kernel<TI, bf16>), dim3(grid), dim3(256), 0, s, (const TI*)x, mean, std_, (bf16*)cols, B, T, H, W, p, kpad);
     else if (dtype == AIMB_F32)
-        im2col_kernel<TI, float><<<grid, 256, 0, s>>>((const TI*)x, mean, std_, (float*)cols, B, T, H, W, p, kpad);
+        launch_k((im2col_kernel<TI, float>), dim3(grid), dim3(256), 0, s, (const TI*)x, mean, std_, (float*)cols, B, T, H, W, p, kpad);
     else return AIMB_ERR_ARG;
     AIMB_CHECK_LAUNCH();
     return AIMB_OK;
@@ -639,10 +651,10 @@ extern "C" int aimb_tail_fwd(const void* x, const void* gamma, const void* beta,
     cudaStream_t s = (cudaStream_t)stream;
     unsigned grid = (unsigned)((B * T + 3) / 4);
     if (dtype == AIMB_BF16)
-        tail_fwd_kernel<bf16><<<grid, 128, 0, s>>>((const bf16*)x, (const bf16*)gamma, (const bf16*)beta, feat, mean, rstd,
+        launch_k((tail_fwd_kernel<bf16>), dim3(grid), dim3(128), 0, s, (const bf16*)x, (const bf16*)gamma, (const bf16*)beta, feat, mean, rstd,
                                                    B * T, T, n, D, eps);
     else if (dtype == AIMB_F32)
-        tail_fwd_kernel<float><<<grid, 128, 0, s>>>((const float*)x, (const float*)gamma, (const float*)beta, feat, mean,
+        launch_k((tail_fwd_kernel<float>), dim3(grid), dim3(128), 0, s, (const float*)x, (const float*)gamma, (const float*)beta, feat, mean,
                                                     rstd, B * T, T, n, D, eps);
     else return AIMB_ERR_ARG;
     AIMB_CHECK_LAUNCH();
@@ -663,10 +675,10 @@ extern "C" int aimb_tail_bwd(const float* dfeat, const void* x, const float* mea
     if (cudaMemsetAsync(dbeta, 0, (size_t)D * 4, s) != cudaSuccess) return AIMB_ERR_CUDA;
     unsigned grid = (unsigned)((B * T + 3) / 4);
     if (dtype == AIMB_BF16)
-        tail_bwd_kernel<bf16><<<grid, 128, 0, s>>>(dfeat, (const bf16*)x, mean, rstd, (const bf16*)gamma, (bf16*)dx, dgamma,
+        launch_k((tail_bwd_kernel<bf16>), dim3(grid), dim3(128), 0, s, dfeat, (const bf16*)x, mean, rstd, (const bf16*)gamma, (bf16*)dx, dgamma,
                                                    dbeta, B * T, T, n, D);
     else if (dtype == AIMB_F32)
-        tail_bwd_kernel<float><<<grid, 128, 0, s>>>(dfeat, (const float*)x, mean, rstd, (const float*)gamma, (float*)dx,
+        launch_k((tail_bwd_kernel<float>), dim3(grid), dim3(128), 0, s, dfeat, (const float*)x, mean, rstd, (const float*)gamma, (float*)dx,
                                                     dgamma, dbeta, B * T, T, n, D);
     else return AIMB_ERR_ARG;
     AIMB_CHECK_LAUNCH();
@@ -686,9 +698,9 @@ extern "C" int aimb_colsum(const void* x, int64_t ld, const float* row_scale, in
     while (rpb > 16 && (int64_t)gx * ((R + rpb - 1) / rpb) < 296) rpb >>= 1;   // >= 2 waves of blocks
     dim3 grid(gx, (unsigned)((R + rpb - 1) / rpb)), block(32, 8);
     if (dtype == AIMB_BF16)
-        colsum_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)x, ld, row_scale, row_mod, alpha, out, R, C, rpb);
+        launch_k((colsum_kernel<bf16>), dim3(grid), dim3(block), 0, s, (const bf16*)x, ld, row_scale, row_mod, alpha, out, R, C, rpb);
     else if (dtype == AIMB_F32)
-        colsum_kernel<float><<<grid, block, 0, s>>>((const float*)x, ld, row_scale, row_mod, alpha, out, R, C, rpb);
+        launch_k((colsum_kernel<float>), dim3(grid), dim3(block), 0, s, (const float*)x, ld, row_scale, row_mod, alpha, out, R, C, rpb);
     else return AIMB_ERR_ARG;
     AIMB_CHECK_LAUNCH();
     return AIMB_OK;
@@ -701,9 +713,9 @@ extern "C" int aimb_transpose_batched(const void* src, void* dst, const int64_t*
     cudaStream_t s = (cudaStream_t)stream;
     dim3 grid(48, 1, nmat), block(32, 8);
     if (dtype == AIMB_BF16)
-        transpose_batched_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)src, (bf16*)dst, table);
+        launch_k((transpose_batched_kernel<bf16>), dim3(grid), dim3(block), 0, s, (const bf16*)src, (bf16*)dst, table);
     else if (dtype == AIMB_F32)
-        transpose_batched_kernel<float><<<grid, block, 0, s>>>((const float*)src, (float*)dst, table);
+        launch_k((transpose_batched_kernel<float>), dim3(grid), dim3(block), 0, s, (const float*)src, (float*)dst, table);
     else return AIMB_ERR_ARG;
     AIMB_CHECK_LAUNCH();
     return AIMB_OK;
@@ -716,8 +728,8 @@ extern "C" int aimb_temb_grad(const void* dz, float* out, int32_t B, int32_t T, 
     if (cudaMemsetAsync(out, 0, (size_t)T * D * 4, s) != cudaSuccess) return AIMB_ERR_CUDA;
     if (B == 0) return AIMB_OK;
     dim3 grid((D + 31) / 32, B * T), block(32, 8);
-    if (dtype == AIMB_BF16) temb_grad_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)dz, out, T, n, D);
-    else if (dtype == AIMB_F32) temb_grad_kernel<float><<<grid, block, 0, s>>>((const float*)dz, out, T, n, D);
+    if (dtype == AIMB_BF16) launch_k((temb_grad_kernel<bf16>), dim3(grid), dim3(block), 0, s, (const bf16*)dz, out, T, n, D);
+    else if (dtype == AIMB_F32) launch_k((temb_grad_kernel<float>), dim3(grid), dim3(block), 0, s, (const float*)dz, out, T, n, D);
     else return AIMB_ERR_ARG;
     AIMB_CHECK_LAUNCH();
     return AIMB_OK;
@@ -727,8 +739,8 @@ extern "C" int aimb_transpose(const void* in, void* out, int32_t R, int32_t C, i
     if (!in || !out || R <= 0 || C <= 0) return AIMB_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
-    if (dtype == AIMB_BF16) transpose_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)in, (bf16*)out, R, C);
-    else if (dtype == AIMB_F32) transpose_kernel<float><<<grid, block, 0, s>>>((const float*)in, (float*)out, R, C);
+    if (dtype == AIMB_BF16) launch_k((transpose_kernel<bf16>), dim3(grid), dim3(block), 0, s, (const bf16*)in, (bf16*)out, R, C);
+    else if (dtype == AIMB_F32) launch_k((transpose_kernel<float>), dim3(grid), dim3(block), 0, s, (const float*)in, (float*)out, R, C);
     else return AIMB_ERR_ARG;
     AIMB_CHECK_LAUNCH();
     return AIMB_OK;
@@ -741,10 +753,10 @@ extern "C" int aimb_fork_combine(const void* x, const void* a_o, const void* s_f
     cudaStream_t s = (cudaStream_t)stream;
     unsigned grid = (unsigned)(((int64_t)BT * n + 3) / 4);
     if (dtype == AIMB_BF16)
-        fork_combine_kernel<bf16><<<grid, 128, 0, s>>>((const bf16*)x, (const bf16*)a_o, (const bf16*)s_frame, lam, rs, (bf16*)out,
+        launch_k((fork_combine_kernel<bf16>), dim3(grid), dim3(128), 0, s, (const bf16*)x, (const bf16*)a_o, (const bf16*)s_frame, lam, rs, (bf16*)out,
                                                        BT, n, D);
     else if (dtype == AIMB_F32)
-        fork_combine_kernel<float><<<grid, 128, 0, s>>>((const float*)x, (const float*)a_o, (const float*)s_frame, lam, rs,
+        launch_k((fork_combine_kernel<float>), dim3(grid), dim3(128), 0, s, (const float*)x, (const float*)a_o, (const float*)s_frame, lam, rs,
                                                         (float*)out, BT, n, D);
     else return AIMB_ERR_ARG;
     AIMB_CHECK_LAUNCH();
@@ -759,9 +771,9 @@ extern "C" int aimb_fork_combine_bwd(const void* dx, const float* lam, const flo
     const int V = dtype == AIMB_BF16 ? 8 : 4;
     dim3 grid((D / V + 31) / 32, BT), block(32, 8);
     if (dtype == AIMB_BF16)
-        fork_combine_bwd_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)dx, lam, rs, (bf16*)d_ao, (bf16*)d_s, n, D);
+        launch_k((fork_combine_bwd_kernel<bf16>), dim3(grid), dim3(block), 0, s, (const bf16*)dx, lam, rs, (bf16*)d_ao, (bf16*)d_s, n, D);
     else if (dtype == AIMB_F32)
-        fork_combine_bwd_kernel<float><<<grid, block, 0, s>>>((const float*)dx, lam, rs, (float*)d_ao, (float*)d_s, n, D);
+        launch_k((fork_combine_bwd_kernel<float>), dim3(grid), dim3(block), 0, s, (const float*)dx, lam, rs, (float*)d_ao, (float*)d_s, n, D);
     else return AIMB_ERR_ARG;
     AIMB_CHECK_LAUNCH();
     return AIMB_OK;

@@ -11,6 +11,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const T* __restrict__ A, int64_t a_sm, int64_t a_sk,
                                                         const T* __restrict__ B, int64_t b_sn, int64_t b_sk,
                                                         EpiParams epi, int64_t M, int N, int K) {
+    pdl_grid_sync();
     __shared__ __align__(16) float As[SBK][SBM + 4];
     __shared__ __align__(16) float Bs[SBK][SBN + 4];
     const int tid = threadIdx.x;
@@ -74,9 +75,9 @@ int gemm_simt_launch(const void* A, int64_t a_sm, int64_t a_sk, const void* B, i
     if (M == 0) return AIMB_OK;
     dim3 grid((N + SBN - 1) / SBN, (unsigned)((M + SBM - 1) / SBM));
     if (dtype == AIMB_BF16)
-        gemm_simt_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)A, a_sm, a_sk, (const bf16*)B, b_sn, b_sk, epi, M, N, K);
+        launch_k((gemm_simt_kernel<bf16>), dim3(grid), dim3(256), 0, s, (const bf16*)A, a_sm, a_sk, (const bf16*)B, b_sn, b_sk, epi, M, N, K);
     else if (dtype == AIMB_F32)
-        gemm_simt_kernel<float><<<grid, 256, 0, s>>>((const float*)A, a_sm, a_sk, (const float*)B, b_sn, b_sk, epi, M, N,
+        launch_k((gemm_simt_kernel<float>), dim3(grid), dim3(256), 0, s, (const float*)A, a_sm, a_sk, (const float*)B, b_sn, b_sk, epi, M, N,
                                                      K);
     else return AIMB_ERR_ARG;
     AIMB_CHECK_LAUNCH();

@@ -259,6 +259,7 @@ template <int BN, int V>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const EpiParams epi,
                const int M, const int N, const int K) {
+    pdl_trigger();   // the next kernel may start its prologue; it blocks in its own pdl_wait() until this grid is done
     using Cfg = TileCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -290,6 +291,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();      // barrier init, TMEM allocation, descriptor prefetch above overlapped the previous kernel's tail
 
     if (warp == 0) {
         if (lane == 0) {
@@ -389,6 +391,7 @@ template <int BN, int V>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const EpiParams epi,
                 const int M, const int N, const int K) {
+    pdl_trigger();   // the next kernel may start its prologue; it blocks in its own pdl_wait() until this grid is done
     using Cfg = TileCfg2<BN>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -423,6 +426,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     ptx::cluster_sync();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -587,7 +591,7 @@ static int launch_tc_v(const CUtensorMap& ta, const CUtensorMap& tb, const EpiPa
     }
     int total = (N / BN) * ((M + BM - 1) / BM);
     int grid = total < num_sms() ? total : num_sms();
-    gemm_tc_kernel<BN, V><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(ta, tb, p, M, N, K);
+    launch_k((gemm_tc_kernel<BN, V>), dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, s, ta, tb, p, M, N, K);
     AIMB_CHECK_LAUNCH();
     return AIMB_OK;
 }
@@ -617,7 +621,7 @@ static int launch_tc2_v(const CUtensorMap& ta, const CUtensorMap& tb, const EpiP
     int total = (N / BN) * ((M + 2 * BM - 1) / (2 * BM));
     int pairs = num_sms() / 2;
     if (total < pairs) pairs = total;
-    gemm_tc2_kernel<BN, V><<<2 * pairs, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(ta, tb, p, M, N, K);
+    launch_k((gemm_tc2_kernel<BN, V>), dim3(2 * pairs), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, s, ta, tb, p, M, N, K);
     AIMB_CHECK_LAUNCH();
     return AIMB_OK;
 }
@@ -717,6 +721,7 @@ template <int NS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ, float* __restrict__ out,
                 const int64_t ldo, const int transposed_out, const float alpha, const int KB, const int kb_per_split) {
+    pdl_trigger();   // the next kernel may start its prologue; it blocks in its own pdl_wait() until this grid is done
     constexpr int BOX = 64 * 64 * 2;                 // one [64 r][64 c] bf16 box
     constexpr int A_BYTES = 2 * BOX, B_BYTES = (NS / 64) * BOX, STG = A_BYTES + B_BYTES;
     constexpr int STAGES = (200 * 1024) / STG > 6 ? 6 : (200 * 1024) / STG;
@@ -745,6 +750,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();      // barrier init, TMEM allocation, descriptor prefetch above overlapped the previous kernel's tail
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
@@ -834,7 +840,7 @@ static int launch_wgrad(const CUtensorMap& tp, const CUtensorMap& tq, float* out
     int per = (KB + splits - 1) / splits;
     splits = (KB + per - 1) / per;
     dim3 grid(mtiles, splits);
-    wgrad_tc_kernel<NS><<<grid, TC_THREADS, SMEM, s>>>(tp, tq, out, ldo, transposed, alpha, KB, per);
+    launch_k((wgrad_tc_kernel<NS>), dim3(grid), dim3(TC_THREADS), SMEM, s, tp, tq, out, ldo, transposed, alpha, KB, per);
     AIMB_CHECK_LAUNCH();
     return AIMB_OK;
 }
