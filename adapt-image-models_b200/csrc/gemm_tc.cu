@@ -136,7 +136,7 @@ __device__ __forceinline__ void epilogue_vec8(const EpiParams& e, int64_t m, int
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] += t[j];
     }
-    st8_bf16((bf16*)e.out + off, v);
+    if (e.out) st8_bf16((bf16*)e.out + off, v);
 }
 
 // Epilogue of one warp for its 32 rows x NCOLS columns of a tile (shared by the 1-CTA and 2-CTA kernels).
@@ -145,7 +145,8 @@ __device__ __forceinline__ void epilogue_vec8(const EpiParams& e, int64_t m, int
 // chunk's operand prefetch has been issued).
 template <int NCOLS, int ACT, int DACT, int EXT, typename WaitFn>
 __device__ __forceinline__ void epilogue_warp_t(const EpiParams& epi, float* stg, float* scol, int col_in_tile, uint32_t taddr,
-                                                int64_t row_base, int n_base, int M, int lane, WaitFn wait_acc) {
+                                                int64_t row_base, int n_base, int M, int lane, WaitFn wait_acc,
+                                                uint8_t* a2 = nullptr, int a2_row0 = 0, int a2_col0 = 0) {
     // Latency plan: everything that does not depend on the accumulator (bias -> smem, the first chunk's
     // residual / saved-activation operands) is requested BEFORE the accumulator-ready wait; inside the loop the
     // TMEM load of chunk c+1 and the operand loads of chunk c+1 are in flight while chunk c is processed.
@@ -192,6 +193,15 @@ __device__ __forceinline__ void epilogue_warp_t(const EpiParams& epi, float* stg
                 epilogue_vec8<ACT, DACT, EXT>(epi, row, n0, v, bias8, cur, i);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) cs8[j] += v[j];
+            }
+            if (a2) {   // fused adapter: the bf16 result is also the A operand of the second GEMM (K-major, 128B swizzle)
+                const int trow = a2_row0 + rl, tcol = a2_col0 + c + c0;
+                uint4 pk;
+                __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) hp[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                if (row >= M) pk = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4*>(a2 + (tcol >> 6) * (BM * 128) + trow * 128 + ((((tcol & 63) >> 3) ^ (trow & 7)) << 4)) = pk;
             }
         }
         if (epi.colsum_out) {      // bias gradient of the consumer: reduce the 8 row-lanes that share these columns,
@@ -501,6 +511,178 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp == 1) {
         __syncwarp();
         ptx::tmem_dealloc_2cta<Cfg::TMEM_COLS>(tmem_base);
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------- fused adapter
+// Adapter bottleneck (vit_clip.py:51-69) as ONE kernel per direction:
+//   forward : out = res1 + res2 + alpha * rs * (gelu(a W1^T + b1) W2^T + b2)      (h, g' = rs*gelu(h) kept for backward)
+//   backward: d_a = res1 + ((dy W2) . gelu'(h) * alpha * rs) W1                   (d_h kept for the weight gradients,
+//                                                                                 its column sums = db1)
+// Per 128-row tile: GEMM1 (K = D, N = R) accumulates in TMEM; its epilogue writes the bf16 hidden tile to global AND,
+// swizzled, into shared memory, where it is the K-major A operand of GEMM2 (K = R, N = D in chunks of BN2) — the
+// [M, R] hidden never makes a round trip through HBM between the two GEMMs and the second launch disappears.
+// TMEM: acc1 = columns [0, R); acc2 double-buffered at [0, BN2) (reuses acc1's columns once it is drained) and
+// [256, 256 + BN2).  One tile per CTA (M/128 <= #SMs for every configuration of the path).
+template <int R, int BN2> struct AdapterCfg {
+    static constexpr int B1_BYTES = R * BK * 2, B2_BYTES = BN2 * BK * 2;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + (B1_BYTES > B2_BYTES ? B1_BYTES : B2_BYTES);
+    static constexpr int A2_BYTES = (R / BK) * BM * 128;
+    static constexpr int STAGES_RAW = (232448 - STG_BYTES - A2_BYTES - 1024 - 256) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 4 ? 4 : STAGES_RAW;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + A2_BYTES + STG_BYTES + 1024 + 256;
+    static_assert(STAGES >= 2, "adapter kernel needs at least a double-buffered ring");
+    static_assert(R % 64 == 0 && R <= 256 && BN2 <= 256 && BN2 % 64 == 0, "TMEM plan");
+};
+
+template <int R, int BN2, int V1, int V2>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+adapter_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB1,
+                  const __grid_constant__ CUtensorMap tmB2, const EpiParams epi1, const EpiParams epi2, const int M, const int D) {
+    pdl_trigger();
+    using Cfg = AdapterCfg<R, BN2>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* a2 = smem + STAGES * Cfg::STAGE_BYTES;                               // [R/64][128 rows][128 B] swizzled
+    float* stg_all = reinterpret_cast<float*>(a2 + Cfg::A2_BYTES);
+    float* scol = stg_all + EPI_WARPS * STG_WARP_FLOATS;
+    if (threadIdx.x < 256) scol[threadIdx.x] = 0.f;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(a2 + Cfg::A2_BYTES + STG_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* acc1_bar = empty_bar + STAGES;      // GEMM1 accumulator complete
+    uint64_t* a2_bar = acc1_bar + 1;              // hidden tile written to smem by the 8 epilogue warps
+    uint64_t* tfull_bar = a2_bar + 1;             // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;         // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_blk = blockIdx.x;
+    const int KB1 = D / BK, KB2 = R / BK, NCH = D / BN2;
+
+    if (threadIdx.x == 0) {
+        ptx::prefetch_tmap(&tmA);
+        ptx::prefetch_tmap(&tmB1);
+        ptx::prefetch_tmap(&tmB2);
+        for (int i = 0; i < STAGES; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
+        ptx::mbar_init(acc1_bar, 1);
+        ptx::mbar_init(a2_bar, EPI_WARPS);
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], EPI_WARPS); }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) ptx::tmem_alloc<512>(tmem_ptr);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = 0; kb < KB1; ++kb) {
+                ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                ptx::mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + Cfg::B1_BYTES);
+                uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                ptx::tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+                ptx::tma_load_2d(sa + A_STAGE_BYTES, &tmB1, &full_bar[stage], kb * BK, 0);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            for (int j = 0; j < NCH; ++j)
+                for (int kb = 0; kb < KB2; ++kb) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::B2_BYTES);
+                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    ptx::tma_load_2d(sa + A_STAGE_BYTES, &tmB2, &full_bar[stage], kb * BK, j * BN2);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc1 = ptx::umma_idesc_bf16(BM, R);
+            constexpr uint32_t idesc2 = ptx::umma_idesc_bf16(BM, BN2);
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = 0; kb < KB1; ++kb) {
+                ptx::mbar_wait(&full_bar[stage], phase);
+                ptx::tc_fence_after();
+                const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                const uint64_t adesc = ptx::umma_desc_kmajor_sw128(sa);
+                const uint64_t bdesc = ptx::umma_desc_kmajor_sw128(sa + A_STAGE_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k)
+                    ptx::umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc1, (kb | k) != 0 ? 1u : 0u);
+                ptx::umma_commit(&empty_bar[stage]);
+                if (kb == KB1 - 1) ptx::umma_commit(acc1_bar);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            ptx::mbar_wait(a2_bar, 0);            // hidden tile is in smem (and acc1's TMEM columns are drained)
+            ptx::tc_fence_after();
+            const uint32_t a2s = ptx::smem_u32(a2);
+            for (int j = 0; j < NCH; ++j) {
+                const int buf = j & 1;
+                ptx::mbar_wait(&tempty_bar[buf], ((j >> 1) & 1) ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * 256;
+                for (int kb = 0; kb < KB2; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t sb = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES + A_STAGE_BYTES);
+                    const uint64_t adesc = ptx::umma_desc_kmajor_sw128(a2s + kb * (BM * 128));
+                    const uint64_t bdesc = ptx::umma_desc_kmajor_sw128(sb);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc2, (kb | k) != 0 ? 1u : 0u);
+                    ptx::umma_commit(&empty_bar[stage]);
+                    if (kb == KB2 - 1) ptx::umma_commit(&tfull_bar[buf]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;
+        float* stg = stg_all + (warp - 2) * STG_WARP_FLOATS;
+        const int64_t row_base = (int64_t)m_blk * BM + quad * 32;
+        using E1 = EpiVariant<V1>;
+        using E2 = EpiVariant<V2>;
+        // ---- epilogue 1: hidden tile -> global (kept for backward) and -> smem (A operand of GEMM2)
+        epilogue_warp_t<R / 2, E1::ACT, E1::DACT, E1::EXT>(
+            epi1, stg, scol, half * (R / 2), tmem_base + ((uint32_t)(quad * 32) << 16) + half * (R / 2), row_base,
+            half * (R / 2), M, lane,
+            [&]() {
+                ptx::mbar_wait(acc1_bar, 0);
+                ptx::tc_fence_after();
+            },
+            a2, quad * 32, half * (R / 2));
+        ptx::fence_proxy_async();            // make the generic-proxy smem writes visible to the tensor core (async proxy)
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(a2_bar);
+        if (epi1.colsum_out) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const int te = threadIdx.x - 64;
+            if (te < R) { atomicAdd(epi1.colsum_out + te, scol[te]); scol[te] = 0.f; }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+        // ---- epilogue 2: output chunks
+        for (int j = 0; j < NCH; ++j) {
+            const int buf = j & 1;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 256 + half * (BN2 / 2);
+            epilogue_warp_t<BN2 / 2, E2::ACT, E2::DACT, E2::EXT>(epi2, stg, scol, half * (BN2 / 2), taddr, row_base,
+                                                                j * BN2 + half * (BN2 / 2), M, lane, [&]() {
+                                                                    ptx::mbar_wait(&tfull_bar[buf], (j >> 1) & 1);
+                                                                    ptx::tc_fence_after();
+                                                                });
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty_bar[buf]);
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        ptx::tmem_dealloc<512>(tmem_base);
     }
 }
 
@@ -869,6 +1051,54 @@ int wgrad_tc_launch(const void* dY, int64_t ldy, const void* X, int64_t ldx, flo
     return AIMB_ERR_UNSUPPORTED;
 }
 
+// ---- fused adapter host side
+template <int R, int BN2, int V1, int V2>
+static int launch_adapter_v(const CUtensorMap& ta, const CUtensorMap& tb1, const CUtensorMap& tb2, const EpiParams& e1,
+                            const EpiParams& e2, int M, int D, cudaStream_t s) {
+    using Cfg = AdapterCfg<R, BN2>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(adapter_tc_kernel<R, BN2, V1, V2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) !=
+            cudaSuccess)
+            return AIMB_ERR_CUDA;
+        attr_set = true;
+    }
+    launch_k((adapter_tc_kernel<R, BN2, V1, V2>), dim3((M + BM - 1) / BM), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, s, ta, tb1, tb2, e1,
+             e2, M, D);
+    AIMB_CHECK_LAUNCH();
+    return AIMB_OK;
+}
+template <int R, int BN2>
+static int launch_adapter(const CUtensorMap& ta, const CUtensorMap& tb1, const CUtensorMap& tb2, const EpiParams& e1,
+                          const EpiParams& e2, int M, int D, cudaStream_t s) {
+    const int v1 = pick_variant(e1), v2 = pick_variant(e2);
+    if (v1 == 2 && v2 == 3) return launch_adapter_v<R, BN2, 2, 3>(ta, tb1, tb2, e1, e2, M, D, s);
+    if (v1 == 2 && v2 == 4) return launch_adapter_v<R, BN2, 2, 4>(ta, tb1, tb2, e1, e2, M, D, s);
+    if (v1 == 2 && v2 == 0) return launch_adapter_v<R, BN2, 2, 0>(ta, tb1, tb2, e1, e2, M, D, s);
+    if (v1 == 6 && v2 == 3) return launch_adapter_v<R, BN2, 6, 3>(ta, tb1, tb2, e1, e2, M, D, s);
+    if (v1 == 6 && v2 == 0) return launch_adapter_v<R, BN2, 6, 0>(ta, tb1, tb2, e1, e2, M, D, s);
+    return AIMB_ERR_UNSUPPORTED;
+}
+
+// A [M, D]; B1 [R, D]; B2 [D, R] (all K-major: nn.Linear weights forward, their transposes backward)
+int adapter_tc_launch(const void* A, int64_t lda, const void* B1, const void* B2, const EpiParams& e1, const EpiParams& e2,
+                      int64_t M, int D, int R, cudaStream_t s) {
+    if (M < BM || M >= (1ll << 31) || (M + BM - 1) / BM > 4096 || D % 64 || (lda % 8) || ((uintptr_t)A & 15)) return AIMB_ERR_UNSUPPORTED;
+    int bn2 = (D % 192 == 0) ? 192 : (D % 256 == 0 ? 256 : 0);
+    if (!bn2) return AIMB_ERR_UNSUPPORTED;
+    CUtensorMap ta, tb1, tb2;
+    int rc = make_tmap_bf16(&ta, A, M, D, lda, BM);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&tb1, B1, R, D, D, R);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&tb2, B2, D, R, R, bn2);
+    if (rc) return rc;
+    if (R == 192 && bn2 == 192) return launch_adapter<192, 192>(ta, tb1, tb2, e1, e2, (int)M, D, s);
+    if (R == 256 && bn2 == 256) return launch_adapter<256, 256>(ta, tb1, tb2, e1, e2, (int)M, D, s);
+    if (R == 64 && bn2 == 256) return launch_adapter<64, 256>(ta, tb1, tb2, e1, e2, (int)M, D, s);
+    return AIMB_ERR_UNSUPPORTED;
+}
+
 }  // namespace aimb
 
 using namespace aimb;
@@ -918,4 +1148,16 @@ extern "C" int aimb_gemm_wgrad(const void* dY, int64_t ldy, const void* X, int64
     }
     // C[n, k] = sum_r dY[r, n] * X[r, k]:  "M" = N rows (stride 1 over n, ldy over r), "N" = K
     return gemm_simt_launch(dY, 1, ldy, X, 1, ldx, p, N, K, (int)R, dtype, s);
+}
+
+extern "C" int aimb_adapter_fused(const void* A, int64_t lda, const void* W1, const void* W2, const aimb_epilogue_t* epi1,
+                                  const aimb_epilogue_t* epi2, int64_t M, int32_t D, int32_t R, int32_t dtype, void* stream) {
+    if (!A || !W1 || !W2 || !epi1 || !epi2 || !epi2->out || M < 0 || D <= 0 || R <= 0) return AIMB_ERR_ARG;
+    if (dtype != AIMB_BF16) return AIMB_ERR_UNSUPPORTED;
+    if (M == 0) return AIMB_OK;
+    EpiParams e1 = make_epi(epi1, R), e2 = make_epi(epi2, D);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (e1.colsum_out && cudaMemsetAsync(e1.colsum_out, 0, (size_t)R * 4, s) != cudaSuccess) return AIMB_ERR_CUDA;
+    if (e2.colsum_out) return AIMB_ERR_UNSUPPORTED;
+    return adapter_tc_launch(A, lda, W1, W2, e1, e2, M, D, R, s);
 }

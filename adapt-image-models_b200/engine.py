@@ -15,6 +15,7 @@ contiguous row ranges and temporal attention reads rows at stride n in place.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional
 
@@ -63,6 +64,7 @@ class Engine:
         self.saved: Optional[dict] = None
         self.attn_impl = lib.IMPL_AUTO
         self.gemm_impl = lib.IMPL_AUTO
+        self.fuse_adapters = os.environ.get("AIMB200_FUSE_ADAPTERS", "0") == "1"   # opt-in: measured on par at M = 12608
 
     # ------------------------------------------------------------------ buffers (stable pointers across steps)
     def buf(self, name, shape, dtype=None, key=None):
@@ -123,10 +125,15 @@ class Engine:
         M, r = a.shape[0], d.r
         h = self.buf(name + "_h", (M, r), key=bk) if training else None
         g = self.buf(name + "_g", (M, r), key=bk)
-        self.gemm(a, W[pre + name + ".D_fc1.weight"], g, bias=W[pre + name + ".D_fc1.bias"], act=lib.ACT_GELU,
-                  out_pre=h, row_scale=rs)
-        self.gemm(g, W[pre + name + ".D_fc2.weight"], out, bias=W[pre + name + ".D_fc2.bias"], row_scale=rs,
-                  bias_rowscaled=rs is not None, alpha=alpha, res1=res1, res2=res2)
+        w1, w2 = W[pre + name + ".D_fc1.weight"], W[pre + name + ".D_fc2.weight"]
+        epi1 = dict(bias=W[pre + name + ".D_fc1.bias"], act=lib.ACT_GELU, out_pre=h, row_scale=rs)
+        epi2 = dict(bias=W[pre + name + ".D_fc2.bias"], row_scale=rs, bias_rowscaled=rs is not None, alpha=alpha,
+                    res1=res1, res2=res2)
+        if self.fuse_adapters and self.gemm_impl == lib.IMPL_AUTO and lib.adapter_fused_supported(a, r, d.D):
+            lib.adapter_fused(a, w1, w2, g, out, epi1, epi2)      # one kernel: the hidden tile stays on chip
+        else:
+            self.gemm(a, w1, g, **epi1)
+            self.gemm(g, w2, out, **epi2)
         return h, g
 
     def _mlp_fwd(self, i, x2, W, d, training, mask_m, bk):
@@ -356,9 +363,14 @@ class Engine:
             lib.colsum(dy, grads[k2b], row_scale=rs, alpha=alpha)
         # d_h = rs * alpha * (dy W2) * gelu'(h) ; db1 = column sums of d_h, taken in the same epilogue
         d_h = self.buf("d_h", (M, r))
-        self.gemm(dy, WT[k2w], d_h, dact_src=h, dact=lib.ACT_GELU, alpha=alpha, row_scale=rs, colsum_out=grads[k1b])
+        epi1 = dict(dact_src=h, dact=lib.ACT_GELU, alpha=alpha, row_scale=rs, colsum_out=grads[k1b])
+        epi2 = dict(res1=d_a_res)
+        if self.fuse_adapters and self.gemm_impl == lib.IMPL_AUTO and lib.adapter_fused_supported(dy, r, D):
+            lib.adapter_fused(dy, WT[k2w], WT[k1w], d_h, d_a_out, epi1, epi2)
+        else:
+            self.gemm(dy, WT[k2w], d_h, **epi1)
+            self.gemm(d_h, WT[k1w], d_a_out, **epi2)
         lib.gemm_wgrad(d_h, a, grads[k1w])
-        self.gemm(d_h, WT[k1w], d_a_out, res1=d_a_res)
         return d_a_out
 
     def _block_bwd(self, i, dx, W, WT, grads, d, S, prev_mask_m=None):

@@ -49,6 +49,7 @@ SIGNATURES = {
     "aimb_tail_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "aimb_gemm_nt": [_P, _L, _P, _L, C.POINTER(Epilogue), _L, _I, _I, _I, _I, _P],
     "aimb_gemm_strided": [_P, _L, _L, _P, _L, _L, C.POINTER(Epilogue), _L, _I, _I, _I, _P],
+    "aimb_adapter_fused": [_P, _L, _P, _P, C.POINTER(Epilogue), C.POINTER(Epilogue), _L, _I, _I, _I, _P],
     "aimb_gemm_wgrad": [_P, _L, _P, _L, _P, _L, _I, _I, _F, _I, _I, _I, _P],
     "aimb_colsum": [_P, _L, _P, _I, _F, _P, _L, _I, _I, _I, _P],
     "aimb_transpose": [_P, _P, _I, _I, _I, _P],
@@ -215,6 +216,25 @@ def gemm_nt(a, w, out, impl=IMPL_AUTO, **epi):
     _count()
     _chk(load().aimb_gemm_nt(_ptr(a), a.stride(0), _ptr(w), w.stride(0), C.byref(e), M, N, K, dt_code(a), impl,
                              _stream()), f"gemm_nt[{M}x{N}x{K}]")
+    return out
+
+
+def adapter_fused_supported(a, R, D) -> bool:
+    return (a.dtype == torch.bfloat16 and a.shape[0] >= 128 and R in (64, 192, 256) and (D % 192 == 0 or D % 256 == 0)
+            and not (R == 64 and D % 256 != 0) and not (R == 192 and D % 192 != 0) and not (R == 256 and D % 256 != 0)
+            and a.stride(1) == 1 and a.stride(0) % 8 == 0)
+
+
+def adapter_fused(a, w1, w2, hidden_out, out, epi1: dict, epi2: dict):
+    """out = epi2(epi1(a @ w1^T) @ w2^T); a [M,D], w1 [R,D], w2 [D,R]; hidden_out [M,R] receives epi1's result."""
+    M, D = a.shape
+    R = w1.shape[0]
+    assert w1.shape == (R, D) and w2.shape == (D, R) and w1.is_contiguous() and w2.is_contiguous()
+    e1 = make_epilogue(hidden_out, ldo=hidden_out.stride(0), **epi1)
+    e2 = make_epilogue(out, ldo=out.stride(0), **epi2)
+    _count()
+    _chk(load().aimb_adapter_fused(_ptr(a), a.stride(0), _ptr(w1), _ptr(w2), C.byref(e1), C.byref(e2), M, D, R, dt_code(a),
+                                   _stream()), f"adapter_fused[{M}x{D}x{R}]")
     return out
 
 

@@ -34,7 +34,7 @@ if args.ncu:
 
 recs = []
 names = ["layernorm_fwd", "layernorm_bwd", "im2col", "stem_assemble_ln", "temb_grad", "tail_fwd", "tail_bwd", "gemm_nt",
-         "gemm_wgrad", "colsum", "transpose", "attn_spatial_fwd", "attn_spatial_bwd", "attn_temporal_fwd", "attn_temporal_bwd"]
+         "gemm_wgrad", "adapter_fused", "colsum", "transpose", "attn_spatial_fwd", "attn_spatial_bwd", "attn_temporal_fwd", "attn_temporal_bwd"]
 for nme in names:
     orig = getattr(lib, nme)
 
@@ -48,6 +48,9 @@ for nme in names:
             if nme == "gemm_nt":
                 tag += f" M{a[0].shape[0]} N{a[1].shape[0]} K{a[0].shape[1]}"
                 fl = 2.0 * a[0].shape[0] * a[1].shape[0] * a[0].shape[1]
+            elif nme == "adapter_fused":
+                tag += f" M{a[0].shape[0]} D{a[0].shape[1]} R{a[1].shape[0]} " + ("bwd" if "dact_src" in a[5] else "fwd")
+                fl = 4.0 * a[0].shape[0] * a[0].shape[1] * a[1].shape[0]
             elif nme == "gemm_wgrad":
                 tag += f" R{a[0].shape[0]} N{a[0].shape[1]} K{a[1].shape[1]}"
                 fl = 2.0 * a[0].shape[0] * a[0].shape[1] * a[1].shape[1]

@@ -129,6 +129,15 @@ int aimb_gemm_strided(const void* A, int64_t a_sm, int64_t a_sk, const void* B, 
 /* Adapter weight gradient (autograd of vit_clip.py:62,64): dW[N,K] (fp32) (+)= alpha * dY[R,N]^T * X[R,K]. */
 int aimb_gemm_wgrad(const void* dY, int64_t ldy, const void* X, int64_t ldx, float* dW, int64_t R, int32_t N,
                     int32_t K, float alpha, int32_t accumulate, int32_t dtype, int32_t impl, void* stream);
+/* Adapter bottleneck (vit_clip.py:51-69) as ONE kernel: H = epi1(A[M,D] * W1[R,D]^T) is written to epi1->out (and
+ * epi1->out_pre) and, without a round trip through HBM, used as the left operand of epi2(H * W2[D,R]^T) -> epi2->out.
+ *   forward : epi1 = {bias b1, act GELU, row_scale, out g', out_pre h}, epi2 = {bias b2 (row-scaled), alpha, res1[, res2]}
+ *   backward: A = dy, W1 := W2^T [R,D], W2 := W1^T [D,R]; epi1 = {dact_src h, dact GELU, alpha, row_scale, out d_h,
+ *             colsum_out db1}, epi2 = {res1}.
+ * bf16 only; M >= 128, R in {64, 192, 256}, D a multiple of 192 or 256 (returns AIMB_ERR_UNSUPPORTED otherwise: the
+ * caller then issues the two aimb_gemm_nt calls this kernel fuses). */
+int aimb_adapter_fused(const void* A, int64_t lda, const void* W1, const void* W2, const aimb_epilogue_t* epi1,
+                       const aimb_epilogue_t* epi2, int64_t M, int32_t D, int32_t R, int32_t dtype, void* stream);
 /* Bias gradient: out[c] (+)= alpha * sum_r x[r, c] * (row_scale ? row_scale[r % row_mod] : 1)  (fp32 out). */
 int aimb_colsum(const void* x, int64_t ld, const float* row_scale, int32_t row_mod, float alpha, float* out,
                 int64_t R, int32_t C, int32_t accumulate, int32_t dtype, void* stream);

@@ -174,6 +174,51 @@ def test_gemm_tc_matches_simt_bitwise_inputs():
     assert _err(o1, o2.double()) < 8e-3
 
 
+@pytest.mark.parametrize("M,D,R", [(12608, 768, 192), (1576, 768, 192), (300, 1024, 256), (136, 256, 64), (128, 768, 192)])
+def test_adapter_fused_forward_and_backward(M, D, R):
+    """One-kernel adapter (GEMM1 -> smem hidden -> GEMM2) against fp64 math and against the two-GEMM path."""
+    lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(M + R)
+    bf = torch.bfloat16
+    a = torch.randn(M, D, device="cuda", generator=g).to(bf)
+    w1 = (torch.randn(R, D, device="cuda", generator=g) / math.sqrt(D)).to(bf)
+    w2 = (torch.randn(D, R, device="cuda", generator=g) / math.sqrt(R)).to(bf)
+    b1 = (0.1 * torch.randn(R, device="cuda", generator=g)).to(bf)
+    b2 = (0.1 * torch.randn(D, device="cuda", generator=g)).to(bf)
+    r1 = torch.randn(M, D, device="cuda", generator=g).to(bf)
+    r2 = torch.randn(M, D, device="cuda", generator=g).to(bf)
+    rs = (torch.rand(197, device="cuda", generator=g) > 0.3).float() / 0.7
+    rsm = rs.double()[torch.arange(M, device="cuda") % 197][:, None]
+    # ---- forward
+    h = torch.empty(M, R, device="cuda", dtype=bf)
+    gg = torch.empty_like(h)
+    out = torch.empty(M, D, device="cuda", dtype=bf)
+    lib.adapter_fused(a, w1, w2, gg, out, dict(bias=b1, act=lib.ACT_GELU, out_pre=h, row_scale=rs),
+                      dict(bias=b2, row_scale=rs, bias_rowscaled=True, alpha=0.5, res1=r1, res2=r2))
+    href = a.double() @ w1.double().T + b1.double()
+    gref = F.gelu(href.to(bf).double()) * rsm
+    oref = 0.5 * (gref.to(bf).double() @ w2.double().T + b2.double() * rsm) + r1.double() + r2.double()
+    assert _err(h, href) < 1e-2 and _err(gg, gref) < 1e-2 and _err(out, oref) < 1.5e-2
+    g2, o2 = torch.empty_like(gg), torch.empty_like(out)
+    lib.gemm_nt(a, w1, g2, bias=b1, act=lib.ACT_GELU, row_scale=rs)
+    lib.gemm_nt(g2, w2, o2, bias=b2, row_scale=rs, bias_rowscaled=True, alpha=0.5, res1=r1, res2=r2)
+    assert _err(out, o2.double()) < 8e-3
+    # ---- backward: d_h = rs*alpha*(dy w2)*gelu'(h), db1 = colsum(d_h), d_a = res + d_h w1
+    dy = torch.randn(M, D, device="cuda", generator=g).to(bf)
+    w2t, w1t = w2.t().contiguous(), w1.t().contiguous()          # [R, D], [D, R]
+    d_h = torch.empty(M, R, device="cuda", dtype=bf)
+    d_a = torch.empty(M, D, device="cuda", dtype=bf)
+    db1 = torch.full((R,), float("nan"), device="cuda")
+    lib.adapter_fused(dy, w2t, w1t, d_h, d_a, dict(dact_src=h, dact=lib.ACT_GELU, alpha=0.5, row_scale=rs, colsum_out=db1),
+                      dict(res1=r1))
+    u = h.double().requires_grad_(True)
+    F.gelu(u).sum().backward()
+    dh_ref = (dy.double() @ w2.double()) * u.grad * 0.5 * rsm
+    da_ref = dh_ref.to(bf).double() @ w1.double() + r1.double()
+    assert _err(d_h, dh_ref) < 1.5e-2 and _err(d_a, da_ref) < 1.5e-2
+    assert _err(db1, dh_ref.sum(0)) < 5e-3
+
+
 @pytest.mark.parametrize("R", [1576, 12608, 100, 64])
 @pytest.mark.parametrize("N,K", [(192, 768), (768, 192), (256, 1024), (1024, 256), (64, 256), (128, 128)])
 def test_wgrad_tc(R, N, K):
