@@ -153,3 +153,52 @@ def test_edge_shapes_and_errors():
     with torch.no_grad():
         out = m(torch.randn(3, 3, 4, 64, 64, device="cuda"))
     assert out.shape == (3, 256, 4, 1, 1) and bool(torch.isfinite(out).all())
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("name,kw,batch", [
+    # cfg4 / cfg5 shapes of BASELINE.json at reduced depth: ViT-L/14 (patch 14 -> K = 588 padded to 640, 257 tokens,
+    # width 1024, 16 heads, r = 256), 8 and 32 frames; cfg3: ViT-B/16 with 16 frames
+    ("vitl14_t8", dict(input_resolution=224, num_frames=8, patch_size=14, width=1024, layers=2, heads=16), 1),
+    ("vitl14_t32", dict(input_resolution=224, num_frames=32, patch_size=14, width=1024, layers=1, heads=16), 1),
+    ("vitb16_t16", dict(input_resolution=224, num_frames=16, patch_size=16, width=768, layers=2, heads=12), 1),
+])
+def test_other_baseline_shapes_vs_oracle(mode, name, kw, batch):
+    """Logits and gradients against the CPU oracle (live, same seeded fixture) for the model shapes of cfg3-cfg5."""
+    cfg = O.OracleCfg(**kw, block="aim")
+    m = _build(cfg, mode)
+    x = O.fixture_clip(cfg, batch)
+    hw, hb = O.fixture_head(cfg, 400)
+    labels = torch.tensor([5] * batch)
+    lg, loss, grads = _cuda_logits_and_grads(m, cfg, x, hw, hb, labels)
+    ref_loss, ref_lg, ref_g = O.loss_and_grads(O.fixture_state_dict(cfg), x, labels, cfg, hw, hb)
+    tol_l, tol_g = (1e-3, 1e-3) if mode == "fp32" else (2e-2, 6e-2)
+    assert O.normalised_max_err(lg, ref_lg) < tol_l
+    assert int(lg.argmax()) == int(ref_lg.argmax())
+    worst = max(O.normalised_max_err(grads[k], ref_g[k]) for k in grads)
+    print(f"[{name} {mode}] logits {O.normalised_max_err(lg, ref_lg):.2e}, worst grad {worst:.2e}")
+    assert worst < tol_g
+
+
+def test_inference_three_views_sharded_like_recognizer3d():
+    """cfg4-style inference: [videos, views, C, T, H, W] -> views are batch rows (recognizer3d.py:36), softmax-mean over
+    views ('prob', recognizers/base.py:186-192); a 2-way shard of the videos gives the same scores as one pass."""
+    cfg = O.OracleCfg(**TINY, block="aim")
+    m = _build(cfg, "bf16").eval()
+    hw, hb = O.fixture_head(cfg, 16)
+    g = torch.Generator().manual_seed(4)
+    vids = torch.randn(4, 3, 3, 4, 64, 64, generator=g)                  # 4 videos x 3 views
+
+    def scores(v):
+        with torch.no_grad():
+            feat = m(v.reshape(-1, 3, 4, 64, 64).cuda())
+            lg = O.head_logits(feat, hw.cuda(), hb.cuda())
+        return torch.softmax(lg, -1).reshape(v.shape[0], 3, -1).mean(1).cpu()
+
+    full = scores(vids)
+    shard = torch.cat([scores(vids[0::2]), scores(vids[1::2])])           # rank-strided shards, then gather
+    order = torch.cat([torch.arange(0, 4, 2), torch.arange(1, 4, 2)])
+    assert torch.allclose(full[order], shard, atol=2e-3)
+    ref = O.head_logits(O.backbone(O.fixture_state_dict(cfg), vids.reshape(-1, 3, 4, 64, 64), cfg), hw, hb)
+    ref = torch.softmax(ref, -1).reshape(4, 3, -1).mean(1)
+    assert O.normalised_max_err(full, ref) < 2e-2
