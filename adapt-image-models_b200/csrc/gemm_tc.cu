@@ -23,7 +23,9 @@ constexpr int UMMA_K = 16;
 constexpr int TC_THREADS = 192;          // wgrad kernel: 1 producer + 1 MMA + 4 epilogue warps
 constexpr int GEMM_THREADS = 320;        // GEMM: 1 producer + 1 MMA + 8 epilogue warps
 constexpr int EPI_WARPS = 8;
-constexpr int STG_WARP_FLOATS = 32 * 33 + 128;     // per-warp 32x32 fp32 transpose buffer (padded) + bias slice
+constexpr int STG_LD = 36;                          // row stride (floats) of the transpose tile: 16-byte aligned rows,
+                                                    // conflict-free for the 128-bit stores and loads used below
+constexpr int STG_WARP_FLOATS = 32 * STG_LD + 128;  // per-warp 32x32 fp32 transpose buffer (padded) + bias slice
 constexpr int STG_BYTES = EPI_WARPS * STG_WARP_FLOATS * 4 + 1024;   // + scol[256]: per-CTA column-sum partials
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 
@@ -140,7 +142,7 @@ __device__ __forceinline__ void epilogue_vec8(const EpiParams& e, int64_t m, int
 }
 
 // Epilogue of one warp for its 32 rows x NCOLS columns of a tile (shared by the 1-CTA and 2-CTA kernels).
-// Accumulators are transposed through a private 32x33 fp32 smem tile so that global traffic is 16 B per lane,
+// Accumulators are transposed through a private 32x36 fp32 smem tile so that global traffic is 16 B per lane,
 // 8 rows x 64 B per instruction.  `wait_acc` blocks until the accumulator is ready (called after the first
 // chunk's operand prefetch has been issued).
 template <int NCOLS, int ACT, int DACT, int EXT, typename WaitFn>
@@ -152,7 +154,7 @@ __device__ __forceinline__ void epilogue_warp_t(const EpiParams& epi, float* stg
     // TMEM load of chunk c+1 and the operand loads of chunk c+1 are in flight while chunk c is processed.
     constexpr bool DB = (EXT != 7);          // the generic variant trades the prefetch for registers
     const int row_l = lane >> 2, c0 = (lane & 3) * 8;
-    float* sbias = stg + 32 * 33;            // [NCOLS] fp32 bias of this warp's columns
+    float* sbias = stg + 32 * STG_LD;        // [NCOLS] fp32 bias of this warp's columns
     if (epi.bias) {
         for (int j = lane; j < NCOLS; j += 32) sbias[j] = __bfloat162float(((const bf16*)epi.bias)[n_base + j]);
     }
@@ -166,7 +168,8 @@ __device__ __forceinline__ void epilogue_warp_t(const EpiParams& epi, float* stg
     for (int c = 0; c < NCOLS; c += 32) {
         ptx::tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<uint4*>(stg + lane * STG_LD + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
         if (c + 32 < NCOLS) {
             ptx::tmem_ld_32x32b_x32(taddr + c + 32, r);     // registers are free again: next chunk's TMEM load
             if (DB) epi_prefetch<EXT>(epi, nxt, row_base, row_l, n_base + c + 32 + c0, M);
@@ -186,9 +189,9 @@ __device__ __forceinline__ void epilogue_warp_t(const EpiParams& epi, float* stg
             const int rl = i * 8 + row_l;
             const int64_t row = row_base + rl;
             float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = stg[rl * 33 + c0 + j];
-            if (dbg == 2) { if (v[0] == 1.2345e-30f && v[7] == 3.3e-31f) stg[lane * 33] = v[3]; continue; }
+            *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(stg + rl * STG_LD + c0);
+            *reinterpret_cast<float4*>(v + 4) = *reinterpret_cast<const float4*>(stg + rl * STG_LD + c0 + 4);
+            if (dbg == 2) { if (v[0] == 1.2345e-30f && v[7] == 3.3e-31f) stg[lane * STG_LD] = v[3]; continue; }
             if (row < M) {
                 epilogue_vec8<ACT, DACT, EXT>(epi, row, n0, v, bias8, cur, i);
 #pragma unroll
