@@ -10,5 +10,6 @@ from .registry import BACKBONES, build_backbone  # noqa: E402,F401
 from .backbone import ViT_CLIP  # noqa: E402,F401
 from .parallel import GradSync  # noqa: E402,F401
 from .graphs import GraphedStep  # noqa: E402,F401
+from .recognizer import Recognizer3D, I3DHead, trainable_state_dict, load_checkpoint  # noqa: E402,F401
 
-__all__ += ["BACKBONES", "build_backbone", "ViT_CLIP", "GradSync", "GraphedStep"]
+__all__ += ["BACKBONES", "build_backbone", "ViT_CLIP", "GradSync", "GraphedStep", "Recognizer3D", "I3DHead", "trainable_state_dict", "load_checkpoint"]

@@ -15,6 +15,7 @@ out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
 bias = torch.randn(N, device="cuda").bfloat16()
 L.aimb_debug_force_bn(bn)
 L.aimb_debug_cta_mode(mode)
+res = torch.randn(M, N, device="cuda").bfloat16() if len(sys.argv) > 6 and sys.argv[6] == "res" else None
 for _ in range(5):
-    lib.gemm_nt(a, w, out, bias=bias)
+    lib.gemm_nt(a, w, out, bias=bias, res1=res)
 torch.cuda.synchronize()
