@@ -7,6 +7,9 @@ namespace aimb {
 template <typename T> struct VecIO;
 template <> struct VecIO<float> {
     static constexpr int N = 4;
+    typedef float4 Raw;
+    static __device__ __forceinline__ Raw ldraw(const float* p) { return *reinterpret_cast<const float4*>(p); }
+    static __device__ __forceinline__ void unpack(const Raw& t, float* v) { v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
     static __device__ __forceinline__ void ld(const float* p, float* v) {
         float4 t = *reinterpret_cast<const float4*>(p);
         v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
@@ -17,6 +20,13 @@ template <> struct VecIO<float> {
 };
 template <> struct VecIO<bf16> {
     static constexpr int N = 8;
+    typedef uint4 Raw;
+    static __device__ __forceinline__ Raw ldraw(const bf16* p) { return *reinterpret_cast<const uint4*>(p); }
+    static __device__ __forceinline__ void unpack(const Raw& t, float* v) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+    }
     static __device__ __forceinline__ void ld(const bf16* p, float* v) {
         uint4 t = *reinterpret_cast<const uint4*>(p);
         const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
@@ -48,6 +58,20 @@ template <typename T> struct RowRegs {
 #pragma unroll
                 for (int j = 0; j < V; ++j) v[it][j] = 0.f;
             }
+        }
+    }
+};
+
+// A row held as raw 16-byte vectors (half the registers of RowRegs for bf16): used to keep the NEXT row's loads
+// in flight while the current row is being processed.
+template <typename T, int NIT> struct RowRaw {
+    static constexpr int V = VecIO<T>::N;
+    typename VecIO<T>::Raw v[NIT];
+    __device__ __forceinline__ void load(const T* row, int D, int lane) {
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            int c = (it * 32 + lane) * V;
+            if (c < D) v[it] = VecIO<T>::ldraw(row + c);
         }
     }
 };
@@ -116,15 +140,15 @@ __global__ void __launch_bounds__(128) layernorm_fwd_kernel(const T* __restrict_
 // One warp per row, RPW rows per warp.  Optionally accumulates cs_out[c] += alpha * w[row] * dx[row, c] (the bias
 // gradient of the adapter fed by dx) from the values already in registers: per-lane column partials over the
 // warp's rows, reduced across the 4 warps through smem, one atomicAdd per column per block.
-template <typename T, int RPW>
-__global__ void __launch_bounds__(128) layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+template <typename T, int RPW, int NIT>      // NIT = ceil(D / (32 lanes * 16-byte vector)): registers sized to the row length
+__global__ void __launch_bounds__(128, 3) layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                                             const float* __restrict__ mean_i,
                                                             const float* __restrict__ rstd_i,
                                                             const T* __restrict__ gamma, const T* dres, T* dx,
                                                             const float* __restrict__ cs_w, int cs_mod, float cs_alpha,
                                                             float* __restrict__ cs_out, int64_t rows, int D) {
     pdl_grid_sync();
-    constexpr int V = RowRegs<T>::V, NIT = RowRegs<T>::NIT;
+    constexpr int V = VecIO<T>::N;
     constexpr int NWARP = 4;
     __shared__ float red[RPW > 1 ? NWARP * MAXD : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -134,30 +158,40 @@ __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const T* __restrict_
 #pragma unroll
         for (int j = 0; j < V; ++j) cs[it][j] = 0.f;
     // each warp handles RPW consecutive rows; with the fused column sums a block flushes one atomic per column
-    // for its 4*RPW rows (measured: fewer, fatter persistent blocks lose more in memory parallelism than they save)
+    // for its 4*RPW rows.  The rows are software-pipelined: the raw 16-byte loads (dy, x, dres) of row k+1 are issued
+    // before row k is reduced, so one memory latency per row is hidden behind the previous row's math.
+    const int64_t row_first = ((int64_t)blockIdx.x * NWARP + warp) * RPW;
+    RowRaw<T, NIT> n_dy, n_x, n_res;
+    if (row_first < rows) {
+        n_dy.load(dy + row_first * D, D, lane);
+        n_x.load(x + row_first * D, D, lane);
+        if (dres) n_res.load(dres + row_first * D, D, lane);
+    }
 #pragma unroll 1
     for (int k = 0; k < RPW; ++k) {
-        const int64_t row = ((int64_t)blockIdx.x * NWARP + warp) * RPW + k;
+        const int64_t row = row_first + k;
         if (row >= rows) break;
-        RowRegs<T> g, xh;
-        g.load(dy + row * D, D, lane);
-        xh.load(x + row * D, D, lane);
+        RowRaw<T, NIT> c_dy = n_dy, c_x = n_x, c_res = n_res;
+        if (k + 1 < RPW && row + 1 < rows) {
+            n_dy.load(dy + (row + 1) * D, D, lane);
+            n_x.load(x + (row + 1) * D, D, lane);
+            if (dres) n_res.load(dres + (row + 1) * D, D, lane);
+        }
         const float mean = mean_i[row], rstd = rstd_i[row];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
             int c = (it * 32 + lane) * V;
             if (c < D) {
-                float gm[V];
+                float gm[V], a[V], b[V];
                 VecIO<T>::ld(gamma + c, gm);
+                VecIO<T>::unpack(c_dy.v[it], a);
+                VecIO<T>::unpack(c_x.v[it], b);
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
-                    float gg = g.v[it][j] * gm[j];
-                    float h = (xh.v[it][j] - mean) * rstd;
-                    g.v[it][j] = gg;
-                    xh.v[it][j] = h;
+                    float gg = a[j] * gm[j];
                     s1 += gg;
-                    s2 += gg * h;
+                    s2 += gg * ((b[j] - mean) * rstd);
                 }
             }
         }
@@ -165,18 +199,21 @@ __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const T* __restrict_
         s2 = warp_sum(s2) / D;
         const float w = (RPW > 1 && cs_w) ? cs_w[row % cs_mod] : 1.f;
 #pragma unroll
-        for (int it = 0; it < NIT; ++it) {
-            int c = (it * 32 + lane) * V;
+        for (int it = 0; it < NIT; ++it) {       // second sweep re-derives g and xhat from the raw registers (cheap ALU)
+            int c = (it * 32 + lane) * V;        // instead of keeping two more fp32 copies of the row alive
             if (c < D) {
-                float o[V];
-                if (dres) VecIO<T>::ld(dres + row * D + c, o);
+                float gm[V], a[V], b[V], o[V];
+                VecIO<T>::ld(gamma + c, gm);
+                VecIO<T>::unpack(c_dy.v[it], a);
+                VecIO<T>::unpack(c_x.v[it], b);
+                if (dres) VecIO<T>::unpack(c_res.v[it], o);
                 else {
 #pragma unroll
                     for (int j = 0; j < V; ++j) o[j] = 0.f;
                 }
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
-                    o[j] += rstd * (g.v[it][j] - s1 - xh.v[it][j] * s2);
+                    o[j] += rstd * (a[j] * gm[j] - s1 - (b[j] - mean) * rstd * s2);
                     if (RPW > 1) cs[it][j] = fmaf(w, o[j], cs[it][j]);
                 }
                 VecIO<T>::st(dx + row * D + c, o);
@@ -547,35 +584,39 @@ extern "C" int aimb_layernorm_fwd(const void* x, const void* gamma, const void* 
     return AIMB_OK;
 }
 
+template <typename T, int NIT>
+static void ln_bwd_launch_t(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma,
+                            const void* dres, void* dx, const float* cs_w, int cs_mod, float cs_alpha, float* cs_out,
+                            int64_t rows, int D, cudaStream_t s) {
+    if (cs_out) {
+        constexpr int RPW = 8;
+        unsigned grid = (unsigned)((rows + 4 * RPW - 1) / (4 * RPW));
+        launch_k((layernorm_bwd_kernel<T, RPW, NIT>), dim3(grid), dim3(128), 0, s, (const T*)dy, (const T*)x, mean, rstd,
+                 (const T*)gamma, (const T*)dres, (T*)dx, cs_w, cs_mod > 0 ? cs_mod : 1, cs_alpha, cs_out, rows, D);
+    } else {
+        unsigned grid = (unsigned)((rows + 3) / 4);
+        launch_k((layernorm_bwd_kernel<T, 1, NIT>), dim3(grid), dim3(128), 0, s, (const T*)dy, (const T*)x, mean, rstd,
+                 (const T*)gamma, (const T*)dres, (T*)dx, (const float*)nullptr, 1, 1.f, (float*)nullptr, rows, D);
+    }
+}
+
 static int ln_bwd_launch(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma,
                          const void* dres, void* dx, const float* cs_w, int cs_mod, float cs_alpha, float* cs_out,
                          int64_t rows, int D, int dtype, cudaStream_t s) {
     if (!dy || !x || !mean || !rstd || !gamma || !dx || rows < 0 || !vec_ok(D, dtype)) return AIMB_ERR_ARG;
     if (cs_out && cudaMemsetAsync(cs_out, 0, (size_t)D * 4, s) != cudaSuccess) return AIMB_ERR_CUDA;
     if (rows == 0) return AIMB_OK;
-    if (cs_out) {
-        constexpr int RPW = 8;
-        unsigned grid = (unsigned)((rows + 4 * RPW - 1) / (4 * RPW));
-        if (dtype == AIMB_BF16)
-            launch_k((layernorm_bwd_kernel<bf16, RPW>), dim3(grid), dim3(128), 0, s, (const bf16*)dy, (const bf16*)x, mean, rstd, (const bf16*)gamma,
-                                                                 (const bf16*)dres, (bf16*)dx, cs_w, cs_mod > 0 ? cs_mod : 1,
-                                                                 cs_alpha, cs_out, rows, D);
-        else if (dtype == AIMB_F32)
-            launch_k((layernorm_bwd_kernel<float, RPW>), dim3(grid), dim3(128), 0, s, (const float*)dy, (const float*)x, mean, rstd,
-                                                                  (const float*)gamma, (const float*)dres, (float*)dx, cs_w,
-                                                                  cs_mod > 0 ? cs_mod : 1, cs_alpha, cs_out, rows, D);
-        else return AIMB_ERR_ARG;
-    } else {
-        unsigned grid = (unsigned)((rows + 3) / 4);
-        if (dtype == AIMB_BF16)
-            launch_k((layernorm_bwd_kernel<bf16, 1>), dim3(grid), dim3(128), 0, s, (const bf16*)dy, (const bf16*)x, mean, rstd, (const bf16*)gamma,
-                                                               (const bf16*)dres, (bf16*)dx, nullptr, 1, 1.f, nullptr, rows, D);
-        else if (dtype == AIMB_F32)
-            launch_k((layernorm_bwd_kernel<float, 1>), dim3(grid), dim3(128), 0, s, (const float*)dy, (const float*)x, mean, rstd,
-                                                                (const float*)gamma, (const float*)dres, (float*)dx, nullptr, 1,
-                                                                1.f, nullptr, rows, D);
-        else return AIMB_ERR_ARG;
-    }
+    const int vec = dtype == AIMB_BF16 ? 8 : 4;
+    const int nit = (D + 32 * vec - 1) / (32 * vec);
+#define AIMB_LN_BWD(T_, N_) ln_bwd_launch_t<T_, N_>(dy, x, mean, rstd, gamma, dres, dx, cs_w, cs_mod, cs_alpha, cs_out, rows, D, s)
+    if (dtype == AIMB_BF16) {
+        if (nit <= 1) AIMB_LN_BWD(bf16, 1); else if (nit <= 2) AIMB_LN_BWD(bf16, 2); else if (nit <= 3) AIMB_LN_BWD(bf16, 3);
+        else AIMB_LN_BWD(bf16, 4);
+    } else if (dtype == AIMB_F32) {
+        if (nit <= 2) AIMB_LN_BWD(float, 2); else if (nit <= 4) AIMB_LN_BWD(float, 4); else if (nit <= 6) AIMB_LN_BWD(float, 6);
+        else AIMB_LN_BWD(float, 8);
+    } else return AIMB_ERR_ARG;
+#undef AIMB_LN_BWD
     AIMB_CHECK_LAUNCH();
     return AIMB_OK;
 }
