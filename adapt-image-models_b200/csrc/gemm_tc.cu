@@ -99,9 +99,9 @@ template <int ACT> __device__ __forceinline__ float act_grad_fn(float u, int rt)
 
 // v[8] = accumulators of row m, columns n0..n0+7; bias8 = bias of those columns; x/i = prefetched operands.
 // ACT / DACT are compile-time: only the activation actually used is in the instruction stream.
-template <int ACT, int DACT, int EXT>
+template <int ACT, int DACT, int EXT, typename XT>
 __device__ __forceinline__ void epilogue_vec8(const EpiParams& e, int64_t m, int n0, float* v, const float* bias8,
-                                              const EpiExt& x, int i) {
+                                              const XT& x, int i) {
     float rs = 1.f;
     if (e.row_scale) rs = e.row_scale[m % e.row_mod];
     const int64_t off = m * e.ldo + n0;
@@ -384,6 +384,220 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+
+
+// ---------------------------------------------------------------------------------------- wide epilogue (v4)
+// Same mainloop as gemm_tc_kernel, but the epilogue is spread over 4*(BN/64) warps (one 32-row x 64-column slab
+// each) working in 16-column chunks: 16-register TMEM loads, 2 x 16 B residual vectors per lane and chunk.  The
+// low register footprint is what allows 12-16 epilogue warps per CTA (ncu showed the 8-warp epilogue latency bound:
+// IPC 0.12 per warp, long-scoreboard + fixed-latency stalls), i.e. twice the memory/ALU latency tolerance per SM.
+struct EpiExt16 {
+    uint4 d[2], r1[2], r2[2];
+};
+template <int EXT>
+__device__ __forceinline__ void epi_prefetch16(const EpiParams& e, EpiExt16& x, int64_t row_base, int row_l, int n0, int M) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int64_t row = row_base + i * 16 + row_l;
+        if (row < M) {
+            const int64_t off = row * e.ldo + n0;
+            if ((EXT & 1) && (EXT != 7 || e.dact_src)) x.d[i] = *reinterpret_cast<const uint4*>((const bf16*)e.dact_src + off);
+            if ((EXT & 2) && (EXT != 7 || e.res1)) x.r1[i] = *reinterpret_cast<const uint4*>((const bf16*)e.res1 + off);
+            if ((EXT & 4) && (EXT != 7 || e.res2)) x.r2[i] = *reinterpret_cast<const uint4*>((const bf16*)e.res2 + off);
+        }
+    }
+}
+constexpr int STG16_LD = 20;                                 // floats per staged row (16 + 4): conflict-free 128-bit access
+constexpr int STG16_WARP_FLOATS = 32 * STG16_LD + 64;        // + this warp's 64 bias values
+template <int BN> struct TileCfg3 {
+    static constexpr int EPI_W = 4 * (BN / 64);              // epilogue warps: 4 TMEM quadrants x (BN/64) column slabs
+    static constexpr int THREADS = 64 + 32 * EPI_W;
+    static constexpr int STG = EPI_W * STG16_WARP_FLOATS * 4 + 1024;
+    static constexpr int B_STAGE_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int STAGES_RAW = (232448 - STG - 1024 - 256) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+    static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG + 1024 + 256;
+};
+
+template <int ACT, int DACT, int EXT, typename WaitFn>
+__device__ __forceinline__ void epilogue_slab64(const EpiParams& epi, float* stg, float* scol, int col_in_tile, uint32_t taddr,
+                                                int64_t row_base, int n_base, int M, int lane, WaitFn wait_acc) {
+    constexpr bool DB = (EXT != 7);
+    const int row_l = lane & 15, c0 = (lane >> 4) * 8;       // 16 rows x two 8-column vectors per pass, 2 passes per chunk
+    float* sbias = stg + 32 * STG16_LD;
+    if (epi.bias) {
+        sbias[lane] = __bfloat162float(((const bf16*)epi.bias)[n_base + lane]);
+        sbias[lane + 32] = __bfloat162float(((const bf16*)epi.bias)[n_base + lane + 32]);
+    }
+    EpiExt16 cur, nxt;
+    epi_prefetch16<EXT>(epi, cur, row_base, row_l, n_base + c0, M);
+    wait_acc();
+    uint32_t r[16];
+    ptx::tmem_ld_32x32b_x16(taddr, r);
+#pragma unroll 1
+    for (int c = 0; c < 64; c += 16) {
+        ptx::tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<uint4*>(stg + lane * STG16_LD + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+        if (c + 16 < 64) {
+            ptx::tmem_ld_32x32b_x16(taddr + c + 16, r);
+            if (DB) epi_prefetch16<EXT>(epi, nxt, row_base, row_l, n_base + c + 16 + c0, M);
+        }
+        __syncwarp();
+        const int n0 = n_base + c + c0;
+        float bias8[8];
+        if (epi.bias) {
+            *reinterpret_cast<float4*>(bias8) = *reinterpret_cast<const float4*>(sbias + c + c0);
+            *reinterpret_cast<float4*>(bias8 + 4) = *reinterpret_cast<const float4*>(sbias + c + c0 + 4);
+        }
+        float cs8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cs8[j] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int rl = i * 16 + row_l;
+            const int64_t row = row_base + rl;
+            float v[8];
+            *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(stg + rl * STG16_LD + c0);
+            *reinterpret_cast<float4*>(v + 4) = *reinterpret_cast<const float4*>(stg + rl * STG16_LD + c0 + 4);
+            if (row < M) {
+                epilogue_vec8<ACT, DACT, EXT>(epi, row, n0, v, bias8, cur, i);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) cs8[j] += v[j];
+            }
+        }
+        if (epi.colsum_out) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float t = cs8[j];
+                t += __shfl_xor_sync(0xffffffffu, t, 1);
+                t += __shfl_xor_sync(0xffffffffu, t, 2);
+                t += __shfl_xor_sync(0xffffffffu, t, 4);
+                t += __shfl_xor_sync(0xffffffffu, t, 8);
+                if ((lane & 15) == 0) atomicAdd(scol + col_in_tile + c + c0 + j, t);
+            }
+        }
+        __syncwarp();
+        if (DB) cur = nxt;
+        else if (c + 16 < 64) epi_prefetch16<EXT>(epi, cur, row_base, row_l, n_base + c + 16 + c0, M);
+    }
+}
+
+template <int BN, int V>
+__global__ void __launch_bounds__(TileCfg3<BN>::THREADS, 1)
+gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const EpiParams epi,
+                const int M, const int N, const int K) {
+    pdl_trigger();
+    using Cfg = TileCfg3<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr int EPI_W = Cfg::EPI_W;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+    float* stg_all = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+    float* scol = stg_all + EPI_W * STG16_WARP_FLOATS;
+    if (threadIdx.x < 256) scol[threadIdx.x] = 0.f;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::STG);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = N / BN;
+    const int m_tiles = (M + BM - 1) / BM;
+    const int total = n_tiles * m_tiles;
+    const int KB = K / BK;
+    if (threadIdx.x == 0) {
+        ptx::prefetch_tmap(&tmA);
+        ptx::prefetch_tmap(&tmB);
+        for (int i = 0; i < STAGES; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], EPI_W); }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) ptx::tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+                for (int kb = 0; kb < KB; ++kb) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    ptx::tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+                    ptx::tma_load_2d(sa + A_STAGE_BYTES, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN);
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = 0; kb < KB; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint64_t adesc = ptx::umma_desc_kmajor_sw128(sa);
+                    const uint64_t bdesc = ptx::umma_desc_kmajor_sw128(sa + A_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    ptx::umma_commit(&empty_bar[stage]);
+                    if (kb == KB - 1) ptx::umma_commit(&tfull_bar[as]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        using EV = EpiVariant<V>;
+        const int quad = warp & 3;
+        const int slab = (warp - 2) >> 2;                     // 64-column slab of the tile
+        float* stg = stg_all + (warp - 2) * STG16_WARP_FLOATS;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+            const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            const int64_t row_base = (int64_t)m_blk * BM + quad * 32;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN + slab * 64;
+            epilogue_slab64<EV::ACT, EV::DACT, EV::EXT>(epi, stg, scol, slab * 64, taddr, row_base, n_blk * BN + slab * 64, M, lane,
+                                                        [&]() {
+                                                            ptx::mbar_wait(&tfull_bar[as], aphase);
+                                                            ptx::tc_fence_after();
+                                                        });
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (epi.colsum_out) {
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_W) : "memory");
+                const int te = threadIdx.x - 64;
+                if (te < BN) { atomicAdd(epi.colsum_out + n_blk * BN + te, scol[te]); scol[te] = 0.f; }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_W) : "memory");
+            }
+            if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        ptx::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    }
+}
 
 // ---------------------------------------------------------------------------------------- 2-CTA GEMM
 // Same pipeline with tcgen05.mma.cta_group::2: a CTA pair computes a 256 x BN tile.  Each CTA TMA-loads its
@@ -690,6 +904,7 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------- host side
+static int g_wide_epilogue = 1;   // 1 (default): gemm_tc3_kernel (4*(BN/64) epilogue warps, 16-column chunks); 0: gemm_tc_kernel
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -776,6 +991,18 @@ static int launch_tc_v(const CUtensorMap& ta, const CUtensorMap& tb, const EpiPa
     }
     int total = (N / BN) * ((M + BM - 1) / BM);
     int grid = total < num_sms() ? total : num_sms();
+    if (g_wide_epilogue) {
+        using Cfg3 = TileCfg3<BN>;
+        static bool attr3 = false;
+        if (!attr3) {
+            if (cudaFuncSetAttribute(gemm_tc3_kernel<BN, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg3::SMEM_BYTES) != cudaSuccess)
+                return AIMB_ERR_CUDA;
+            attr3 = true;
+        }
+        launch_k((gemm_tc3_kernel<BN, V>), dim3(grid), dim3(Cfg3::THREADS), Cfg3::SMEM_BYTES, s, ta, tb, p, M, N, K);
+        AIMB_CHECK_LAUNCH();
+        return AIMB_OK;
+    }
     launch_k((gemm_tc_kernel<BN, V>), dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, s, ta, tb, p, M, N, K);
     AIMB_CHECK_LAUNCH();
     return AIMB_OK;
@@ -1109,7 +1336,10 @@ using namespace aimb;
 static int g_force_bn = 0;
 static int g_cta_mode = 0;   // 0/1: 1-CTA kernel (default), 2: CTA-pair (cta_group::2) kernel where it tiles
 extern "C" void aimb_debug_force_bn(int bn) { g_force_bn = bn; }
-extern "C" void aimb_debug_cta_mode(int mode) { g_cta_mode = mode; }
+extern "C" void aimb_debug_cta_mode(int mode) {
+    g_cta_mode = mode == 3 ? 1 : mode;   // 0/3: 1-CTA mainloop + wide epilogue (default), 1: 8-warp epilogue, 2: CTA pairs
+    aimb::g_wide_epilogue = (mode == 3 || mode == 0);
+}
 extern "C" void aimb_debug_skip_epilogue(int v) { cudaMemcpyToSymbol(g_dbg_skip_epilogue, &v, sizeof(int)); }
 
 extern "C" int aimb_gemm_nt(const void* A, int64_t lda, const void* W, int64_t ldw, const aimb_epilogue_t* epi, int64_t M,

@@ -91,6 +91,8 @@ def load():
     # programmatic dependent launch: every kernel implements the protocol (tests pass with it), but inside the captured
     # step it measured neutral (17.12 vs 17.09 ms) -> opt-in
     lib.aimb_debug_set_pdl(1 if os.environ.get("AIMB200_PDL", "0") == "1" else 0)
+    if os.environ.get("AIMB200_GEMM_MODE"):
+        lib.aimb_debug_cta_mode(int(os.environ["AIMB200_GEMM_MODE"]))
     _lib = lib
     return lib
 

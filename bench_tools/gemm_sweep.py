@@ -45,13 +45,13 @@ shapes = [(12608, 2304, 768), (12608, 768, 3072), (12608, 768, 768), (12608, 307
 if len(sys.argv) > 1:
     shapes = shapes[: int(sys.argv[1])]
 for (M, N, K) in shapes:
-    for mode in (1, 2):
-        for bn in (192, 256):
+    for mode in (1, 3):
+        for bn in (128, 192, 256):
             if N % bn or (mode == 2 and bn < 192):
                 continue
-            for skip in (0, 2, 1):
+            for skip in (0,):
                 us, tf = bench(M, N, K, bn, mode, skip)
-                print(f"M{M} N{N} K{K} {'1cta' if mode == 1 else '2cta'} BN{bn} {['epi  ','ldtm ','trans'][skip]} {us:8.1f} us {tf:7.1f} TFLOP/s", flush=True)
+                print(f"M{M} N{N} K{K} { {1:'1cta',2:'2cta',3:'wide'}[mode] } BN{bn} {['epi  ','ldtm ','trans'][skip]} {us:8.1f} us {tf:7.1f} TFLOP/s", flush=True)
 # reference point: cuBLAS through torch for the same shape (library call, context only)
 for (M, N, K) in shapes:
     a = torch.randn(M, K, device=dev).bfloat16()
