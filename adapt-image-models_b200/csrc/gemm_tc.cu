@@ -84,15 +84,31 @@ __device__ __forceinline__ void unpack8(const uint4& t, float* v) {
     for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
 }
 
+// QuickGELU for the bf16 tensor-core epilogues: sigmoid(z) = 0.5 + 0.5 tanh(z / 2) with the single-instruction
+// MUFU.TANH (max relative error 2^-11, an order below bf16 rounding) — 4 instructions per element instead of ~12
+// for the ex2 / rcp form (ncu: the c_fc epilogues were ~45 % issue-bound).  fp32 parity mode never comes here.
+__device__ __forceinline__ float tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float quick_gelu_fast(float u) {
+    const float h = 0.5f * u;
+    return fmaf(h, tanh_fast(0.851f * u), h);
+}
+__device__ __forceinline__ float quick_gelu_grad_fast(float u) {   // s + 1.702 u s (1 - s), s = (1 + t) / 2
+    const float t = tanh_fast(0.851f * u);
+    return fmaf(0.4255f * u, fmaf(-t, t, 1.f), fmaf(0.5f, t, 0.5f));
+}
 template <int ACT> __device__ __forceinline__ float act_fn(float v, int rt) {
     if (ACT < 0) return apply_act(rt, v);
-    if (ACT == AIMB_ACT_QUICKGELU) return quick_gelu(v);
+    if (ACT == AIMB_ACT_QUICKGELU) return quick_gelu_fast(v);
     if (ACT == AIMB_ACT_GELU) return gelu_erf(v);
     return v;
 }
 template <int ACT> __device__ __forceinline__ float act_grad_fn(float u, int rt) {
     if (ACT < 0) return apply_act_grad(rt, u);
-    if (ACT == AIMB_ACT_QUICKGELU) return quick_gelu_grad(u);
+    if (ACT == AIMB_ACT_QUICKGELU) return quick_gelu_grad_fast(u);
     if (ACT == AIMB_ACT_GELU) return gelu_erf_grad(u);
     return 1.f;
 }
@@ -111,10 +127,17 @@ __device__ __forceinline__ void epilogue_vec8(const EpiParams& e, int64_t m, int
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = fmaf(bias8[j], bs, v[j]);
     }
-    if (e.out_pre) {
-        st8_bf16((bf16*)e.out_pre + off, v);
+    if (e.out_pre) {     // the activation sees the bf16-rounded pre-activation, exactly what backward will read
+        uint4 pk;
+        uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = roundT<bf16>(v[j]);
+        for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            pw[j] = *reinterpret_cast<uint32_t*>(&h2);
+            v[2 * j] = __uint_as_float(pw[j] << 16);
+            v[2 * j + 1] = __uint_as_float(pw[j] & 0xffff0000u);
+        }
+        *reinterpret_cast<uint4*>((bf16*)e.out_pre + off) = pk;
     }
     if (ACT != AIMB_ACT_NONE && (ACT > 0 || e.act != AIMB_ACT_NONE)) {
 #pragma unroll
@@ -126,8 +149,10 @@ __device__ __forceinline__ void epilogue_vec8(const EpiParams& e, int64_t m, int
         for (int j = 0; j < 8; ++j) v[j] *= act_grad_fn<DACT>(t[j], e.dact);
     }
     const float sc = e.alpha * ((e.row_scale && !e.bias_rowscaled) ? rs : 1.f);
+    if (sc != 1.f) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] *= sc;
+        for (int j = 0; j < 8; ++j) v[j] *= sc;
+    }
     if ((EXT & 2) && (EXT != 7 || e.res1)) {
         unpack8(x.r1[i], t);
 #pragma unroll
@@ -435,10 +460,18 @@ __device__ __forceinline__ void epilogue_slab64(const EpiParams& epi, float* stg
     epi_prefetch16<EXT>(epi, cur, row_base, row_l, n_base + c0, M);
     wait_acc();
     uint32_t r[16];
+    const int dbg = g_dbg_skip_epilogue;     // bench_tools only: 1 = drain TMEM, 2 = + staging, 3 = all but global stores
+    EpiParams epi_l = epi;
+    if (dbg == 3) { epi_l.out = nullptr; epi_l.out_pre = nullptr; }
     ptx::tmem_ld_32x32b_x16(taddr, r);
 #pragma unroll 1
     for (int c = 0; c < 64; c += 16) {
         ptx::tmem_wait_ld();
+        if (dbg == 1) {
+            if (r[0] == 0x7fc12345u && r[5] == 0x12345u) stg[lane] = __uint_as_float(r[1]);
+            if (c + 16 < 64) ptx::tmem_ld_32x32b_x16(taddr + c + 16, r);
+            continue;
+        }
 #pragma unroll
         for (int j = 0; j < 16; j += 4)
             *reinterpret_cast<uint4*>(stg + lane * STG16_LD + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
@@ -447,6 +480,13 @@ __device__ __forceinline__ void epilogue_slab64(const EpiParams& epi, float* stg
             if (DB) epi_prefetch16<EXT>(epi, nxt, row_base, row_l, n_base + c + 16 + c0, M);
         }
         __syncwarp();
+        if (dbg == 2) {
+            float4 a = *reinterpret_cast<const float4*>(stg + row_l * STG16_LD + c0);
+            float4 b = *reinterpret_cast<const float4*>(stg + (row_l + 16) * STG16_LD + c0 + 4);
+            if (a.x == 1.2345e-30f && b.y == 3.21e-30f) sbias[lane] = a.y;
+            __syncwarp();
+            continue;
+        }
         const int n0 = n_base + c + c0;
         float bias8[8];
         if (epi.bias) {
@@ -464,7 +504,7 @@ __device__ __forceinline__ void epilogue_slab64(const EpiParams& epi, float* stg
             *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(stg + rl * STG16_LD + c0);
             *reinterpret_cast<float4*>(v + 4) = *reinterpret_cast<const float4*>(stg + rl * STG16_LD + c0 + 4);
             if (row < M) {
-                epilogue_vec8<ACT, DACT, EXT>(epi, row, n0, v, bias8, cur, i);
+                epilogue_vec8<ACT, DACT, EXT>(epi_l, row, n0, v, bias8, cur, i);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) cs8[j] += v[j];
             }
@@ -591,6 +631,337 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
         }
     }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        ptx::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------- row-layout epilogue (v5)
+// gemm_tc4_kernel: same TMA / tcgen05 mainloop, but the epilogue never transposes fp32 accumulators.  Measured on
+// the v4 kernel (bench_tools/gemm_epi.py, SKIPS=1,2,3,0): draining TMEM and the math are hidden under the mainloop,
+// what is not hidden are (a) residual / saved-activation loads — one 16-column chunk of look-ahead is ~16 KB in
+// flight per SM, a few % of what HBM latency x bandwidth needs — and (b) stores issued as 16 rows x 32 B per warp
+// instruction (the LSU pays per row segment: two output streams cost 30 us on the c_fc GEMM).  Here:
+//   * each epilogue warp owns a 32-row x 64-column slab and 4 KB shared-memory slab buffers (128 B rows, 16-byte
+//     chunks XOR-swizzled by row & 7 — conflict-free both for "lane = row" and for "8 lanes = one row" access);
+//   * residual / dact operands for the WHOLE slab are fetched with cp.async (16 B per lane, 4 full rows per
+//     instruction) one tile ahead — no registers, 4 KB per warp and tensor in flight;
+//   * the math runs in the TMEM-native layout (lane = row, 16 consecutive columns per tcgen05.ld.x16), results are
+//     packed to bf16 and written IN PLACE over the consumed residual chunk;
+//   * the slab is flushed with full 128-byte lines: 8 lanes x 16 B per row, 4 rows per store instruction;
+//   * column sums (bias gradients) are taken at flush time from the values actually stored.
+template <int V> struct EpiBufs {
+    static constexpr int EXT = EpiVariant<V>::EXT;
+    static constexpr bool PRE = (V == 1 || V == 2);
+    static constexpr int NEXT = ((EXT & 1) ? 1 : 0) + ((EXT & 2) ? 1 : 0) + ((EXT & 4) ? 1 : 0);
+    static constexpr int NBUF = (NEXT > 0 ? NEXT : 1) + (PRE ? 1 : 0);       // out aliases the first operand buffer
+    static constexpr int WARP_BYTES = NBUF * 4096 + 256;                     // + 64 fp32 bias values
+};
+template <int BN, int V> struct TileCfg4 {
+    static constexpr int EPI_W = 4 * (BN / 64);
+    static constexpr int THREADS = 64 + 32 * EPI_W;
+    static constexpr int EPI_BYTES = EPI_W * EpiBufs<V>::WARP_BYTES + 1024;  // + scol[256]
+    static constexpr int B_STAGE_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int STAGES_RAW = (232448 - EPI_BYTES - 1024 - 256) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+    static constexpr bool OK = STAGES >= 3;
+    static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    static constexpr int SMEM_BYTES = (STAGES > 0 ? STAGES : 1) * STAGE_BYTES + EPI_BYTES + 1024 + 256;
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t slab_off(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
+
+// one warp instruction = 4 full 128-byte rows of the slab
+__device__ __forceinline__ void slab_fetch(uint32_t buf, const bf16* g, int64_t ldo, int64_t row_base, int n_base, int M, int lane) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int row = i * 4 + (lane >> 3), ch = lane & 7;
+        if (row_base + row < M) cp_async16(buf + slab_off(row, ch), g + (row_base + row) * ldo + n_base + ch * 8);
+    }
+}
+
+// 8 columns of one row: v = accumulators in, packed bf16 result out (and the packed pre-activation when asked)
+template <int ACT, int DACT, int EXT>
+__device__ __forceinline__ uint4 epi_math8(const EpiParams& e, float rs, float* v, const float* bias8, const uint4& xd,
+                                           const uint4& x1, const uint4& x2, uint4& pre_pk, bool want_pre) {
+    float t[8];
+    if (e.bias) {
+        const float bs = e.bias_rowscaled ? rs : 1.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(bias8[j], bs, v[j]);
+    }
+    if (want_pre) {
+        uint32_t* pw = reinterpret_cast<uint32_t*>(&pre_pk);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            pw[j] = *reinterpret_cast<uint32_t*>(&h2);
+            v[2 * j] = __uint_as_float(pw[j] << 16);
+            v[2 * j + 1] = __uint_as_float(pw[j] & 0xffff0000u);
+        }
+    }
+    if (ACT != AIMB_ACT_NONE) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = act_fn<ACT>(v[j], e.act);
+    }
+    if ((EXT & 1) && DACT != AIMB_ACT_NONE) {
+        unpack8(xd, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] *= act_grad_fn<DACT>(t[j], e.dact);
+    }
+    const float sc = e.alpha * ((e.row_scale && !e.bias_rowscaled) ? rs : 1.f);
+    if (sc != 1.f) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] *= sc;
+    }
+    if (EXT & 2) {
+        unpack8(x1, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += t[j];
+    }
+    if (EXT & 4) {
+        unpack8(x2, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += t[j];
+    }
+    uint4 o;
+    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        ow[j] = *reinterpret_cast<uint32_t*>(&h2);
+    }
+    return o;
+}
+
+__device__ __forceinline__ bool want_pre_k(const EpiParams& e, bool pre) { return pre && e.out_pre != nullptr; }
+template <int BN, int V>
+__global__ void __launch_bounds__(TileCfg4<BN, V>::THREADS, 1)
+gemm_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmP, const EpiParams epi,
+                const int M, const int N, const int K) {
+    pdl_trigger();
+    using Cfg = TileCfg4<BN, V>;
+    using EB = EpiBufs<V>;
+    using EV = EpiVariant<V>;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr int EPI_W = Cfg::EPI_W;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES;
+    float* scol = reinterpret_cast<float*>(epi_smem + EPI_W * EB::WARP_BYTES);   // [slab buffers][bias][scol]
+    if (threadIdx.x < 256) scol[threadIdx.x] = 0.f;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + Cfg::EPI_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = N / BN;
+    const int m_tiles = (M + BM - 1) / BM;
+    const int total = n_tiles * m_tiles;
+    const int KB = K / BK;
+    if (threadIdx.x == 0) {
+        ptx::prefetch_tmap(&tmA);
+        ptx::prefetch_tmap(&tmB);
+        for (int i = 0; i < STAGES; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], EPI_W); }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) ptx::tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+                for (int kb = 0; kb < KB; ++kb) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    ptx::tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+                    ptx::tma_load_2d(sa + A_STAGE_BYTES, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN);
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = 0; kb < KB; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint64_t adesc = ptx::umma_desc_kmajor_sw128(sa);
+                    const uint64_t bdesc = ptx::umma_desc_kmajor_sw128(sa + A_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    ptx::umma_commit(&empty_bar[stage]);
+                    if (kb == KB - 1) ptx::umma_commit(&tfull_bar[as]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        constexpr int EXT = EV::EXT;
+        const int ew = warp - 2;
+        const int quad = warp & 3;
+        const int slab = ew >> 2;
+        constexpr bool TMA_ST = (EXT == 0);                   // plain / activation variants: the slab leaves through TMA
+        const uint32_t buf0 = ptx::smem_u32(epi_smem + ew * (EB::NBUF * 4096));   // out (in place over dact_src / res1); 1 KB aligned
+        const uint32_t buf1 = buf0 + 4096;                    // out_pre, or res2
+        float* sbias = reinterpret_cast<float*>(epi_smem + EPI_W * (EB::NBUF * 4096) + ew * 256);
+        if (TMA_ST && lane == 0) { ptx::prefetch_tmap(&tmO); if (want_pre_k(epi, EB::PRE)) ptx::prefetch_tmap(&tmP); }
+        const bf16* g0 = (EXT & 1) ? (const bf16*)epi.dact_src : (const bf16*)epi.res1;
+        const bf16* g1 = (const bf16*)epi.res2;
+        const bool want_pre = EB::PRE && epi.out_pre != nullptr;
+        const int dbg = g_dbg_skip_epilogue;   // bench_tools only: 4 = no flush, 5 = no slab writes either, 6 = STG flush instead of TMA
+        auto fetch = [&](int tile) {
+            const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+            const int64_t rb = (int64_t)m_blk * BM + quad * 32;
+            const int nb = n_blk * BN + slab * 64;
+            if (EXT & 3) slab_fetch(buf0, g0, epi.ldo, rb, nb, M, lane);
+            if (EXT & 4) slab_fetch(buf1, g1, epi.ldo, rb, nb, M, lane);
+        };
+        if (EXT != 0 && (int)blockIdx.x < total) fetch(blockIdx.x);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+            const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            const int64_t row_base = (int64_t)m_blk * BM + quad * 32;
+            const int n_base = n_blk * BN + slab * 64;
+            const int64_t row = row_base + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN + slab * 64;
+            if (epi.bias) {
+                sbias[lane] = __bfloat162float(((const bf16*)epi.bias)[n_base + lane]);
+                sbias[lane + 32] = __bfloat162float(((const bf16*)epi.bias)[n_base + lane + 32]);
+            }
+            float rs = 1.f;
+            if (epi.row_scale && row < M) rs = epi.row_scale[(int)row % epi.row_mod];
+            ptx::mbar_wait(&tfull_bar[as], aphase);
+            ptx::tc_fence_after();
+            uint32_t ra[16], rb16[16];
+            ptx::tmem_ld_32x32b_x16(taddr, ra);
+            cp_async_commit_wait();
+            if (TMA_ST && lane == 0) ptx::bulk_wait_read0();   // the previous tile's TMA store has finished reading the slab
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t (&cur)[16] = (q & 1) ? rb16 : ra;
+                uint32_t (&nxt)[16] = (q & 1) ? ra : rb16;
+                ptx::tmem_wait_ld();
+                if (q < 3) ptx::tmem_ld_32x32b_x16(taddr + (q + 1) * 16, nxt);
+                if (q == 3) {                                  // accumulator drained: hand the TMEM buffer back early
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
+                }
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int ch = 2 * q + hh;
+                    const uint32_t off = slab_off(lane, ch);
+                    uint4 xd = make_uint4(0, 0, 0, 0), x1 = xd, x2 = xd, pre_pk = xd;
+                    if (EXT & 1) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(xd.x), "=r"(xd.y), "=r"(xd.z), "=r"(xd.w) : "r"(buf0 + off));
+                    if ((EXT & 3) == 2) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x1.x), "=r"(x1.y), "=r"(x1.z), "=r"(x1.w) : "r"(buf0 + off));
+                    if (EXT & 4) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x2.x), "=r"(x2.y), "=r"(x2.z), "=r"(x2.w) : "r"(buf1 + off));
+                    float v[8], bias8[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(cur[hh * 8 + j]);
+                    if (epi.bias) {
+                        *reinterpret_cast<float4*>(bias8) = *reinterpret_cast<const float4*>(sbias + ch * 8);
+                        *reinterpret_cast<float4*>(bias8 + 4) = *reinterpret_cast<const float4*>(sbias + ch * 8 + 4);
+                    }
+                    const uint4 o = epi_math8<EV::ACT, EV::DACT, EXT>(epi, rs, v, bias8, xd, x1, x2, pre_pk, want_pre);
+                    if (dbg == 5 && o.x != 0x12345678u) continue;
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(buf0 + off), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+                    if (want_pre)
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(buf1 + off), "r"(pre_pk.x), "r"(pre_pk.y), "r"(pre_pk.z), "r"(pre_pk.w) : "memory");
+                }
+            }
+            if (dbg == 4 || dbg == 5) { __syncwarp(); continue; }
+            if (TMA_ST && !epi.colsum_out && dbg != 6) {
+                ptx::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    ptx::tma_store_2d(&tmO, buf0, n_base, (int)row_base);
+                    if (want_pre) ptx::tma_store_2d(&tmP, buf1, n_base, (int)row_base);
+                    ptx::bulk_commit();
+                }
+                continue;
+            }
+            __syncwarp();
+            // flush: 4 full rows per instruction
+            float cs8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cs8[j] = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = i * 4 + (lane >> 3), ch = lane & 7;
+                const int64_t grow = row_base + r;
+                if (grow < M) {
+                    const uint32_t off = slab_off(r, ch);
+                    uint4 o;
+                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w) : "r"(buf0 + off));
+                    const int64_t goff = grow * epi.ldo + n_base + ch * 8;
+                    *reinterpret_cast<uint4*>((bf16*)epi.out + goff) = o;
+                    if (want_pre) {
+                        uint4 pp;
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(pp.x), "=r"(pp.y), "=r"(pp.z), "=r"(pp.w) : "r"(buf1 + off));
+                        *reinterpret_cast<uint4*>((bf16*)epi.out_pre + goff) = pp;
+                    }
+                    if (epi.colsum_out) {
+                        float t[8];
+                        unpack8(o, t);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) cs8[j] += t[j];
+                    }
+                }
+            }
+            if (epi.colsum_out) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float t = cs8[j];
+                    t += __shfl_xor_sync(0xffffffffu, t, 8);
+                    t += __shfl_xor_sync(0xffffffffu, t, 16);
+                    if (lane < 8) atomicAdd(scol + slab * 64 + lane * 8 + j, t);
+                }
+            }
+            __syncwarp();
+            if (EXT != 0 && tile + (int)gridDim.x < total) fetch(tile + gridDim.x);
+            if (epi.colsum_out) {
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_W) : "memory");
+                const int te = threadIdx.x - 64;
+                if (te < BN) { atomicAdd(epi.colsum_out + n_blk * BN + te, scol[te]); scol[te] = 0.f; }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_W) : "memory");
+            }
+        }
+    }
+    if (warp >= 2 && lane == 0) ptx::bulk_wait0();   // smem must stay valid until the TMA stores have read it
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -904,7 +1275,11 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------- host side
-static int g_wide_epilogue = 1;   // 1 (default): gemm_tc3_kernel (4*(BN/64) epilogue warps, 16-column chunks); 0: gemm_tc_kernel
+// epilogue kernel selection: 0 = auto (gemm_tc4_kernel, except the two-output-stream c_fc variant V=1 which measures
+// faster on gemm_tc_kernel: its stores trickle out chunk by chunk instead of one burst per tile), 1 = gemm_tc_kernel,
+// 3 = gemm_tc3_kernel, 4 = gemm_tc4_kernel wherever its shared-memory budget allows
+static int g_epi_kernel = 0;
+static inline bool use_tc4(int v) { return (g_epi_kernel == 4 || (g_epi_kernel == 0 && v != 1)) && v != 7; }
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -991,7 +1366,26 @@ static int launch_tc_v(const CUtensorMap& ta, const CUtensorMap& tb, const EpiPa
     }
     int total = (N / BN) * ((M + BM - 1) / BM);
     int grid = total < num_sms() ? total : num_sms();
-    if (g_wide_epilogue) {
+    if constexpr (V != 7 && TileCfg4<BN, V>::OK) {
+        if (use_tc4(V)) {
+            using Cfg4 = TileCfg4<BN, V>;
+            static bool attr4 = false;
+            if (!attr4) {
+                if (cudaFuncSetAttribute(gemm_tc4_kernel<BN, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg4::SMEM_BYTES) != cudaSuccess)
+                    return AIMB_ERR_CUDA;
+                attr4 = true;
+            }
+            CUtensorMap to = ta, tp = ta;                       // placeholders when the variant does not store through TMA
+            if (EpiVariant<V>::EXT == 0) {
+                if (make_tmap_bf16(&to, p.out, M, N, p.ldo, 32)) return AIMB_ERR_DRIVER;
+                if (p.out_pre && make_tmap_bf16(&tp, p.out_pre, M, N, p.ldo, 32)) return AIMB_ERR_DRIVER;
+            }
+            launch_k((gemm_tc4_kernel<BN, V>), dim3(grid), dim3(Cfg4::THREADS), Cfg4::SMEM_BYTES, s, ta, tb, to, tp, p, M, N, K);
+            AIMB_CHECK_LAUNCH();
+            return AIMB_OK;
+        }
+    }
+    if (g_epi_kernel == 3 || g_epi_kernel == 4) {
         using Cfg3 = TileCfg3<BN>;
         static bool attr3 = false;
         if (!attr3) {
@@ -1071,7 +1465,29 @@ static int pick_bn2(int64_t M, int N) {
 // Pick the N tile that minimises  waves x (mainloop + fixed per-tile cost)  over the persistent grid.
 // Per-tile time ~ KB*bn (MMA-bound mainloop) + ~1536 (pipeline fill / epilogue tail), fitted to the sweep in
 // profiles/ (bench_tools/gemm_sweep.py): N=2304/3072 prefer 256, N=768 prefers 192.
-static int pick_bn(int64_t M, int N, int K) {
+// which (tile width, epilogue variant) pairs leave >= 3 pipeline stages next to the slab buffers of gemm_tc4_kernel
+template <int V> static bool tc4_ok_v(int bn) {
+    switch (bn) {
+        case 256: return TileCfg4<256, V>::OK;
+        case 192: return TileCfg4<192, V>::OK;
+        case 128: return TileCfg4<128, V>::OK;
+        case 64: return TileCfg4<64, V>::OK;
+    }
+    return false;
+}
+static bool tc4_ok(int bn, int v) {
+    switch (v) {
+        case 0: return tc4_ok_v<0>(bn);
+        case 1: return tc4_ok_v<1>(bn);
+        case 2: return tc4_ok_v<2>(bn);
+        case 3: return tc4_ok_v<3>(bn);
+        case 4: return tc4_ok_v<4>(bn);
+        case 5: return tc4_ok_v<5>(bn);
+        case 6: return tc4_ok_v<6>(bn);
+    }
+    return false;
+}
+static int pick_bn(int64_t M, int N, int K, int variant = -1) {
     const int cand[4] = {256, 192, 128, 64};
     int best = 0; double best_cost = 1e30;
     int64_t mt = (M + BM - 1) / BM;
@@ -1079,6 +1495,7 @@ static int pick_bn(int64_t M, int N, int K) {
     for (int i = 0; i < 4; ++i) {
         int bn = cand[i];
         if (N % bn) continue;
+        if (variant >= 0 && variant < 7 && !tc4_ok(bn, variant)) continue;
         int64_t tiles = mt * (N / bn);
         int64_t waves = (tiles + num_sms() - 1) / num_sms();
         double per_tile = kb * (double)(bn < 128 ? 128 : bn) + 1536.0;   // below N=128 the A-operand traffic dominates
@@ -1107,7 +1524,7 @@ int gemm_tc_launch(const void* A, int64_t lda, const void* W, int64_t ldw, const
             }
         }
     }
-    int bn = force_bn > 0 ? force_bn : pick_bn(M, N, K);
+    int bn = force_bn > 0 ? force_bn : pick_bn(M, N, K, use_tc4(pick_variant(p)) ? pick_variant(p) : -1);
     if (bn == 0 || N % bn) return AIMB_ERR_ARG;
     CUtensorMap ta, tb;
     int rc = make_tmap_bf16(&ta, A, M, K, lda, BM);
@@ -1337,8 +1754,8 @@ static int g_force_bn = 0;
 static int g_cta_mode = 0;   // 0/1: 1-CTA kernel (default), 2: CTA-pair (cta_group::2) kernel where it tiles
 extern "C" void aimb_debug_force_bn(int bn) { g_force_bn = bn; }
 extern "C" void aimb_debug_cta_mode(int mode) {
-    g_cta_mode = mode == 3 ? 1 : mode;   // 0/3: 1-CTA mainloop + wide epilogue (default), 1: 8-warp epilogue, 2: CTA pairs
-    aimb::g_wide_epilogue = (mode == 3 || mode == 0);
+    g_cta_mode = mode == 2 ? 2 : 1;      // 2: CTA-pair kernel (cta_group::2); everything else: 1-CTA mainloop with
+    aimb::g_epi_kernel = mode == 2 ? 1 : mode;   // 0 auto, 1 gemm_tc_kernel, 3 gemm_tc3_kernel, 4 gemm_tc4_kernel
 }
 extern "C" void aimb_debug_skip_epilogue(int v) { cudaMemcpyToSymbol(g_dbg_skip_epilogue, &v, sizeof(int)); }
 
