@@ -10,6 +10,7 @@
 //   backward: one CTA per (frame, head) with Q, K, V, dO in shared memory; phase 1 (warp = 16 query rows) recomputes P
 //             from the saved LSE and produces dQ, phase 2 (warp = 16 key rows) produces dK, dV.  No atomics, no score
 //             matrix in HBM.  (Splitting the phases into separate 2-matrix CTAs was measured slower: 2x smem fills.)
+#include <cstdlib>
 #include "common.cuh"
 
 namespace aimb {
@@ -37,6 +38,11 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
         "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
@@ -147,7 +153,7 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_mma_kernel(const bf16* __rest
         cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
         // every 32-key chunk that is processed holds at least one valid key (npad - n < 32), so the max is finite
         const float mn0 = fmaxf(m0, cm0), mn1 = fmaxf(m1, cm1);
-        const float c0 = exp2f(m0 - mn0), c1 = exp2f(m1 - mn1);
+        const float c0 = ex2_ftz(m0 - mn0), c1 = ex2_ftz(m1 - mn1);
         m0 = mn0; m1 = mn1;
         l0 *= c0; l1 *= c1;
 #pragma unroll
@@ -155,8 +161,8 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_mma_kernel(const bf16* __rest
         uint32_t pa[2][4];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
-            float p0 = exp2f(s[nt][0] - m0), p1 = exp2f(s[nt][1] - m0);
-            float p2 = exp2f(s[nt][2] - m1), p3 = exp2f(s[nt][3] - m1);
+            float p0 = ex2_ftz(s[nt][0] - m0), p1 = ex2_ftz(s[nt][1] - m0);
+            float p2 = ex2_ftz(s[nt][2] - m1), p3 = ex2_ftz(s[nt][3] - m1);
             l0 += p0 + p1; l1 += p2 + p3;
             pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(p0, p1);
             pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p2, p3);
@@ -226,25 +232,41 @@ __global__ void __launch_bounds__(NW * 32) attn_bwd_mma_kernel(const bf16* __res
     load_tile_async(sV, base + 2 * D, ld, n, npad, tid, blockDim.x);
     load_tile_async(sG, gb, D, n, npad, tid, blockDim.x);
     const float* lr = lse + ((int64_t)f * heads + h) * n;
-    for (int i = tid; i < npad; i += blockDim.x) sL[i] = i < n ? lr[i] * LOG2E : 0.f;
-    // delta_i = sum_d dO[i,d] * O[i,d]   (one warp per row; coalesced 128 B rows)
-    for (int i = warp; i < npad; i += nwarps) {
+    // padded rows get lse = +inf: exp2(s - inf) = 0 masks padded QUERIES for free (phase 2 needs no predicate)
+    for (int i = tid; i < npad; i += blockDim.x) sL[i] = i < n ? lr[i] * LOG2E : INFINITY;
+    // sDl_i = -0.125 * delta_i, delta_i = sum_d dO[i,d] * O[i,d].  One THREAD per row with all 16 x 16-byte loads in
+    // flight at once (ncu: the former one-warp-per-row loop serialised ~17 global round trips per warp = 19 % of the
+    // kernel's stall samples).
+    for (int i = tid; i < npad; i += blockDim.x) {
         float acc = 0.f;
         if (i < n) {
-            __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(gb + (int64_t)i * D + 2 * lane);
-            __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(ob + (int64_t)i * D + 2 * lane);
-            float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
-            acc = fa.x * fb.x + fa.y * fb.y;
+            const uint4* gp = reinterpret_cast<const uint4*>(gb + (int64_t)i * D);
+            const uint4* op = reinterpret_cast<const uint4*>(ob + (int64_t)i * D);
+            uint4 a[8], b[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { a[j] = __ldg(gp + j); b[j] = __ldg(op + j); }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t* aw = reinterpret_cast<const uint32_t*>(&a[j]);
+                const uint32_t* bw = reinterpret_cast<const uint32_t*>(&b[j]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float2 fa = unpack_bf16(aw[k]), fb = unpack_bf16(bw[k]);
+                    acc = fmaf(fa.x, fb.x, acc);
+                    acc = fmaf(fa.y, fb.y, acc);
+                }
+            }
         }
-        acc = warp_sum(acc);
-        if (lane == 0) sDl[i] = acc;
+        sDl[i] = -0.125f * acc;
     }
     cp_async_wait_all();
     __syncthreads();
 
     const int g = lane >> 2, t = lane & 3;
-    const int r0 = warp * 16;   // this warp's 16 rows (queries in phase 1, keys in phase 2)
-    if (r0 >= n) return;        // no further block-wide barriers below
+    // a warp owns 16 rows (queries in phase 1, keys in phase 2); with more row tiles than warps (n = 257 runs 17
+    // tiles on 9 warps: 17 warps would be capped at 96 registers and spill) it makes a second pass.
+    // No block-wide barriers below.
+    for (int r0 = warp * 16; r0 < n; r0 += nwarps * 16) {
 
     // ---------------- phase 1: dQ for query rows r0..r0+15
     {
@@ -286,8 +308,12 @@ __global__ void __launch_bounds__(NW * 32) attn_bwd_mma_kernel(const bf16* __res
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     float lsj = (j < 2) ? ls0 : ls1, dlj = (j < 2) ? dl0 : dl1;
-                    float p = (key + (j & 1) < n) ? exp2f(s[nt][j] * SCALE_LOG2 - lsj) : 0.f;
-                    v[j] = p * (dp[nt][j] - dlj) * 0.125f;
+                    float p = ex2_ftz(fmaf(s[nt][j], SCALE_LOG2, -lsj));
+                    v[j] = p * fmaf(dp[nt][j], 0.125f, dlj);
+                }
+                if (kc + 32 > n) {                 // only the last key chunk holds padded keys
+                    if (key >= n) { v[0] = 0.f; v[2] = 0.f; }
+                    if (key + 1 >= n) { v[1] = 0.f; v[3] = 0.f; }
                 }
                 dsa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(v[0], v[1]);
                 dsa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(v[2], v[3]);
@@ -348,10 +374,10 @@ __global__ void __launch_bounds__(NW * 32) attn_bwd_mma_kernel(const bf16* __res
                 float lq0 = sL[q], lq1 = sL[q + 1], dq0 = sDl[q], dq1 = sDl[q + 1];
                 float p[4], v[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < 4; ++j) {      // padded queries: lse = +inf -> p = 0
                     float lsj = (j & 1) ? lq1 : lq0, dlj = (j & 1) ? dq1 : dq0;
-                    p[j] = (q + (j & 1) < n) ? exp2f(s[nt][j] * SCALE_LOG2 - lsj) : 0.f;
-                    v[j] = p[j] * (dp[nt][j] - dlj) * 0.125f;
+                    p[j] = ex2_ftz(fmaf(s[nt][j], SCALE_LOG2, -lsj));
+                    v[j] = p[j] * fmaf(dp[nt][j], 0.125f, dlj);
                 }
                 pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(p[0], p[1]);
                 pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p[2], p[3]);
@@ -386,6 +412,7 @@ __global__ void __launch_bounds__(NW * 32) attn_bwd_mma_kernel(const bf16* __res
             }
         }
     }
+    }   // row-tile passes
 }
 
 // row tiles of 16 are spread over ceil(tiles / 8) CTAs with an equal number of warps each
@@ -422,23 +449,27 @@ static int bwd_launch(const void* qkv, const void* o, const void* d_o, const flo
             return AIMB_ERR_CUDA;
         attr_set = true;
     }
-    launch_k((attn_bwd_mma_kernel<NW>), dim3(frames * heads), dim3(((n + 15) / 16) * 32), smem, s, (const bf16*)qkv, (const bf16*)o, (const bf16*)d_o,
+    const int tiles = (n + 15) / 16;
+    launch_k((attn_bwd_mma_kernel<NW>), dim3(frames * heads), dim3((tiles < NW ? tiles : NW) * 32), smem, s, (const bf16*)qkv, (const bf16*)o, (const bf16*)d_o,
                                                                             lse, (bf16*)d_qkv, n, heads);
     AIMB_CHECK_LAUNCH();
     return AIMB_OK;
 }
 
 // kernels are compiled for the warp counts of the supported token counts (n <= 128: toy sizes, 197 -> 13 warps:
-// ViT-B/16, 257 -> 17 warps: ViT-L/14) so the launch bounds fit the registers.
+// ViT-B/16, 257 -> 9 warps x 2 passes: ViT-L/14) so the launch bounds fit the registers.
 int attn_spatial_bwd_mma(const void* qkv, const void* o, const void* d_o, const float* lse, void* d_qkv, int frames, int n,
                          int heads, cudaStream_t s) {
     int npad = (n + 31) & ~31;
     int nwarps = (n + 15) / 16;
     size_t smem = (size_t)4 * npad * LDS * 2 + (size_t)2 * npad * 4;
-    if (smem > 227 * 1024 || nwarps > 17) return AIMB_ERR_UNSUPPORTED;
+    if (smem > 227 * 1024) return AIMB_ERR_UNSUPPORTED;
     if (nwarps <= 8) return bwd_launch<8>(qkv, o, d_o, lse, d_qkv, frames, n, heads, smem, s);
+    static const int dbg_nw = getenv("AIMB200_ATTN_BWD_NW") ? atoi(getenv("AIMB200_ATTN_BWD_NW")) : 0;   // bench_tools only
+    if (dbg_nw == 7) return bwd_launch<7>(qkv, o, d_o, lse, d_qkv, frames, n, heads, smem, s);
+    if (dbg_nw == 9) return bwd_launch<9>(qkv, o, d_o, lse, d_qkv, frames, n, heads, smem, s);
     if (nwarps <= 13) return bwd_launch<13>(qkv, o, d_o, lse, d_qkv, frames, n, heads, smem, s);
-    return bwd_launch<17>(qkv, o, d_o, lse, d_qkv, frames, n, heads, smem, s);
+    return bwd_launch<9>(qkv, o, d_o, lse, d_qkv, frames, n, heads, smem, s);   // two passes (three beyond n = 288)
 }
 
 }  // namespace aimb

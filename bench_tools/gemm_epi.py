@@ -67,6 +67,8 @@ if len(sys.argv) > 3 and sys.argv[3] == "epi":     # K = 64: mainloop negligible
     cases = [(3072, 64, k) for k in ("none", "bias", "qgelu+pre", "dqgelu", "res1", "res1+res2")] + [(768, 64, k) for k in ("none", "res1", "res1+res2")]
 if len(sys.argv) > 3 and sys.argv[3] == "st":
     cases = [(3072, 768, k) for k in ("bias", "qgelu+pre", "qgelu+alias", "dqgelu")]
+if len(sys.argv) > 3 and sys.argv[3] == "ad":
+    cases = [(192, 768, "gelu+pre"), (192, 768, "dgelu+cs"), (768, 192, "res1"), (768, 192, "res1+res2"), (768, 192, "none"), (768, 768, "res1"), (768, 768, "bias")]
 if len(sys.argv) > 3 and sys.argv[3] == "big":
     cases = [(3072, 768, k) for k in ("bias", "qgelu+pre", "dqgelu")] + [(768, 3072, "res1"), (768, 768, "res1"), (768, 192, "res1"), (768, 192, "res1+res2"), (192, 768, "gelu+pre")]
 for (N, K, kind) in cases:
