@@ -472,4 +472,201 @@ int attn_spatial_bwd_mma(const void* qkv, const void* o, const void* d_o, const 
     return bwd_launch<9>(qkv, o, d_o, lse, d_qkv, frames, n, heads, smem, s);   // two passes (three beyond n = 288)
 }
 
+
+// ------------------------------------------------------------------------------------------ temporal attention, T = 8
+// (vitclip_aim.py:196-200: attention over the 8 frames of one (clip, token), per head.)  One warp owns a PAIR of heads
+// of one (clip, token): 2 x 8 frame rows fill the 16 rows of an m16n8k16 tile.  Q K^T is computed for the full 16 x 16
+// tile and only the two diagonal 8 x 8 blocks are used; P / dS re-enter the tensor core as block-diagonal A operands
+// (C-fragment == A-fragment layout; the transposes needed for dK / dV are one movmatrix each), so P V, dS K, dS^T Q
+// and P^T dO carry no wasted work.  Rows are fetched with 16-byte cp.async (256 contiguous bytes per frame row and
+// tensor) and results leave through a shared-memory tile as 16-byte stores.  ~10x fewer instructions than the SIMT
+// kernel (which ncu showed issue-bound at 837 warp instructions per problem).
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
+    uint32_t d;
+    asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+    return d;
+}
+constexpr int T8_TILE = 16 * LDS;   // bf16 elements of one [16 rows][64 + pad] tile
+
+// rows r = head_local * 8 + frame  <-  global row (row0 + frame * n), columns (h0 + head_local) * 64 ...
+__device__ __forceinline__ void t8_load(bf16* dst, const bf16* src, int64_t frame_stride, int lane) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int e = i * 32 + lane, r = e >> 3, c = (e & 7) * 8;
+        cp_async16(dst + r * LDS + c, src + (int64_t)(r & 7) * frame_stride + (r >> 3) * HD + c);
+    }
+}
+// accumulators [16 rows x 64] -> smem tile -> global, 16 bytes per lane
+__device__ __forceinline__ void t8_store(bf16* tile, bf16* dst, int64_t frame_stride, const float (&acc)[8][4], int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    __syncwarp();
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) {
+        *reinterpret_cast<uint32_t*>(tile + g * LDS + dt * 8 + 2 * t) = pack_bf16(acc[dt][0], acc[dt][1]);
+        *reinterpret_cast<uint32_t*>(tile + (g + 8) * LDS + dt * 8 + 2 * t) = pack_bf16(acc[dt][2], acc[dt][3]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int e = i * 32 + lane, r = e >> 3, c = (e & 7) * 8;
+        *reinterpret_cast<uint4*>(dst + (int64_t)(r & 7) * frame_stride + (r >> 3) * HD + c) = *reinterpret_cast<const uint4*>(tile + r * LDS + c);
+    }
+}
+// softmax over the 8 keys of a row held as 2 values per lane across a quad; returns probabilities
+__device__ __forceinline__ void t8_softmax(float x0, float x1, float& p0, float& p1) {
+    float m = fmaxf(x0, x1);
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    const float e0 = ex2_ftz((x0 - m) * SCALE_LOG2), e1 = ex2_ftz((x1 - m) * SCALE_LOG2);
+    float sum = e0 + e1;
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    const float inv = __fdividef(1.f, sum);
+    p0 = e0 * inv;
+    p1 = e1 * inv;
+}
+// S tile (2 n-tiles of 8 keys) = A[16 x 64] . B[16 keys x 64]^T
+__device__ __forceinline__ void t8_scores(float (&s)[2][4], const uint32_t (&a)[4][4], const bf16* sB, int lane) {
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[nt][j] = 0.f;
+#pragma unroll
+        for (int kp = 0; kp < 2; ++kp) {
+            uint32_t b[4];
+            ldb_frag_nk(b, sB + (nt * 8) * LDS + kp * 32, lane);
+            mma16816(s[nt], a[2 * kp], b[0], b[1]);
+            mma16816(s[nt], a[2 * kp + 1], b[2], b[3]);
+        }
+    }
+}
+// acc[16 x 64] = Ablockdiag[16 x 16] . B[16 rows x 64]
+__device__ __forceinline__ void t8_apply(float (&acc)[8][4], const uint32_t (&a)[4], const bf16* sB, int lane) {
+#pragma unroll
+    for (int dp = 0; dp < 4; ++dp) {
+        uint32_t b[4];
+        ldb_frag_kn(b, sB + dp * 16, lane);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[2 * dp][j] = 0.f; acc[2 * dp + 1][j] = 0.f; }
+        mma16816(acc[2 * dp], a, b[0], b[1]);
+        mma16816(acc[2 * dp + 1], a, b[2], b[3]);
+    }
+}
+
+__global__ void __launch_bounds__(128) attn_temporal8_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o, int B,
+                                                                     int n, int heads) {
+    pdl_grid_sync();
+    extern __shared__ __align__(16) uint8_t smraw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int hp = heads >> 1;
+    const int64_t pair = (int64_t)blockIdx.x * 4 + warp;
+    if (pair >= (int64_t)B * n * hp) return;
+    const int h0 = 2 * (int)(pair % hp);
+    const int tok = (int)((pair / hp) % n);
+    const int b = (int)(pair / ((int64_t)hp * n));
+    const int D = heads * HD, ld = 3 * D;
+    bf16* sQ = reinterpret_cast<bf16*>(smraw) + warp * 3 * T8_TILE;
+    bf16* sK = sQ + T8_TILE;
+    bf16* sV = sK + T8_TILE;
+    const int64_t row0 = (int64_t)b * 8 * n + tok;
+    const bf16* base = qkv + row0 * ld + h0 * HD;
+    const int64_t fs = (int64_t)n * ld;
+    t8_load(sQ, base, fs, lane);
+    t8_load(sK, base + D, fs, lane);
+    t8_load(sV, base + 2 * D, fs, lane);
+    cp_async_wait_all();
+    __syncwarp();
+    uint32_t qa[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) lda_frag(qa[ks], sQ + ks * 16, lane);
+    float s[2][4];
+    t8_scores(s, qa, sK, lane);
+    float pa0, pa1, pb0, pb1;
+    t8_softmax(s[0][0], s[0][1], pa0, pa1);     // head h0,     query frame g
+    t8_softmax(s[1][2], s[1][3], pb0, pb1);     // head h0 + 1, query frame g
+    const uint32_t pa[4] = {pack_bf16(pa0, pa1), 0u, 0u, pack_bf16(pb0, pb1)};
+    float oacc[8][4];
+    t8_apply(oacc, pa, sV, lane);
+    t8_store(sQ, o + row0 * D + h0 * HD, (int64_t)n * D, oacc, lane);
+}
+
+__global__ void __launch_bounds__(128) attn_temporal8_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o,
+                                                                     bf16* __restrict__ d_qkv, int B, int n, int heads) {
+    pdl_grid_sync();
+    extern __shared__ __align__(16) uint8_t smraw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int hp = heads >> 1;
+    const int64_t pair = (int64_t)blockIdx.x * 4 + warp;
+    if (pair >= (int64_t)B * n * hp) return;
+    const int h0 = 2 * (int)(pair % hp);
+    const int tok = (int)((pair / hp) % n);
+    const int b = (int)(pair / ((int64_t)hp * n));
+    const int D = heads * HD, ld = 3 * D;
+    bf16* sQ = reinterpret_cast<bf16*>(smraw) + warp * 4 * T8_TILE;
+    bf16* sK = sQ + T8_TILE;
+    bf16* sV = sK + T8_TILE;
+    bf16* sG = sV + T8_TILE;
+    const int64_t row0 = (int64_t)b * 8 * n + tok;
+    const bf16* base = qkv + row0 * ld + h0 * HD;
+    const int64_t fs = (int64_t)n * ld;
+    t8_load(sQ, base, fs, lane);
+    t8_load(sK, base + D, fs, lane);
+    t8_load(sV, base + 2 * D, fs, lane);
+    t8_load(sG, d_o + row0 * D + h0 * HD, (int64_t)n * D, lane);
+    cp_async_wait_all();
+    __syncwarp();
+    uint32_t a[4][4];
+    float s[2][4], dp[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) lda_frag(a[ks], sQ + ks * 16, lane);
+    t8_scores(s, a, sK, lane);                   // S  = Q K^T
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) lda_frag(a[ks], sG + ks * 16, lane);
+    t8_scores(dp, a, sV, lane);                  // dP = dO V^T
+    float pa0, pa1, pb0, pb1;
+    t8_softmax(s[0][0], s[0][1], pa0, pa1);
+    t8_softmax(s[1][2], s[1][3], pb0, pb1);
+    float da = pa0 * dp[0][0] + pa1 * dp[0][1], db = pb0 * dp[1][2] + pb1 * dp[1][3];   // delta = sum_j P_ij dP_ij
+    da += __shfl_xor_sync(0xffffffffu, da, 1);
+    da += __shfl_xor_sync(0xffffffffu, da, 2);
+    db += __shfl_xor_sync(0xffffffffu, db, 1);
+    db += __shfl_xor_sync(0xffffffffu, db, 2);
+    const uint32_t p_a = pack_bf16(pa0, pa1), p_b = pack_bf16(pb0, pb1);
+    const uint32_t ds_a = pack_bf16(pa0 * (dp[0][0] - da) * 0.125f, pa1 * (dp[0][1] - da) * 0.125f);
+    const uint32_t ds_b = pack_bf16(pb0 * (dp[1][2] - db) * 0.125f, pb1 * (dp[1][3] - db) * 0.125f);
+    bf16* dbase = d_qkv + row0 * ld + h0 * HD;
+    float acc[8][4];
+    {
+        const uint32_t ds[4] = {ds_a, 0u, 0u, ds_b};
+        t8_apply(acc, ds, sK, lane);             // dQ = dS K        (sV is free after dP: staging tile)
+        t8_store(sV, dbase, fs, acc, lane);
+    }
+    {
+        const uint32_t dst[4] = {movmatrix_trans(ds_a), 0u, 0u, movmatrix_trans(ds_b)};
+        t8_apply(acc, dst, sQ, lane);            // dK = dS^T Q
+        t8_store(sV, dbase + D, fs, acc, lane);
+    }
+    {
+        const uint32_t pt[4] = {movmatrix_trans(p_a), 0u, 0u, movmatrix_trans(p_b)};
+        t8_apply(acc, pt, sG, lane);             // dV = P^T dO
+        t8_store(sV, dbase + 2 * D, fs, acc, lane);
+    }
+}
+
+int attn_temporal8_fwd_mma(const void* qkv, void* o, int B, int n, int heads, cudaStream_t s) {
+    const int64_t pairs = (int64_t)B * n * (heads / 2);
+    const size_t smem = (size_t)4 * 3 * T8_TILE * 2;
+    launch_k(attn_temporal8_fwd_mma_kernel, dim3((unsigned)((pairs + 3) / 4)), dim3(128), smem, s, (const bf16*)qkv, (bf16*)o, B, n, heads);
+    AIMB_CHECK_LAUNCH();
+    return AIMB_OK;
+}
+int attn_temporal8_bwd_mma(const void* qkv, const void* d_o, void* d_qkv, int B, int n, int heads, cudaStream_t s) {
+    const int64_t pairs = (int64_t)B * n * (heads / 2);
+    const size_t smem = (size_t)4 * 4 * T8_TILE * 2;
+    launch_k(attn_temporal8_bwd_mma_kernel, dim3((unsigned)((pairs + 3) / 4)), dim3(128), smem, s, (const bf16*)qkv, (const bf16*)d_o,
+             (bf16*)d_qkv, B, n, heads);
+    AIMB_CHECK_LAUNCH();
+    return AIMB_OK;
+}
+
 }  // namespace aimb

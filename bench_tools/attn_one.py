@@ -35,3 +35,24 @@ for name, fn in (("fwd", lambda: lib.attn_spatial_fwd(qkv, o, lse, frames, n, he
     ts.sort()
     flops = (4 if name == "fwd" else 10) * frames * heads * n * n * 64
     print(f"attn_spatial_{name} frames={frames} n={n} heads={heads}: {ts[2]:.1f} us  {flops / ts[2] / 1e6:.1f} TFLOP/s (algorithmic)")
+
+# temporal attention at the same shape: B clips x T = 8 frames
+B, T = frames // 8, 8
+qkv_t = (torch.randn(B * T * n, 3 * D, device=dev) * 0.5).bfloat16()
+o_t = torch.empty(B * T * n, D, device=dev, dtype=torch.bfloat16)
+d_qkv_t = torch.empty_like(qkv_t)
+for name, fn, nbytes in (("fwd", lambda: lib.attn_temporal_fwd(qkv_t, o_t, B, T, n, heads), qkv_t.numel() * 2 + o_t.numel() * 2),
+                         ("bwd", lambda: lib.attn_temporal_bwd(qkv_t, d_o, d_qkv_t, B, T, n, heads), 2 * qkv_t.numel() * 2 + o_t.numel() * 2)):
+    for _ in range(2):
+        fn()
+    ts = []
+    for _ in range(5):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e) * 1e3)
+    ts.sort()
+    print(f"attn_temporal_{name} B={B} T={T} n={n} heads={heads}: {ts[2]:.1f} us  {nbytes / ts[2] / 1e3:.0f} GB/s (algorithmic bytes)")
