@@ -65,6 +65,11 @@ class Engine:
         self.attn_impl = lib.IMPL_AUTO
         self.gemm_impl = lib.IMPL_AUTO
         self.fuse_adapters = os.environ.get("AIMB200_FUSE_ADAPTERS", "0") == "1"   # opt-in: measured on par at M = 12608
+        # adapter weight-gradient kernels are off the critical path of backward: they run on a side stream (captured
+        # into the step graph as parallel branches) and fill the SMs the small dgrad GEMMs / kernel tails leave idle
+        self.wgrad_side = os.environ.get("AIMB200_WGRAD_STREAM", "1") == "1"
+        self._side = None
+        self._side_busy = False
 
     # ------------------------------------------------------------------ buffers (stable pointers across steps)
     def buf(self, name, shape, dtype=None, key=None):
@@ -75,6 +80,25 @@ class Engine:
             t = torch.empty(shape, dtype=dtype, device=self.device)
             self._bufs[k] = t
         return t
+
+    # ------------------------------------------------------------------ side stream for the weight-gradient kernels
+    def _side_begin(self):
+        """side stream, ordered after everything issued so far on the current stream"""
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._side.wait_event(ev)
+        self._side_busy = True
+        return self._side
+
+    def _join_side(self):
+        """the current stream waits for the side stream: call before anything overwrites a buffer a wgrad reads"""
+        if self._side_busy:
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            self._side_busy = False
 
     def release(self):
         self._bufs.clear()
@@ -350,15 +374,23 @@ class Engine:
             on_block_done(-1)
         self.saved = None
 
-    def _adapter_bwd(self, name, pre, dy, a, h, g, W, WT, grads, d, rs, alpha, d_a_out, d_a_res, db2_fused=False):
+    def _adapter_bwd(self, name, pre, dy, a, h, g, W, WT, grads, d, rs, alpha, d_a_out, d_a_res, db2_fused=False,
+                     lazy_join=False):
         """y = alpha * rs * (fc2(gelu(fc1(a)))).  Given dy: adapter weight/bias grads, and
         d_a_out = d_a_res + d(a) (d_a_res may be None).  db2_fused: the fc2 bias gradient (a weighted column sum
-        of dy) was already produced by the kernel that wrote dy."""
+        of dy) was already produced by the kernel that wrote dy.  lazy_join: the caller calls _join_side() itself
+        before `dy` (or `a`, `g`) is overwritten, so the two wgrad kernels may overlap the kernels that follow."""
         M, r, D = dy.shape[0], d.r, d.D
         k1w, k1b = pre + name + ".D_fc1.weight", pre + name + ".D_fc1.bias"
         k2w, k2b = pre + name + ".D_fc2.weight", pre + name + ".D_fc2.bias"
         # fc2: g' = rs*gelu(h) was stored, so dW2 = alpha * dy^T g' ; db2 = alpha * sum_m rs[m] dy[m]
-        lib.gemm_wgrad(dy, g, grads[k2w], alpha=alpha)
+        self._join_side()              # the previous adapter's fc1 wgrad still reads the shared d_h scratch
+        side = self.wgrad_side and not (self.fuse_adapters and lib.adapter_fused_supported(dy, r, D))
+        if side:
+            with torch.cuda.stream(self._side_begin()):
+                lib.gemm_wgrad(dy, g, grads[k2w], alpha=alpha)
+        else:
+            lib.gemm_wgrad(dy, g, grads[k2w], alpha=alpha)
         if not db2_fused:
             lib.colsum(dy, grads[k2b], row_scale=rs, alpha=alpha)
         # d_h = rs * alpha * (dy W2) * gelu'(h) ; db1 = column sums of d_h, taken in the same epilogue
@@ -367,10 +399,17 @@ class Engine:
         epi2 = dict(res1=d_a_res)
         if self.fuse_adapters and self.gemm_impl == lib.IMPL_AUTO and lib.adapter_fused_supported(dy, r, D):
             lib.adapter_fused(dy, WT[k2w], WT[k1w], d_h, d_a_out, epi1, epi2)
-        else:
-            self.gemm(dy, WT[k2w], d_h, **epi1)
-            self.gemm(d_h, WT[k1w], d_a_out, **epi2)
-        lib.gemm_wgrad(d_h, a, grads[k1w])
+            lib.gemm_wgrad(d_h, a, grads[k1w])
+            return d_a_out
+        self.gemm(dy, WT[k2w], d_h, **epi1)
+        if side:
+            with torch.cuda.stream(self._side_begin()):      # ordered after the d_h GEMM, concurrent with the d_a GEMM
+                lib.gemm_wgrad(d_h, a, grads[k1w])
+        self.gemm(d_h, WT[k1w], d_a_out, **epi2)
+        if not side:
+            lib.gemm_wgrad(d_h, a, grads[k1w])
+        elif not lazy_join:
+            self._join_side()
         return d_a_out
 
     def _block_bwd(self, i, dx, W, WT, grads, d, S, prev_mask_m=None):
@@ -385,7 +424,7 @@ class Engine:
         # ---------------- spatial: x2 = x1 + a_s + S_Adapter_noskip(a_s)
         d_as = self.buf("d_a", (M, D))
         self._adapter_bwd("S_Adapter", pre, dx2, S["a_s"], S["h_s"], S["g_s"], W, WT, grads, d, None, 1.0, d_as, dx2,
-                          db2_fused=True)
+                          db2_fused=True, lazy_join=True)
         d_os = self.buf("d_o", (M, D))
         self.gemm(d_as, WT[pre + "attn.out_proj.weight"], d_os)
         d_qkv = self.buf("d_qkv", (M, 3 * D))
@@ -394,12 +433,13 @@ class Engine:
         self.gemm(d_qkv, WT[pre + "attn.in_proj_weight"], d_xn1)
         m2, r2 = S["ln1s"]
         dx1 = dx
+        self._join_side()              # S_Adapter's fc2 wgrad reads dx2, which this LN backward rewrites in place
         lib.layernorm_bwd(d_xn1, S["x1"], m2, r2, W[pre + "ln_1.weight"], dx2, dx1,
                           colsum_out=grads[pre + "T_Adapter.D_fc2.bias"], colsum_row_scale=mask_t)
         # ---------------- temporal: x1 = x + mask_t * T_Adapter(attn(ln_1(x)))
         d_at = self.buf("d_a", (M, D))
         self._adapter_bwd("T_Adapter", pre, dx1, S["a_t"], S["h_t"], S["g_t"], W, WT, grads, d, mask_t, 1.0, d_at, None,
-                          db2_fused=True)
+                          db2_fused=True, lazy_join=True)
         d_ot = self.buf("d_o", (M, D))
         self.gemm(d_at, WT[pre + "attn.out_proj.weight"], d_ot)
         lib.attn_temporal_bwd(S["qkv_t"], d_ot, d_qkv, d.B, d.T, n, d.heads)
@@ -414,6 +454,7 @@ class Engine:
         else:
             self.gemm(d_qkv, WT[pre + "attn.in_proj_weight"], d_xn1t)
         m1, r1 = S["ln1t"]
+        self._join_side()              # T_Adapter's fc2 wgrad reads dx1 == dx, rewritten below; block grads complete
         if i > 0:   # dx is the output gradient of block i-1: its MLP-adapter fc2 bias grad = scale * sum_m mask_m[m] dx[m]
             lib.layernorm_bwd(d_xn1t, S["x"], m1, r1, W[pre + "ln_1.weight"], dx1, dx,
                               colsum_out=grads[f"transformer.resblocks.{i - 1}.MLP_Adapter.D_fc2.bias"],
