@@ -105,6 +105,10 @@ class ViT_CLIP(nn.Module):
         if block == "fork" and num_tadapter != 1:
             raise ValueError("num_tadapter==2 is only defined for block='aim' (the in-tree fork has no T_Adapter_in)")
         if shift:
+            # The reference's own shift branch cannot run: it reshapes xln[2:] (n - 2 = G*G - 1 tokens) to an h x w grid
+            # with h = w = int(sqrt(n - 2)) and einops raises for every resolution (checked against the reference at
+            # 224 and 64, tests/test_boundary.py::test_shift_true_raises_in_reference_too).  Every in-tree config has
+            # shift=False, so there is no behaviour to reproduce.
             raise NotImplementedError("shift=True (PatchShift, vit_clip.py:15-49,233-254) is outside the built path")
         if width % heads or width // heads != 64:
             raise ValueError("head_dim must be 64 (CLIP ViT-B/16, ViT-L/14)")

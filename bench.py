@@ -352,7 +352,7 @@ def run_ours(args):
     tp = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
     if os.path.isfile(tp):      # dram__bytes_read+write per GEMM launch from the committed ncu --set full capture
         traffic = json.load(open(tp)).get("avg_dram_bytes_per_launch")
-    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (TMA + tcgen05/TMEM bf16 GEMM)", "achieved": achieved,
+    roofline = {"bound": "tensor", "kernel": "gemm_tc4_kernel / gemm_tc_kernel (TMA + tcgen05/TMEM bf16 GEMM, fused epilogues)", "achieved": achieved,
                 "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic, "peak_source": peak_src,
                 "launches_per_step": len(recs) // nprof, "avg_launch_us": gemm_ms * 1e3 / max(1, len(recs)),
                 "share_of_step": gemm_ms / prof_ms,

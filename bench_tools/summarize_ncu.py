@@ -51,5 +51,28 @@ def full(path):
         print(f"| `{name}` | " + " | ".join(f"{r[ix[c]]} {units[ix[c]]}" for c in cols) + " |")
 
 
+def traffic(path):
+    """JSON consumed by bench.py's roofline.traffic: DRAM bytes (read + write) per GEMM launch of the capture."""
+    import json
+    out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    ix = {h: i for i, h in enumerate(hdr)}
+
+    def mb(r, k):
+        v = float(r[ix[k]].replace(',', ''))
+        u = units[ix[k]].lower()
+        return v * {'byte': 1e-6, 'kbyte': 1e-3, 'mbyte': 1.0, 'gbyte': 1e3}[u]
+
+    launches = []
+    for r in data:
+        name = re.sub(r'\(.*', '', r[ix['Kernel Name']]).replace('aimb::', '')
+        launches.append({"kernel": name, "dram_read_MB": mb(r, 'dram__bytes_read.sum'), "dram_write_MB": mb(r, 'dram__bytes_write.sum'),
+                         "time_us": float(r[ix['gpu__time_duration.sum']].replace(',', '')),
+                         "tensor_pipe_active_pct": float(r[ix['sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active']])})
+    avg = sum((l["dram_read_MB"] + l["dram_write_MB"]) * 1e6 for l in launches) / max(1, len(launches))
+    print(json.dumps({"source": " ".join(sys.argv[3:]) or path, "avg_dram_bytes_per_launch": avg, "launches": launches}, indent=1))
+
+
 if __name__ == "__main__":
-    {"list": launch_list, "full": full}[sys.argv[1]](sys.argv[2])
+    {"list": launch_list, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])

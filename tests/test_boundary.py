@@ -90,3 +90,20 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(so, sym), f"{sym} declared in include/aimb200.h but not exported"
     assert declared - {"aimb_last_error"} <= set(lib.SIGNATURES), "lib.py must bind every declared entry point"
     assert so.aimb_version() >= 100
+
+
+def test_shift_true_raises_in_reference_too():
+    """the reference's shift=True forward raises (xln[2:] has n-2 = G*G-1 tokens, never a square), so
+    the drop-in raising NotImplementedError at construction loses no behaviour.  Runs only where /root/reference is."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference tree not present (GPU box)")
+    import torch
+    m = ref_loader.load("vit_clip.py")
+    net = m.ViT_CLIP(input_resolution=64, num_frames=4, patch_size=16, width=128, layers=1, heads=2, drop_path_rate=0.0,
+                     shift=True, pretrained=None)
+    with pytest.raises(Exception) as ei, torch.no_grad():
+        net(torch.randn(1, 3, 4, 64, 64))
+    assert "rearrange" in str(ei.value) or "Shape mismatch" in str(ei.value)
