@@ -473,31 +473,37 @@ int attn_spatial_bwd_mma(const void* qkv, const void* o, const void* d_o, const 
 }
 
 
-// ------------------------------------------------------------------------------------------ temporal attention, T = 8
-// (vitclip_aim.py:196-200: attention over the 8 frames of one (clip, token), per head.)  One warp owns a PAIR of heads
-// of one (clip, token): 2 x 8 frame rows fill the 16 rows of an m16n8k16 tile.  Q K^T is computed for the full 16 x 16
-// tile and only the two diagonal 8 x 8 blocks are used; P / dS re-enter the tensor core as block-diagonal A operands
-// (C-fragment == A-fragment layout; the transposes needed for dK / dV are one movmatrix each), so P V, dS K, dS^T Q
-// and P^T dO carry no wasted work.  Rows are fetched with 16-byte cp.async (256 contiguous bytes per frame row and
-// tensor) and results leave through a shared-memory tile as 16-byte stores.  ~10x fewer instructions than the SIMT
-// kernel (which ncu showed issue-bound at 837 warp instructions per problem).
+// ------------------------------------------------------------------------------------------ temporal attention, T = 8 / 16
+// (vitclip_aim.py:196-200: attention over the T frames of one (clip, token), per head.)  The 16 rows of an m16n8k16
+// tile are either the 8 frames of a PAIR of heads (T = 8: Q K^T is computed for the full 16 x 16 tile, only the two
+// diagonal 8 x 8 blocks are used, P / dS re-enter the tensor core as block-diagonal A operands) or the 16 frames of one
+// head (T = 16).  C-fragment == A-fragment layout, so P and dS need no shuffles; the transposes for dK / dV are one
+// movmatrix per 8 x 8 block.  Rows are fetched in place (stride n rows) with 16-byte cp.async and results leave through
+// a shared-memory tile as 16-byte stores.  ~10x fewer instructions than the SIMT kernel (which ncu showed issue-bound
+// at 837 warp instructions per problem).
 __device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
     uint32_t d;
     asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
     return d;
 }
-constexpr int T8_TILE = 16 * LDS;   // bf16 elements of one [16 rows][64 + pad] tile
+constexpr int TT_TILE = 16 * LDS;   // bf16 elements of one [16 rows][64 + pad] tile
 
-// rows r = head_local * 8 + frame  <-  global row (row0 + frame * n), columns (h0 + head_local) * 64 ...
-__device__ __forceinline__ void t8_load(bf16* dst, const bf16* src, int64_t frame_stride, int lane) {
+// tile row r  <->  PAIR: frame r & 7 of head h0 + (r >> 3);  else: frame r of head h0
+template <bool PAIR>
+__device__ __forceinline__ int64_t tt_goff(int r, int64_t frame_stride) {
+    return PAIR ? (int64_t)(r & 7) * frame_stride + (r >> 3) * HD : (int64_t)r * frame_stride;
+}
+template <bool PAIR>
+__device__ __forceinline__ void tt_load(bf16* dst, const bf16* src, int64_t frame_stride, int lane) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int e = i * 32 + lane, r = e >> 3, c = (e & 7) * 8;
-        cp_async16(dst + r * LDS + c, src + (int64_t)(r & 7) * frame_stride + (r >> 3) * HD + c);
+        cp_async16(dst + r * LDS + c, src + tt_goff<PAIR>(r, frame_stride) + c);
     }
 }
 // accumulators [16 rows x 64] -> smem tile -> global, 16 bytes per lane
-__device__ __forceinline__ void t8_store(bf16* tile, bf16* dst, int64_t frame_stride, const float (&acc)[8][4], int lane) {
+template <bool PAIR>
+__device__ __forceinline__ void tt_store(bf16* tile, bf16* dst, int64_t frame_stride, const float (&acc)[8][4], int lane) {
     const int g = lane >> 2, t = lane & 3;
     __syncwarp();
 #pragma unroll
@@ -509,24 +515,46 @@ __device__ __forceinline__ void t8_store(bf16* tile, bf16* dst, int64_t frame_st
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int e = i * 32 + lane, r = e >> 3, c = (e & 7) * 8;
-        *reinterpret_cast<uint4*>(dst + (int64_t)(r & 7) * frame_stride + (r >> 3) * HD + c) = *reinterpret_cast<const uint4*>(tile + r * LDS + c);
+        *reinterpret_cast<uint4*>(dst + tt_goff<PAIR>(r, frame_stride) + c) = *reinterpret_cast<const uint4*>(tile + r * LDS + c);
     }
 }
-// softmax over the 8 keys of a row held as 2 values per lane across a quad; returns probabilities
-__device__ __forceinline__ void t8_softmax(float x0, float x1, float& p0, float& p1) {
-    float m = fmaxf(x0, x1);
+// softmax of one row held as 4 values per lane across a quad (-inf entries = masked)
+__device__ __forceinline__ void tt_softmax(const float (&x)[4], float (&p)[4]) {
+    float m = fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3]));
     m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
     m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-    const float e0 = ex2_ftz((x0 - m) * SCALE_LOG2), e1 = ex2_ftz((x1 - m) * SCALE_LOG2);
-    float sum = e0 + e1;
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { p[j] = ex2_ftz((x[j] - m) * SCALE_LOG2); sum += p[j]; }
     sum += __shfl_xor_sync(0xffffffffu, sum, 1);
     sum += __shfl_xor_sync(0xffffffffu, sum, 2);
     const float inv = __fdividef(1.f, sum);
-    p0 = e0 * inv;
-    p1 = e1 * inv;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) p[j] *= inv;
+}
+// rows g (pa) and g + 8 (pb) of the 16 x 16 score tile -> probabilities; PAIR masks the off-diagonal blocks
+template <bool PAIR>
+__device__ __forceinline__ void tt_probs(const float (&s)[2][4], float (&pa)[4], float (&pb)[4]) {
+    const float xa[4] = {s[0][0], s[0][1], PAIR ? -INFINITY : s[1][0], PAIR ? -INFINITY : s[1][1]};
+    const float xb[4] = {PAIR ? -INFINITY : s[0][2], PAIR ? -INFINITY : s[0][3], s[1][2], s[1][3]};
+    tt_softmax(xa, pa);
+    tt_softmax(xb, pb);
+}
+// values of rows g / g + 8 -> A fragment of the 16 x 16 matrix, and of its transpose
+__device__ __forceinline__ void tt_afrag(const float (&ra)[4], const float (&rb)[4], uint32_t (&a)[4]) {
+    a[0] = pack_bf16(ra[0], ra[1]);   // (row g,     k 0-7)
+    a[1] = pack_bf16(rb[0], rb[1]);   // (row g + 8, k 0-7)
+    a[2] = pack_bf16(ra[2], ra[3]);   // (row g,     k 8-15)
+    a[3] = pack_bf16(rb[2], rb[3]);   // (row g + 8, k 8-15)
+}
+__device__ __forceinline__ void tt_afrag_t(const uint32_t (&a)[4], uint32_t (&at)[4]) {
+    at[0] = movmatrix_trans(a[0]);
+    at[1] = movmatrix_trans(a[2]);
+    at[2] = movmatrix_trans(a[1]);
+    at[3] = movmatrix_trans(a[3]);
 }
 // S tile (2 n-tiles of 8 keys) = A[16 x 64] . B[16 keys x 64]^T
-__device__ __forceinline__ void t8_scores(float (&s)[2][4], const uint32_t (&a)[4][4], const bf16* sB, int lane) {
+__device__ __forceinline__ void tt_scores(float (&s)[2][4], const uint32_t (&a)[4][4], const bf16* sB, int lane) {
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt) {
 #pragma unroll
@@ -540,8 +568,8 @@ __device__ __forceinline__ void t8_scores(float (&s)[2][4], const uint32_t (&a)[
         }
     }
 }
-// acc[16 x 64] = Ablockdiag[16 x 16] . B[16 rows x 64]
-__device__ __forceinline__ void t8_apply(float (&acc)[8][4], const uint32_t (&a)[4], const bf16* sB, int lane) {
+// acc[16 x 64] = A[16 x 16] . B[16 rows x 64]
+__device__ __forceinline__ void tt_apply(float (&acc)[8][4], const uint32_t (&a)[4], const bf16* sB, int lane) {
 #pragma unroll
     for (int dp = 0; dp < 4; ++dp) {
         uint32_t b[4];
@@ -552,119 +580,133 @@ __device__ __forceinline__ void t8_apply(float (&acc)[8][4], const uint32_t (&a)
         mma16816(acc[2 * dp + 1], a, b[2], b[3]);
     }
 }
+// which (clip, token, head) does this warp own
+template <bool PAIR>
+__device__ __forceinline__ bool tt_problem(int warp, int B, int n, int heads, int& h0, int64_t& row0) {
+    constexpr int T_ = PAIR ? 8 : 16;
+    const int hp = PAIR ? heads >> 1 : heads;
+    const int64_t idx = (int64_t)blockIdx.x * 4 + warp;
+    if (idx >= (int64_t)B * n * hp) return false;
+    h0 = (PAIR ? 2 : 1) * (int)(idx % hp);
+    const int tok = (int)((idx / hp) % n);
+    const int b = (int)(idx / ((int64_t)hp * n));
+    row0 = (int64_t)b * T_ * n + tok;
+    return true;
+}
 
-__global__ void __launch_bounds__(128) attn_temporal8_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o, int B,
-                                                                     int n, int heads) {
+template <bool PAIR>
+__global__ void __launch_bounds__(128) attn_temporal_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o, int B,
+                                                                    int n, int heads) {
     pdl_grid_sync();
     extern __shared__ __align__(16) uint8_t smraw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int hp = heads >> 1;
-    const int64_t pair = (int64_t)blockIdx.x * 4 + warp;
-    if (pair >= (int64_t)B * n * hp) return;
-    const int h0 = 2 * (int)(pair % hp);
-    const int tok = (int)((pair / hp) % n);
-    const int b = (int)(pair / ((int64_t)hp * n));
+    int h0;
+    int64_t row0;
+    if (!tt_problem<PAIR>(warp, B, n, heads, h0, row0)) return;
     const int D = heads * HD, ld = 3 * D;
-    bf16* sQ = reinterpret_cast<bf16*>(smraw) + warp * 3 * T8_TILE;
-    bf16* sK = sQ + T8_TILE;
-    bf16* sV = sK + T8_TILE;
-    const int64_t row0 = (int64_t)b * 8 * n + tok;
+    bf16* sQ = reinterpret_cast<bf16*>(smraw) + warp * 3 * TT_TILE;
+    bf16* sK = sQ + TT_TILE;
+    bf16* sV = sK + TT_TILE;
     const bf16* base = qkv + row0 * ld + h0 * HD;
     const int64_t fs = (int64_t)n * ld;
-    t8_load(sQ, base, fs, lane);
-    t8_load(sK, base + D, fs, lane);
-    t8_load(sV, base + 2 * D, fs, lane);
+    tt_load<PAIR>(sQ, base, fs, lane);
+    tt_load<PAIR>(sK, base + D, fs, lane);
+    tt_load<PAIR>(sV, base + 2 * D, fs, lane);
     cp_async_wait_all();
     __syncwarp();
     uint32_t qa[4][4];
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) lda_frag(qa[ks], sQ + ks * 16, lane);
     float s[2][4];
-    t8_scores(s, qa, sK, lane);
-    float pa0, pa1, pb0, pb1;
-    t8_softmax(s[0][0], s[0][1], pa0, pa1);     // head h0,     query frame g
-    t8_softmax(s[1][2], s[1][3], pb0, pb1);     // head h0 + 1, query frame g
-    const uint32_t pa[4] = {pack_bf16(pa0, pa1), 0u, 0u, pack_bf16(pb0, pb1)};
+    tt_scores(s, qa, sK, lane);
+    float pa[4], pb[4];
+    tt_probs<PAIR>(s, pa, pb);
+    uint32_t pf[4];
+    tt_afrag(pa, pb, pf);
     float oacc[8][4];
-    t8_apply(oacc, pa, sV, lane);
-    t8_store(sQ, o + row0 * D + h0 * HD, (int64_t)n * D, oacc, lane);
+    tt_apply(oacc, pf, sV, lane);
+    tt_store<PAIR>(sQ, o + row0 * D + h0 * HD, (int64_t)n * D, oacc, lane);
 }
 
-__global__ void __launch_bounds__(128) attn_temporal8_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o,
-                                                                     bf16* __restrict__ d_qkv, int B, int n, int heads) {
+template <bool PAIR>
+__global__ void __launch_bounds__(128) attn_temporal_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o,
+                                                                    bf16* __restrict__ d_qkv, int B, int n, int heads) {
     pdl_grid_sync();
     extern __shared__ __align__(16) uint8_t smraw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int hp = heads >> 1;
-    const int64_t pair = (int64_t)blockIdx.x * 4 + warp;
-    if (pair >= (int64_t)B * n * hp) return;
-    const int h0 = 2 * (int)(pair % hp);
-    const int tok = (int)((pair / hp) % n);
-    const int b = (int)(pair / ((int64_t)hp * n));
+    int h0;
+    int64_t row0;
+    if (!tt_problem<PAIR>(warp, B, n, heads, h0, row0)) return;
     const int D = heads * HD, ld = 3 * D;
-    bf16* sQ = reinterpret_cast<bf16*>(smraw) + warp * 4 * T8_TILE;
-    bf16* sK = sQ + T8_TILE;
-    bf16* sV = sK + T8_TILE;
-    bf16* sG = sV + T8_TILE;
-    const int64_t row0 = (int64_t)b * 8 * n + tok;
+    bf16* sQ = reinterpret_cast<bf16*>(smraw) + warp * 4 * TT_TILE;
+    bf16* sK = sQ + TT_TILE;
+    bf16* sV = sK + TT_TILE;
+    bf16* sG = sV + TT_TILE;
     const bf16* base = qkv + row0 * ld + h0 * HD;
     const int64_t fs = (int64_t)n * ld;
-    t8_load(sQ, base, fs, lane);
-    t8_load(sK, base + D, fs, lane);
-    t8_load(sV, base + 2 * D, fs, lane);
-    t8_load(sG, d_o + row0 * D + h0 * HD, (int64_t)n * D, lane);
+    tt_load<PAIR>(sQ, base, fs, lane);
+    tt_load<PAIR>(sK, base + D, fs, lane);
+    tt_load<PAIR>(sV, base + 2 * D, fs, lane);
+    tt_load<PAIR>(sG, d_o + row0 * D + h0 * HD, (int64_t)n * D, lane);
     cp_async_wait_all();
     __syncwarp();
     uint32_t a[4][4];
     float s[2][4], dp[2][4];
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) lda_frag(a[ks], sQ + ks * 16, lane);
-    t8_scores(s, a, sK, lane);                   // S  = Q K^T
+    tt_scores(s, a, sK, lane);                   // S  = Q K^T
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) lda_frag(a[ks], sG + ks * 16, lane);
-    t8_scores(dp, a, sV, lane);                  // dP = dO V^T
-    float pa0, pa1, pb0, pb1;
-    t8_softmax(s[0][0], s[0][1], pa0, pa1);
-    t8_softmax(s[1][2], s[1][3], pb0, pb1);
-    float da = pa0 * dp[0][0] + pa1 * dp[0][1], db = pb0 * dp[1][2] + pb1 * dp[1][3];   // delta = sum_j P_ij dP_ij
+    tt_scores(dp, a, sV, lane);                  // dP = dO V^T
+    float pa[4], pb[4];
+    tt_probs<PAIR>(s, pa, pb);
+    const float dpa[4] = {dp[0][0], dp[0][1], dp[1][0], dp[1][1]}, dpb[4] = {dp[0][2], dp[0][3], dp[1][2], dp[1][3]};
+    float da = 0.f, db = 0.f;                    // delta = sum_j P_ij dP_ij (masked entries have P = 0)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { da = fmaf(pa[j], dpa[j], da); db = fmaf(pb[j], dpb[j], db); }
     da += __shfl_xor_sync(0xffffffffu, da, 1);
     da += __shfl_xor_sync(0xffffffffu, da, 2);
     db += __shfl_xor_sync(0xffffffffu, db, 1);
     db += __shfl_xor_sync(0xffffffffu, db, 2);
-    const uint32_t p_a = pack_bf16(pa0, pa1), p_b = pack_bf16(pb0, pb1);
-    const uint32_t ds_a = pack_bf16(pa0 * (dp[0][0] - da) * 0.125f, pa1 * (dp[0][1] - da) * 0.125f);
-    const uint32_t ds_b = pack_bf16(pb0 * (dp[1][2] - db) * 0.125f, pb1 * (dp[1][3] - db) * 0.125f);
+    float dsa[4], dsb[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        dsa[j] = pa[j] * (dpa[j] - da) * 0.125f;
+        dsb[j] = pb[j] * (dpb[j] - db) * 0.125f;
+    }
+    uint32_t pf[4], dsf[4], tf[4];
+    tt_afrag(pa, pb, pf);
+    tt_afrag(dsa, dsb, dsf);
     bf16* dbase = d_qkv + row0 * ld + h0 * HD;
     float acc[8][4];
-    {
-        const uint32_t ds[4] = {ds_a, 0u, 0u, ds_b};
-        t8_apply(acc, ds, sK, lane);             // dQ = dS K        (sV is free after dP: staging tile)
-        t8_store(sV, dbase, fs, acc, lane);
-    }
-    {
-        const uint32_t dst[4] = {movmatrix_trans(ds_a), 0u, 0u, movmatrix_trans(ds_b)};
-        t8_apply(acc, dst, sQ, lane);            // dK = dS^T Q
-        t8_store(sV, dbase + D, fs, acc, lane);
-    }
-    {
-        const uint32_t pt[4] = {movmatrix_trans(p_a), 0u, 0u, movmatrix_trans(p_b)};
-        t8_apply(acc, pt, sG, lane);             // dV = P^T dO
-        t8_store(sV, dbase + 2 * D, fs, acc, lane);
-    }
+    tt_apply(acc, dsf, sK, lane);                // dQ = dS K        (sV is free after dP: staging tile)
+    tt_store<PAIR>(sV, dbase, fs, acc, lane);
+    tt_afrag_t(dsf, tf);
+    tt_apply(acc, tf, sQ, lane);                 // dK = dS^T Q
+    tt_store<PAIR>(sV, dbase + D, fs, acc, lane);
+    tt_afrag_t(pf, tf);
+    tt_apply(acc, tf, sG, lane);                 // dV = P^T dO
+    tt_store<PAIR>(sV, dbase + 2 * D, fs, acc, lane);
 }
 
-int attn_temporal8_fwd_mma(const void* qkv, void* o, int B, int n, int heads, cudaStream_t s) {
-    const int64_t pairs = (int64_t)B * n * (heads / 2);
-    const size_t smem = (size_t)4 * 3 * T8_TILE * 2;
-    launch_k(attn_temporal8_fwd_mma_kernel, dim3((unsigned)((pairs + 3) / 4)), dim3(128), smem, s, (const bf16*)qkv, (bf16*)o, B, n, heads);
+// T = 8 (heads paired, heads must be even) or T = 16
+int attn_temporal_fwd_mma(const void* qkv, void* o, int B, int T, int n, int heads, cudaStream_t s) {
+    const int64_t probs = (int64_t)B * n * (T == 8 ? heads / 2 : heads);
+    const size_t smem = (size_t)4 * 3 * TT_TILE * 2;
+    const dim3 grid((unsigned)((probs + 3) / 4));
+    if (T == 8) launch_k(attn_temporal_fwd_mma_kernel<true>, grid, dim3(128), smem, s, (const bf16*)qkv, (bf16*)o, B, n, heads);
+    else launch_k(attn_temporal_fwd_mma_kernel<false>, grid, dim3(128), smem, s, (const bf16*)qkv, (bf16*)o, B, n, heads);
     AIMB_CHECK_LAUNCH();
     return AIMB_OK;
 }
-int attn_temporal8_bwd_mma(const void* qkv, const void* d_o, void* d_qkv, int B, int n, int heads, cudaStream_t s) {
-    const int64_t pairs = (int64_t)B * n * (heads / 2);
-    const size_t smem = (size_t)4 * 4 * T8_TILE * 2;
-    launch_k(attn_temporal8_bwd_mma_kernel, dim3((unsigned)((pairs + 3) / 4)), dim3(128), smem, s, (const bf16*)qkv, (const bf16*)d_o,
-             (bf16*)d_qkv, B, n, heads);
+int attn_temporal_bwd_mma(const void* qkv, const void* d_o, void* d_qkv, int B, int T, int n, int heads, cudaStream_t s) {
+    const int64_t probs = (int64_t)B * n * (T == 8 ? heads / 2 : heads);
+    const size_t smem = (size_t)4 * 4 * TT_TILE * 2;
+    const dim3 grid((unsigned)((probs + 3) / 4));
+    if (T == 8)
+        launch_k(attn_temporal_bwd_mma_kernel<true>, grid, dim3(128), smem, s, (const bf16*)qkv, (const bf16*)d_o, (bf16*)d_qkv, B, n, heads);
+    else
+        launch_k(attn_temporal_bwd_mma_kernel<false>, grid, dim3(128), smem, s, (const bf16*)qkv, (const bf16*)d_o, (bf16*)d_qkv, B, n, heads);
     AIMB_CHECK_LAUNCH();
     return AIMB_OK;
 }
