@@ -970,6 +970,252 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
 }
 
+
+// ---------------------------------------------------------------------------------------- CTA pair + row-layout epilogue
+// gemm_tc5_kernel: the cta_group::2 mainloop of gemm_tc2_kernel (each CTA loads its 128 rows of A and HALF of the W
+// tile; one tcgen05.mma spans both SMs) with the row-layout epilogue of gemm_tc4_kernel.  Per-FLOP L2->SM operand
+// traffic drops 1.5x, which is what the epilogue's own L2 traffic competes with on the N = 2304 / 3072 shapes.
+template <int BN, int V> struct TileCfg5 {
+    static constexpr int EPI_W = 4 * (BN / 64);
+    static constexpr int THREADS = 64 + 32 * EPI_W;
+    static constexpr int EPI_BYTES = EPI_W * EpiBufs<V>::WARP_BYTES + 1024;
+    static constexpr int B_STAGE_BYTES = (BN / 2) * BK * 2;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int STAGES_RAW = (232448 - EPI_BYTES - 1024 - 256) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+    static constexpr bool OK = STAGES >= 3;
+    static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    static constexpr int SMEM_BYTES = (STAGES > 0 ? STAGES : 1) * STAGE_BYTES + EPI_BYTES + 1024 + 256;
+};
+template <int BN, int V>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TileCfg5<BN, V>::THREADS, 1)
+gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmP, const EpiParams epi,
+                const int M, const int N, const int K) {
+    pdl_trigger();
+    using Cfg = TileCfg5<BN, V>;
+    using EB = EpiBufs<V>;
+    using EV = EpiVariant<V>;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr int EPI_W = Cfg::EPI_W;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES;
+    float* scol = reinterpret_cast<float*>(epi_smem + EPI_W * EB::WARP_BYTES);   // [slab buffers][bias][scol]
+    if (threadIdx.x < 256) scol[threadIdx.x] = 0.f;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + Cfg::EPI_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int n_tiles = N / BN;
+    const int m_tiles = (M + 2 * BM - 1) / (2 * BM);
+    const int total = n_tiles * m_tiles;
+    const int KB = K / BK;
+    if (threadIdx.x == 0) {
+        ptx::prefetch_tmap(&tmA);
+        ptx::prefetch_tmap(&tmB);
+        for (int i = 0; i < STAGES; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], 2 * EPI_W); }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) ptx::tmem_alloc_2cta<Cfg::TMEM_COLS>(tmem_ptr);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = pair; tile < total; tile += npairs) {
+                const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+                for (int kb = 0; kb < KB; ++kb) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    ptx::tma_load_2d_2sm(sa, &tmA, &full_bar[stage], kb * BK, m_blk * 2 * BM + (int)rank * BM);
+                    ptx::tma_load_2d_2sm(sa + A_STAGE_BYTES, &tmB, &full_bar[stage], kb * BK, n_blk * BN + (int)rank * (BN / 2));
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = ptx::umma_idesc_bf16(2 * BM, BN);
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int tile = pair; tile < total; tile += npairs, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = 0; kb < KB; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint64_t adesc = ptx::umma_desc_kmajor_sw128(sa);
+                    const uint64_t bdesc = ptx::umma_desc_kmajor_sw128(sa + A_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        ptx::umma_bf16_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    ptx::umma_commit_2cta(&empty_bar[stage], 3);
+                    if (kb == KB - 1) ptx::umma_commit_2cta(&tfull_bar[as], 3);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        constexpr int EXT = EV::EXT;
+        const int ew = warp - 2;
+        const int quad = warp & 3;
+        const int slab = ew >> 2;
+        constexpr bool TMA_ST = (EXT == 0);                   // plain / activation variants: the slab leaves through TMA
+        const uint32_t buf0 = ptx::smem_u32(epi_smem + ew * (EB::NBUF * 4096));   // out (in place over dact_src / res1); 1 KB aligned
+        const uint32_t buf1 = buf0 + 4096;                    // out_pre, or res2
+        float* sbias = reinterpret_cast<float*>(epi_smem + EPI_W * (EB::NBUF * 4096) + ew * 256);
+        if (TMA_ST && lane == 0) { ptx::prefetch_tmap(&tmO); if (want_pre_k(epi, EB::PRE)) ptx::prefetch_tmap(&tmP); }
+        const bf16* g0 = (EXT & 1) ? (const bf16*)epi.dact_src : (const bf16*)epi.res1;
+        const bf16* g1 = (const bf16*)epi.res2;
+        const bool want_pre = EB::PRE && epi.out_pre != nullptr;
+        const int dbg = g_dbg_skip_epilogue;   // bench_tools only: 4 = no flush, 5 = no slab writes either, 6 = STG flush instead of TMA
+        auto fetch = [&](int tile) {
+            const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+            const int64_t rb = (int64_t)m_blk * 2 * BM + (int64_t)rank * BM + quad * 32;
+            const int nb = n_blk * BN + slab * 64;
+            if (EXT & 3) slab_fetch(buf0, g0, epi.ldo, rb, nb, M, lane);
+            if (EXT & 4) slab_fetch(buf1, g1, epi.ldo, rb, nb, M, lane);
+        };
+        if (EXT != 0 && pair < total) fetch(pair);
+        int it = 0;
+        for (int tile = pair; tile < total; tile += npairs, ++it) {
+            const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            const int64_t row_base = (int64_t)m_blk * 2 * BM + (int64_t)rank * BM + quad * 32;
+            const int n_base = n_blk * BN + slab * 64;
+            const int64_t row = row_base + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN + slab * 64;
+            if (epi.bias) {
+                sbias[lane] = __bfloat162float(((const bf16*)epi.bias)[n_base + lane]);
+                sbias[lane + 32] = __bfloat162float(((const bf16*)epi.bias)[n_base + lane + 32]);
+            }
+            float rs = 1.f;
+            if (epi.row_scale && row < M) rs = epi.row_scale[(int)row % epi.row_mod];
+            ptx::mbar_wait(&tfull_bar[as], aphase);
+            ptx::tc_fence_after();
+            uint32_t ra[16], rb16[16];
+            ptx::tmem_ld_32x32b_x16(taddr, ra);
+            cp_async_commit_wait();
+            if (TMA_ST && lane == 0) ptx::bulk_wait_read0();   // the previous tile's TMA store has finished reading the slab
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t (&cur)[16] = (q & 1) ? rb16 : ra;
+                uint32_t (&nxt)[16] = (q & 1) ? ra : rb16;
+                ptx::tmem_wait_ld();
+                if (q < 3) ptx::tmem_ld_32x32b_x16(taddr + (q + 1) * 16, nxt);
+                if (q == 3) {                                  // accumulator drained: hand the TMEM buffer back early
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive_cluster(&tempty_bar[as], 0);   // the leader's MMA warp waits for both CTAs
+                }
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int ch = 2 * q + hh;
+                    const uint32_t off = slab_off(lane, ch);
+                    uint4 xd = make_uint4(0, 0, 0, 0), x1 = xd, x2 = xd, pre_pk = xd;
+                    if (EXT & 1) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(xd.x), "=r"(xd.y), "=r"(xd.z), "=r"(xd.w) : "r"(buf0 + off));
+                    if ((EXT & 3) == 2) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x1.x), "=r"(x1.y), "=r"(x1.z), "=r"(x1.w) : "r"(buf0 + off));
+                    if (EXT & 4) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x2.x), "=r"(x2.y), "=r"(x2.z), "=r"(x2.w) : "r"(buf1 + off));
+                    float v[8], bias8[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(cur[hh * 8 + j]);
+                    if (epi.bias) {
+                        *reinterpret_cast<float4*>(bias8) = *reinterpret_cast<const float4*>(sbias + ch * 8);
+                        *reinterpret_cast<float4*>(bias8 + 4) = *reinterpret_cast<const float4*>(sbias + ch * 8 + 4);
+                    }
+                    const uint4 o = epi_math8<EV::ACT, EV::DACT, EXT>(epi, rs, v, bias8, xd, x1, x2, pre_pk, want_pre);
+                    if (dbg == 5 && o.x != 0x12345678u) continue;
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(buf0 + off), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+                    if (want_pre)
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(buf1 + off), "r"(pre_pk.x), "r"(pre_pk.y), "r"(pre_pk.z), "r"(pre_pk.w) : "memory");
+                }
+            }
+            if (dbg == 4 || dbg == 5) { __syncwarp(); continue; }
+            if (TMA_ST && !epi.colsum_out && dbg != 6) {
+                ptx::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    ptx::tma_store_2d(&tmO, buf0, n_base, (int)row_base);
+                    if (want_pre) ptx::tma_store_2d(&tmP, buf1, n_base, (int)row_base);
+                    ptx::bulk_commit();
+                }
+                continue;
+            }
+            __syncwarp();
+            // flush: 4 full rows per instruction
+            float cs8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cs8[j] = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = i * 4 + (lane >> 3), ch = lane & 7;
+                const int64_t grow = row_base + r;
+                if (grow < M) {
+                    const uint32_t off = slab_off(r, ch);
+                    uint4 o;
+                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w) : "r"(buf0 + off));
+                    const int64_t goff = grow * epi.ldo + n_base + ch * 8;
+                    *reinterpret_cast<uint4*>((bf16*)epi.out + goff) = o;
+                    if (want_pre) {
+                        uint4 pp;
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(pp.x), "=r"(pp.y), "=r"(pp.z), "=r"(pp.w) : "r"(buf1 + off));
+                        *reinterpret_cast<uint4*>((bf16*)epi.out_pre + goff) = pp;
+                    }
+                    if (epi.colsum_out) {
+                        float t[8];
+                        unpack8(o, t);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) cs8[j] += t[j];
+                    }
+                }
+            }
+            if (epi.colsum_out) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float t = cs8[j];
+                    t += __shfl_xor_sync(0xffffffffu, t, 8);
+                    t += __shfl_xor_sync(0xffffffffu, t, 16);
+                    if (lane < 8) atomicAdd(scol + slab * 64 + lane * 8 + j, t);
+                }
+            }
+            __syncwarp();
+            if (EXT != 0 && tile + npairs < total) fetch(tile + npairs);
+            if (epi.colsum_out) {
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_W) : "memory");
+                const int te = threadIdx.x - 64;
+                if (te < BN) { atomicAdd(epi.colsum_out + n_blk * BN + te, scol[te]); scol[te] = 0.f; }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_W) : "memory");
+            }
+        }
+    }
+    if (warp >= 2 && lane == 0) ptx::bulk_wait0();   // smem must stay valid until the TMA stores have read it
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();     // no CTA may exit (or free TMEM) while its peer can still signal / read it
+    if (warp == 1) {
+        __syncwarp();
+        ptx::tmem_dealloc_2cta<Cfg::TMEM_COLS>(tmem_base);
+    }
+}
+
+
 // ---------------------------------------------------------------------------------------- 2-CTA GEMM
 // Same pipeline with tcgen05.mma.cta_group::2: a CTA pair computes a 256 x BN tile.  Each CTA TMA-loads its
 // own 128 rows of A and only HALF of the W tile (BN/2 rows); the pair's tensor cores read both halves, so the
@@ -1279,6 +1525,7 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // faster on gemm_tc_kernel: its stores trickle out chunk by chunk instead of one burst per tile), 1 = gemm_tc_kernel,
 // 3 = gemm_tc3_kernel, 4 = gemm_tc4_kernel wherever its shared-memory budget allows
 static int g_epi_kernel = 0;
+static int g_pair_epi = 0;          // 1: gemm_tc5_kernel (CTA pairs + row-layout epilogue) where it tiles
 static inline bool use_tc4(int v) { return (g_epi_kernel == 4 || (g_epi_kernel == 0 && v != 1)) && v != 7; }
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1446,6 +1693,46 @@ static int launch_tc2(const CUtensorMap& ta, const CUtensorMap& tb, const EpiPar
 }
 
 // 2-CTA tile choice: minimise waves x per-tile cost over the 74 CTA pairs.
+
+template <int BN, int V>
+static int launch_tc5_v(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p, int M, int N, int K, cudaStream_t s) {
+    if constexpr (V != 7 && TileCfg5<BN, V>::OK) {
+        using Cfg = TileCfg5<BN, V>;
+        static bool attr_set = false;
+        if (!attr_set) {
+            if (cudaFuncSetAttribute(gemm_tc5_kernel<BN, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
+                return AIMB_ERR_CUDA;
+            attr_set = true;
+        }
+        CUtensorMap to = ta, tp = ta;
+        if (EpiVariant<V>::EXT == 0) {
+            if (make_tmap_bf16(&to, p.out, M, N, p.ldo, 32)) return AIMB_ERR_DRIVER;
+            if (p.out_pre && make_tmap_bf16(&tp, p.out_pre, M, N, p.ldo, 32)) return AIMB_ERR_DRIVER;
+        }
+        int total = (N / BN) * ((M + 2 * BM - 1) / (2 * BM));
+        int pairs = num_sms() / 2;
+        if (total < pairs) pairs = total;
+        launch_k((gemm_tc5_kernel<BN, V>), dim3(2 * pairs), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, s, ta, tb, to, tp, p, M, N, K);
+        AIMB_CHECK_LAUNCH();
+        return AIMB_OK;
+    } else {
+        return AIMB_ERR_UNSUPPORTED;
+    }
+}
+template <int BN>
+static int launch_tc5(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p, int M, int N, int K, cudaStream_t s) {
+    switch (pick_variant(p)) {
+        case 0: return launch_tc5_v<BN, 0>(ta, tb, p, M, N, K, s);
+        case 1: return launch_tc5_v<BN, 1>(ta, tb, p, M, N, K, s);
+        case 2: return launch_tc5_v<BN, 2>(ta, tb, p, M, N, K, s);
+        case 3: return launch_tc5_v<BN, 3>(ta, tb, p, M, N, K, s);
+        case 4: return launch_tc5_v<BN, 4>(ta, tb, p, M, N, K, s);
+        case 5: return launch_tc5_v<BN, 5>(ta, tb, p, M, N, K, s);
+        case 6: return launch_tc5_v<BN, 6>(ta, tb, p, M, N, K, s);
+    }
+    return AIMB_ERR_UNSUPPORTED;
+}
+
 static int pick_bn2(int64_t M, int N) {
     const int cand[3] = {256, 192, 0};
     int best = 0; double best_cost = 1e30;
@@ -1522,6 +1809,23 @@ int gemm_tc_launch(const void* A, int64_t lda, const void* W, int64_t ldw, const
                 case 256: return launch_tc2<256>(ta2, tb2, p, (int)M, N, K, s);
                 case 192: return launch_tc2<192>(ta2, tb2, p, (int)M, N, K, s);
             }
+        }
+    }
+    if (g_pair_epi && M > BM) {                         // CTA pairs + row-layout epilogue where the variant's buffers fit
+        const int bn5 = (force_bn == 256 || force_bn == 192 || force_bn == 128) ? force_bn : (N % 256 == 0 ? 256 : (N % 192 == 0 ? 192 : 0));
+        if (bn5 && N % bn5 == 0) {
+            CUtensorMap ta5, tb5;
+            int rc5 = make_tmap_bf16(&ta5, A, M, K, lda, BM);
+            if (rc5) return rc5;
+            rc5 = make_tmap_bf16(&tb5, W, N, K, ldw, bn5 / 2);
+            if (rc5) return rc5;
+            rc5 = AIMB_ERR_UNSUPPORTED;
+            switch (bn5) {
+                case 256: rc5 = launch_tc5<256>(ta5, tb5, p, (int)M, N, K, s); break;
+                case 192: rc5 = launch_tc5<192>(ta5, tb5, p, (int)M, N, K, s); break;
+                case 128: rc5 = launch_tc5<128>(ta5, tb5, p, (int)M, N, K, s); break;
+            }
+            if (rc5 != AIMB_ERR_UNSUPPORTED) return rc5;
         }
     }
     int bn = force_bn > 0 ? force_bn : pick_bn(M, N, K, use_tc4(pick_variant(p)) ? pick_variant(p) : -1);
@@ -1755,7 +2059,8 @@ static int g_cta_mode = 0;   // 0/1: 1-CTA kernel (default), 2: CTA-pair (cta_gr
 extern "C" void aimb_debug_force_bn(int bn) { g_force_bn = bn; }
 extern "C" void aimb_debug_cta_mode(int mode) {
     g_cta_mode = mode == 2 ? 2 : 1;      // 2: CTA-pair kernel (cta_group::2); everything else: 1-CTA mainloop with
-    aimb::g_epi_kernel = mode == 2 ? 1 : mode;   // 0 auto, 1 gemm_tc_kernel, 3 gemm_tc3_kernel, 4 gemm_tc4_kernel
+    aimb::g_epi_kernel = (mode == 2 || mode == 5) ? (mode == 5 ? 0 : 1) : mode;   // 0 auto, 1 gemm_tc_kernel, 3 gemm_tc3_kernel, 4 gemm_tc4_kernel
+    aimb::g_pair_epi = mode == 5;        // 5: gemm_tc5_kernel (CTA pairs + row-layout epilogue), falling back to auto
 }
 extern "C" void aimb_debug_skip_epilogue(int v) { cudaMemcpyToSymbol(g_dbg_skip_epilogue, &v, sizeof(int)); }
 
