@@ -70,6 +70,11 @@ class Engine:
         self.wgrad_side = os.environ.get("AIMB200_WGRAD_STREAM", "1") == "1"
         self._side = None
         self._side_busy = False
+        # bias-gradient column sums that used to be fused into the LayerNorm backward (slower variant of the kernel,
+        # on the critical path) run as a separate reduction on a second side stream
+        self.ln_colsum_side = os.environ.get("AIMB200_LN_COLSUM_STREAM", "1") == "1"
+        self._side2 = None
+        self._side2_busy = False
 
     # ------------------------------------------------------------------ buffers (stable pointers across steps)
     def buf(self, name, shape, dtype=None, key=None):
@@ -99,6 +104,31 @@ class Engine:
             ev.record(self._side)
             torch.cuda.current_stream(self.device).wait_event(ev)
             self._side_busy = False
+
+    def _ln_bwd(self, dy, x, mean, rstd, gamma, dres, dx, colsum_out=None, colsum_row_scale=None, colsum_alpha=1.0):
+        """LayerNorm backward (+ optional weighted column sums of its result = an adapter's fc2 bias gradient)"""
+        if colsum_out is None or not (self.wgrad_side and self.ln_colsum_side):
+            self._join_side2()
+            return lib.layernorm_bwd(dy, x, mean, rstd, gamma, dres, dx, colsum_out=colsum_out,
+                                     colsum_row_scale=colsum_row_scale, colsum_alpha=colsum_alpha)
+        self._join_side2()             # a previous column sum may still read the buffer this call rewrites
+        lib.layernorm_bwd(dy, x, mean, rstd, gamma, dres, dx)
+        if self._side2 is None:
+            self._side2 = torch.cuda.Stream(device=self.device)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._side2.wait_event(ev)
+        with torch.cuda.stream(self._side2):
+            lib.colsum(dx, colsum_out, row_scale=colsum_row_scale, alpha=colsum_alpha)
+        self._side2_busy = True
+        return dx
+
+    def _join_side2(self):
+        if self._side2_busy:
+            ev = torch.cuda.Event()
+            ev.record(self._side2)
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            self._side2_busy = False
 
     def release(self):
         self._bufs.clear()
@@ -189,7 +219,7 @@ class Engine:
         self._adapter_bwd("MLP_Adapter", pre, dx, S["xn2"], S["h_m"], S["g_m"], W, WT, grads, d, mask_m, d.scale,
                           d_xn2, d_xn2, db2_fused=db2_fused)
         m3, r3 = S["ln2"]
-        lib.layernorm_bwd(d_xn2, S["x2"], m3, r3, W[pre + "ln_2.weight"], dx, dx, colsum_out=colsum_for)
+        self._ln_bwd(d_xn2, S["x2"], m3, r3, W[pre + "ln_2.weight"], dx, dx, colsum_out=colsum_for)
         return dx
 
     def _block_fwd(self, i, x, W, d, training, masks, sv):
@@ -434,8 +464,8 @@ class Engine:
         m2, r2 = S["ln1s"]
         dx1 = dx
         self._join_side()              # S_Adapter's fc2 wgrad reads dx2, which this LN backward rewrites in place
-        lib.layernorm_bwd(d_xn1, S["x1"], m2, r2, W[pre + "ln_1.weight"], dx2, dx1,
-                          colsum_out=grads[pre + "T_Adapter.D_fc2.bias"], colsum_row_scale=mask_t)
+        self._ln_bwd(d_xn1, S["x1"], m2, r2, W[pre + "ln_1.weight"], dx2, dx1,
+                     colsum_out=grads[pre + "T_Adapter.D_fc2.bias"], colsum_row_scale=mask_t)
         # ---------------- temporal: x1 = x + mask_t * T_Adapter(attn(ln_1(x)))
         d_at = self.buf("d_a", (M, D))
         self._adapter_bwd("T_Adapter", pre, dx1, S["a_t"], S["h_t"], S["g_t"], W, WT, grads, d, mask_t, 1.0, d_at, None,
@@ -456,9 +486,9 @@ class Engine:
         m1, r1 = S["ln1t"]
         self._join_side()              # T_Adapter's fc2 wgrad reads dx1 == dx, rewritten below; block grads complete
         if i > 0:   # dx is the output gradient of block i-1: its MLP-adapter fc2 bias grad = scale * sum_m mask_m[m] dx[m]
-            lib.layernorm_bwd(d_xn1t, S["x"], m1, r1, W[pre + "ln_1.weight"], dx1, dx,
-                              colsum_out=grads[f"transformer.resblocks.{i - 1}.MLP_Adapter.D_fc2.bias"],
-                              colsum_row_scale=prev_mask_m, colsum_alpha=d.scale)
+            self._ln_bwd(d_xn1t, S["x"], m1, r1, W[pre + "ln_1.weight"], dx1, dx,
+                         colsum_out=grads[f"transformer.resblocks.{i - 1}.MLP_Adapter.D_fc2.bias"],
+                         colsum_row_scale=prev_mask_m, colsum_alpha=d.scale)
         else:
-            lib.layernorm_bwd(d_xn1t, S["x"], m1, r1, W[pre + "ln_1.weight"], dx1, dx)
+            self._ln_bwd(d_xn1t, S["x"], m1, r1, W[pre + "ln_1.weight"], dx1, dx)
         return dx
