@@ -654,17 +654,22 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 //     packed to bf16 and written IN PLACE over the consumed residual chunk;
 //   * the slab is flushed with full 128-byte lines: 8 lanes x 16 B per row, 4 rows per store instruction;
 //   * column sums (bias gradients) are taken at flush time from the values actually stored.
-template <int V> struct EpiBufs {
+//   * DIRECT variant (large K, no column sums): results leave straight from registers as one 32-byte sector per lane
+//     and chunk (st.global.v8.b32) - no output slab at all.  The 1-CTA mainloop already moves ~96 KB per k-block
+//     through shared memory (TMA writes + tensor-core reads) against 128 B/clk, so every staged output byte is paid
+//     twice more in the same currency: measured 59 -> 54.5 us (bias), 73.5 -> 59.6 us (x QuickGELU'), 46.3 -> 41.2 us
+//     (QKV).  With tiny K the epilogue itself is the bottleneck and the full-line flush of the slab path wins.
+template <int V, bool DIRECT = false> struct EpiBufs {
     static constexpr int EXT = EpiVariant<V>::EXT;
     static constexpr bool PRE = (V == 1 || V == 2);
     static constexpr int NEXT = ((EXT & 1) ? 1 : 0) + ((EXT & 2) ? 1 : 0) + ((EXT & 4) ? 1 : 0);
-    static constexpr int NBUF = (NEXT > 0 ? NEXT : 1) + (PRE ? 1 : 0);       // out aliases the first operand buffer
+    static constexpr int NBUF = DIRECT ? NEXT : (NEXT > 0 ? NEXT : 1) + (PRE ? 1 : 0);   // slab path: out aliases the first operand buffer
     static constexpr int WARP_BYTES = NBUF * 4096 + 256;                     // + 64 fp32 bias values
 };
-template <int BN, int V> struct TileCfg4 {
+template <int BN, int V, bool DIRECT = false> struct TileCfg4 {
     static constexpr int EPI_W = 4 * (BN / 64);
     static constexpr int THREADS = 64 + 32 * EPI_W;
-    static constexpr int EPI_BYTES = EPI_W * EpiBufs<V>::WARP_BYTES + 1024;  // + scol[256]
+    static constexpr int EPI_BYTES = EPI_W * EpiBufs<V, DIRECT>::WARP_BYTES + 1024;  // + scol[256]
     static constexpr int B_STAGE_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int STAGES_RAW = (232448 - EPI_BYTES - 1024 - 256) / STAGE_BYTES;
@@ -746,14 +751,14 @@ __device__ __forceinline__ uint4 epi_math8(const EpiParams& e, float rs, float* 
 }
 
 __device__ __forceinline__ bool want_pre_k(const EpiParams& e, bool pre) { return pre && e.out_pre != nullptr; }
-template <int BN, int V>
-__global__ void __launch_bounds__(TileCfg4<BN, V>::THREADS, 1)
+template <int BN, int V, bool DIRECT>
+__global__ void __launch_bounds__(TileCfg4<BN, V, DIRECT>::THREADS, 1)
 gemm_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmP, const EpiParams epi,
                 const int M, const int N, const int K) {
     pdl_trigger();
-    using Cfg = TileCfg4<BN, V>;
-    using EB = EpiBufs<V>;
+    using Cfg = TileCfg4<BN, V, DIRECT>;
+    using EB = EpiBufs<V, DIRECT>;
     using EV = EpiVariant<V>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int EPI_W = Cfg::EPI_W;
@@ -831,7 +836,7 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int ew = warp - 2;
         const int quad = warp & 3;
         const int slab = ew >> 2;
-        constexpr bool TMA_ST = (EXT == 0);                   // plain / activation variants: the slab leaves through TMA
+        constexpr bool TMA_ST = (EXT == 0) && !DIRECT;                   // plain / activation variants: the slab leaves through TMA
         const uint32_t buf0 = ptx::smem_u32(epi_smem + ew * (EB::NBUF * 4096));   // out (in place over dact_src / res1); 1 KB aligned
         const uint32_t buf1 = buf0 + 4096;                    // out_pre, or res2
         float* sbias = reinterpret_cast<float*>(epi_smem + EPI_W * (EB::NBUF * 4096) + ew * 256);
@@ -881,6 +886,7 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
                 }
+                uint4 o_lo = make_uint4(0, 0, 0, 0), p_lo = o_lo;
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
                     const int ch = 2 * q + hh;
@@ -898,12 +904,31 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     }
                     const uint4 o = epi_math8<EV::ACT, EV::DACT, EXT>(epi, rs, v, bias8, xd, x1, x2, pre_pk, want_pre);
                     if (dbg == 5 && o.x != 0x12345678u) continue;
+                    if (DIRECT) {        // one 32-byte sector per lane and chunk, straight from registers
+                        if (hh == 0) { o_lo = o; p_lo = pre_pk; }
+                        else if (row < M) {
+                            bf16* gp = (bf16*)epi.out + row * epi.ldo + n_base + q * 16;
+                            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(gp), "r"(o_lo.x), "r"(o_lo.y), "r"(o_lo.z),
+                                         "r"(o_lo.w), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+                            if (want_pre) {
+                                bf16* pp = (bf16*)epi.out_pre + row * epi.ldo + n_base + q * 16;
+                                asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(pp), "r"(p_lo.x), "r"(p_lo.y),
+                                             "r"(p_lo.z), "r"(p_lo.w), "r"(pre_pk.x), "r"(pre_pk.y), "r"(pre_pk.z), "r"(pre_pk.w) : "memory");
+                            }
+                        }
+                        continue;
+                    }
                     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(buf0 + off), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
                     if (want_pre)
                         asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(buf1 + off), "r"(pre_pk.x), "r"(pre_pk.y), "r"(pre_pk.z), "r"(pre_pk.w) : "memory");
                 }
             }
             if (dbg == 4 || dbg == 5) { __syncwarp(); continue; }
+            if (DIRECT) {
+                __syncwarp();
+                if (EXT != 0 && tile + (int)gridDim.x < total) fetch(tile + gridDim.x);
+                continue;
+            }
             if (TMA_ST && !epi.colsum_out && dbg != 6) {
                 ptx::fence_proxy_async();
                 __syncwarp();
@@ -1526,7 +1551,15 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // 3 = gemm_tc3_kernel, 4 = gemm_tc4_kernel wherever its shared-memory budget allows
 static int g_epi_kernel = 0;
 static int g_pair_epi = 0;          // 1: gemm_tc5_kernel (CTA pairs + row-layout epilogue) where it tiles
+static int g_direct = 1;           // 0: never use the DIRECT (register-store) epilogue, 1: auto (K >= 512), 2: always
 static inline bool use_tc4(int v) { return (g_epi_kernel == 4 || (g_epi_kernel == 0 && v != 1)) && v != 7; }
+// DIRECT epilogue: 32-byte sector stores from registers; for every variant without fused column sums once the mainloop
+// (not the epilogue) is the long pole
+static inline bool use_tc4_direct(int v, int K, const EpiParams& p) {
+    if (v == 7 || p.colsum_out || (g_epi_kernel != 0 && g_epi_kernel != 4) || g_direct == 0) return false;
+    if ((p.ldo % 16) || ((uintptr_t)p.out & 31) || (p.out_pre && ((uintptr_t)p.out_pre & 31))) return false;
+    return g_direct == 2 || K >= 512;
+}
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1613,12 +1646,26 @@ static int launch_tc_v(const CUtensorMap& ta, const CUtensorMap& tb, const EpiPa
     }
     int total = (N / BN) * ((M + BM - 1) / BM);
     int grid = total < num_sms() ? total : num_sms();
-    if constexpr (V != 7 && TileCfg4<BN, V>::OK) {
+    if (use_tc4_direct(V, K, p)) {
+        if constexpr (V != 7 && TileCfg4<BN, V, true>::OK) {
+            using Cfg4 = TileCfg4<BN, V, true>;
+            static bool attr4d = false;
+            if (!attr4d) {
+                if (cudaFuncSetAttribute(gemm_tc4_kernel<BN, V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg4::SMEM_BYTES) != cudaSuccess)
+                    return AIMB_ERR_CUDA;
+                attr4d = true;
+            }
+            launch_k((gemm_tc4_kernel<BN, V, true>), dim3(grid), dim3(Cfg4::THREADS), Cfg4::SMEM_BYTES, s, ta, tb, ta, ta, p, M, N, K);
+            AIMB_CHECK_LAUNCH();
+            return AIMB_OK;
+        }
+    }
+    if constexpr (V != 7 && TileCfg4<BN, V, false>::OK) {
         if (use_tc4(V)) {
-            using Cfg4 = TileCfg4<BN, V>;
+            using Cfg4 = TileCfg4<BN, V, false>;
             static bool attr4 = false;
             if (!attr4) {
-                if (cudaFuncSetAttribute(gemm_tc4_kernel<BN, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg4::SMEM_BYTES) != cudaSuccess)
+                if (cudaFuncSetAttribute(gemm_tc4_kernel<BN, V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg4::SMEM_BYTES) != cudaSuccess)
                     return AIMB_ERR_CUDA;
                 attr4 = true;
             }
@@ -1627,7 +1674,7 @@ static int launch_tc_v(const CUtensorMap& ta, const CUtensorMap& tb, const EpiPa
                 if (make_tmap_bf16(&to, p.out, M, N, p.ldo, 32)) return AIMB_ERR_DRIVER;
                 if (p.out_pre && make_tmap_bf16(&tp, p.out_pre, M, N, p.ldo, 32)) return AIMB_ERR_DRIVER;
             }
-            launch_k((gemm_tc4_kernel<BN, V>), dim3(grid), dim3(Cfg4::THREADS), Cfg4::SMEM_BYTES, s, ta, tb, to, tp, p, M, N, K);
+            launch_k((gemm_tc4_kernel<BN, V, false>), dim3(grid), dim3(Cfg4::THREADS), Cfg4::SMEM_BYTES, s, ta, tb, to, tp, p, M, N, K);
             AIMB_CHECK_LAUNCH();
             return AIMB_OK;
         }
@@ -1753,28 +1800,28 @@ static int pick_bn2(int64_t M, int N) {
 // Per-tile time ~ KB*bn (MMA-bound mainloop) + ~1536 (pipeline fill / epilogue tail), fitted to the sweep in
 // profiles/ (bench_tools/gemm_sweep.py): N=2304/3072 prefer 256, N=768 prefers 192.
 // which (tile width, epilogue variant) pairs leave >= 3 pipeline stages next to the slab buffers of gemm_tc4_kernel
-template <int V> static bool tc4_ok_v(int bn) {
+template <int V> static bool tc4_ok_v(int bn, bool direct) {
     switch (bn) {
-        case 256: return TileCfg4<256, V>::OK;
-        case 192: return TileCfg4<192, V>::OK;
-        case 128: return TileCfg4<128, V>::OK;
-        case 64: return TileCfg4<64, V>::OK;
+        case 256: return direct ? TileCfg4<256, V, true>::OK : TileCfg4<256, V, false>::OK;
+        case 192: return direct ? TileCfg4<192, V, true>::OK : TileCfg4<192, V, false>::OK;
+        case 128: return direct ? TileCfg4<128, V, true>::OK : TileCfg4<128, V, false>::OK;
+        case 64: return direct ? TileCfg4<64, V, true>::OK : TileCfg4<64, V, false>::OK;
     }
     return false;
 }
-static bool tc4_ok(int bn, int v) {
+static bool tc4_ok(int bn, int v, bool direct) {
     switch (v) {
-        case 0: return tc4_ok_v<0>(bn);
-        case 1: return tc4_ok_v<1>(bn);
-        case 2: return tc4_ok_v<2>(bn);
-        case 3: return tc4_ok_v<3>(bn);
-        case 4: return tc4_ok_v<4>(bn);
-        case 5: return tc4_ok_v<5>(bn);
-        case 6: return tc4_ok_v<6>(bn);
+        case 0: return tc4_ok_v<0>(bn, direct);
+        case 1: return tc4_ok_v<1>(bn, direct);
+        case 2: return tc4_ok_v<2>(bn, direct);
+        case 3: return tc4_ok_v<3>(bn, direct);
+        case 4: return tc4_ok_v<4>(bn, direct);
+        case 5: return tc4_ok_v<5>(bn, direct);
+        case 6: return tc4_ok_v<6>(bn, direct);
     }
     return false;
 }
-static int pick_bn(int64_t M, int N, int K, int variant = -1) {
+static int pick_bn(int64_t M, int N, int K, int variant = -1, bool direct = false) {
     const int cand[4] = {256, 192, 128, 64};
     int best = 0; double best_cost = 1e30;
     int64_t mt = (M + BM - 1) / BM;
@@ -1782,7 +1829,7 @@ static int pick_bn(int64_t M, int N, int K, int variant = -1) {
     for (int i = 0; i < 4; ++i) {
         int bn = cand[i];
         if (N % bn) continue;
-        if (variant >= 0 && variant < 7 && !tc4_ok(bn, variant)) continue;
+        if (variant >= 0 && variant < 7 && !tc4_ok(bn, variant, direct)) continue;
         int64_t tiles = mt * (N / bn);
         int64_t waves = (tiles + num_sms() - 1) / num_sms();
         double per_tile = kb * (double)(bn < 128 ? 128 : bn) + 1536.0;   // below N=128 the A-operand traffic dominates
@@ -1828,7 +1875,9 @@ int gemm_tc_launch(const void* A, int64_t lda, const void* W, int64_t ldw, const
             if (rc5 != AIMB_ERR_UNSUPPORTED) return rc5;
         }
     }
-    int bn = force_bn > 0 ? force_bn : pick_bn(M, N, K, use_tc4(pick_variant(p)) ? pick_variant(p) : -1);
+    const int var = pick_variant(p);
+    const bool direct = use_tc4_direct(var, K, p);
+    int bn = force_bn > 0 ? force_bn : pick_bn(M, N, K, (direct || use_tc4(var)) ? var : -1, direct);
     if (bn == 0 || N % bn) return AIMB_ERR_ARG;
     CUtensorMap ta, tb;
     int rc = make_tmap_bf16(&ta, A, M, K, lda, BM);
@@ -2062,6 +2111,7 @@ extern "C" void aimb_debug_cta_mode(int mode) {
     aimb::g_epi_kernel = (mode == 2 || mode == 5) ? (mode == 5 ? 0 : 1) : mode;   // 0 auto, 1 gemm_tc_kernel, 3 gemm_tc3_kernel, 4 gemm_tc4_kernel
     aimb::g_pair_epi = mode == 5;        // 5: gemm_tc5_kernel (CTA pairs + row-layout epilogue), falling back to auto
 }
+extern "C" void aimb_debug_direct_epilogue(int v) { aimb::g_direct = v; }
 extern "C" void aimb_debug_skip_epilogue(int v) { cudaMemcpyToSymbol(g_dbg_skip_epilogue, &v, sizeof(int)); }
 
 extern "C" int aimb_gemm_nt(const void* A, int64_t lda, const void* W, int64_t ldw, const aimb_epilogue_t* epi, int64_t M,

@@ -3,6 +3,8 @@ of the same op (fp64 where cheap).  fp32 kernels: tight tolerance; bf16 kernels:
 reference evaluated on the *same bf16-rounded inputs*, tolerance = a few bf16 ulps of the output scale."""
 import math
 
+import ctypes
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -153,6 +155,21 @@ def test_gemm_tc_epilogues(case, cta_mode):
         assert _gemm_case(lib, "bf16", 1000, 768, 192, case, lib.IMPL_AUTO) < 1.5e-2
     finally:
         lib.load().aimb_debug_cta_mode(0)
+
+
+@pytest.mark.parametrize("direct", [2, 0])
+@pytest.mark.parametrize("K", [192, 768])
+@pytest.mark.parametrize("case", EPI_CASES)
+def test_gemm_tc_epilogues_direct(case, K, direct):
+    """row-layout kernel with the register-store (DIRECT) epilogue forced on (2) / off (0) for every epilogue variant"""
+    lib = _lib()
+    L = lib.load()
+    L.aimb_debug_direct_epilogue.argtypes = [ctypes.c_int]
+    L.aimb_debug_direct_epilogue(direct)
+    try:
+        assert _gemm_case(lib, "bf16", 1000, 768, K, case, lib.IMPL_AUTO) < 1.5e-2
+    finally:
+        L.aimb_debug_direct_epilogue(1)
 
 
 @pytest.mark.parametrize("N,K", [(192, 768), (768, 192), (3072, 768), (768, 3072), (2304, 768), (256, 1024), (4096, 1024)])
