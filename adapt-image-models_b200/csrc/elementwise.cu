@@ -389,40 +389,51 @@ __global__ void __launch_bounds__(128) tail_bwd_kernel(const float* __restrict__
 }
 
 // ------------------------------------------------------------------ column sums (bias grads, temporal-embedding grad)
-// block = 32 lanes (each a 16-byte column vector) x 8 row lanes; every block reduces `rows_per_block` rows of
-// 32 column vectors, then one atomicAdd per column.
+// block = 32 lanes (each a 16-byte column vector) x 32 row lanes; a block reduces `rows_per_block` (128) rows of 32
+// column vectors with 4 independent loads in flight per thread, then one atomicAdd per column.  (More, smaller blocks
+// were measured slower: every block adds into the same C addresses and the atomics serialise in L2.)
 template <typename T>
-__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, int64_t ld,
-                                                     const float* __restrict__ row_scale, int row_mod, float alpha,
-                                                     float* __restrict__ out, int64_t R, int C, int rows_per_block) {
+__global__ void __launch_bounds__(1024) colsum_kernel(const T* __restrict__ x, int64_t ld,
+                                                      const float* __restrict__ row_scale, int row_mod, float alpha,
+                                                      float* __restrict__ out, int64_t R, int C, int rows_per_block) {
     pdl_grid_sync();
     constexpr int V = VecIO<T>::N;
-    __shared__ float red[8][32][V + 1];
+    __shared__ float red[32][32][V + 1];
     const int c = (blockIdx.x * 32 + threadIdx.x) * V;
     int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
     int64_t r1 = r0 + rows_per_block < R ? r0 + rows_per_block : R;
     float s[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) s[j] = 0.f;
-    if (c < C)
-        for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
-            float v[V];
-            VecIO<T>::ld(x + r * ld + c, v);
-            float w = row_scale ? row_scale[r % row_mod] : 1.f;
+    if (c < C) {
+        const T* xc = x + c;
+        for (int64_t r = r0 + threadIdx.y; r < r1; r += 128) {
+            typename VecIO<T>::Raw raw[4];
+            float w[4];
 #pragma unroll
-            for (int j = 0; j < V; ++j) s[j] = fmaf(v[j], w, s[j]);
+            for (int u = 0; u < 4; ++u) {
+                const int64_t ru = r + 32 * u;
+                const bool ok = ru < r1;
+                raw[u] = VecIO<T>::ldraw(xc + (ok ? ru : r) * ld);
+                w[u] = !ok ? 0.f : (row_scale ? row_scale[(int)(ru % row_mod)] : 1.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float v[V];
+                VecIO<T>::unpack(raw[u], v);
+#pragma unroll
+                for (int j = 0; j < V; ++j) s[j] = fmaf(v[j], w[u], s[j]);
+            }
         }
+    }
 #pragma unroll
     for (int j = 0; j < V; ++j) red[threadIdx.y][threadIdx.x][j] = s[j];
     __syncthreads();
-    if (threadIdx.y == 0 && c < C) {
+    if (threadIdx.y < V && c < C) {          // row lane j finishes column j of every vector
+        float t = 0.f;
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-            float t = 0.f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x][j];
-            atomicAdd(out + c + j, alpha * t);
-        }
+        for (int i = 0; i < 32; ++i) t += red[i][threadIdx.x][threadIdx.y];
+        atomicAdd(out + c + threadIdx.y, alpha * t);
     }
 }
 
@@ -735,9 +746,8 @@ extern "C" int aimb_colsum(const void* x, int64_t ld, const float* row_scale, in
     if (!accumulate && cudaMemsetAsync(out, 0, (size_t)C * 4, s) != cudaSuccess) return AIMB_ERR_CUDA;
     if (R == 0) return AIMB_OK;
     const int gx = (C / V + 31) / 32;
-    int rpb = 128;
-    while (rpb > 16 && (int64_t)gx * ((R + rpb - 1) / rpb) < 296) rpb >>= 1;   // >= 2 waves of blocks
-    dim3 grid(gx, (unsigned)((R + rpb - 1) / rpb)), block(32, 8);
+    const int rpb = 128;
+    dim3 grid(gx, (unsigned)((R + rpb - 1) / rpb)), block(32, 32);
     if (dtype == AIMB_BF16)
         launch_k((colsum_kernel<bf16>), dim3(grid), dim3(block), 0, s, (const bf16*)x, ld, row_scale, row_mod, alpha, out, R, C, rpb);
     else if (dtype == AIMB_F32)
