@@ -689,8 +689,234 @@ __global__ void __launch_bounds__(128) attn_temporal_bwd_mma_kernel(const bf16* 
     tt_store<PAIR>(sV, dbase + 2 * D, fs, acc, lane);
 }
 
-// T = 8 (heads paired, heads must be even) or T = 16
+
+// ------------------------------------------------------------------------------------------ temporal attention, T = 32
+// One warp per (clip, token, head): the 32 frames are two 16-row m-tiles; S is 32 x 32 (4 key n-tiles), P / dS feed
+// the second GEMMs as two k-steps of A fragments, and the transposed fragments for dK / dV are 16 movmatrix each.
+constexpr int T32_TILE = 32 * LDS;
+__device__ __forceinline__ void t32_load(bf16* dst, const bf16* src, int64_t frame_stride, int lane) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int e = i * 32 + lane, r = e >> 3, c = (e & 7) * 8;
+        cp_async16(dst + r * LDS + c, src + (int64_t)r * frame_stride + c);
+    }
+}
+__device__ __forceinline__ void t32_store(bf16* tile, bf16* dst, int64_t frame_stride, const float (&acc)[2][8][4], int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    __syncwarp();
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int dt = 0; dt < 8; ++dt) {
+            *reinterpret_cast<uint32_t*>(tile + (mt * 16 + g) * LDS + dt * 8 + 2 * t) = pack_bf16(acc[mt][dt][0], acc[mt][dt][1]);
+            *reinterpret_cast<uint32_t*>(tile + (mt * 16 + g + 8) * LDS + dt * 8 + 2 * t) = pack_bf16(acc[mt][dt][2], acc[mt][dt][3]);
+        }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int e = i * 32 + lane, r = e >> 3, c = (e & 7) * 8;
+        *reinterpret_cast<uint4*>(dst + (int64_t)r * frame_stride + c) = *reinterpret_cast<const uint4*>(tile + r * LDS + c);
+    }
+}
+// s[mt][nt][4] = A[32 x 64] . B[32 rows x 64]^T
+__device__ __forceinline__ void t32_scores(float (&s)[2][4][4], const bf16* sA, const bf16* sB, int lane) {
+    uint32_t a[2][4][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) lda_frag(a[mt][ks], sA + mt * 16 * LDS + ks * 16, lane);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s[mt][nt][j] = 0.f;
+#pragma unroll
+        for (int kp = 0; kp < 2; ++kp) {
+            uint32_t b[4];
+            ldb_frag_nk(b, sB + (nt * 8) * LDS + kp * 32, lane);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                mma16816(s[mt][nt], a[mt][2 * kp], b[0], b[1]);
+                mma16816(s[mt][nt], a[mt][2 * kp + 1], b[2], b[3]);
+            }
+        }
+    }
+}
+// acc[mt][dt] = sum over the two k-steps of A[mt][kk] . B[32 rows x 64]
+__device__ __forceinline__ void t32_apply(float (&acc)[2][8][4], const uint32_t (&a)[2][2][4], const bf16* sB, int lane) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int dt = 0; dt < 8; ++dt)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[mt][dt][j] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+        for (int dp = 0; dp < 4; ++dp) {
+            uint32_t b[4];
+            ldb_frag_kn(b, sB + kk * 16 * LDS + dp * 16, lane);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                mma16816(acc[mt][2 * dp], a[mt][kk], b[0], b[1]);
+                mma16816(acc[mt][2 * dp + 1], a[mt][kk], b[2], b[3]);
+            }
+        }
+}
+// row softmax over 32 keys: row (mt, g) holds s[mt][nt][0..1], row (mt, g + 8) holds s[mt][nt][2..3]; in place -> P
+__device__ __forceinline__ void t32_softmax(float (&s)[2][4][4]) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float m = -INFINITY;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) m = fmaxf(m, fmaxf(s[mt][nt][2 * h], s[mt][nt][2 * h + 1]));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+            float sum = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const float e = ex2_ftz((s[mt][nt][2 * h + j] - m) * SCALE_LOG2);
+                    s[mt][nt][2 * h + j] = e;
+                    sum += e;
+                }
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            const float inv = __fdividef(1.f, sum);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) { s[mt][nt][2 * h] *= inv; s[mt][nt][2 * h + 1] *= inv; }
+        }
+}
+// A fragments (row tile mt, k-step kk over keys) of a 32 x 32 matrix held in score layout
+__device__ __forceinline__ void t32_afrag(const float (&x)[2][4][4], uint32_t (&a)[2][2][4]) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+            a[mt][kk][0] = pack_bf16(x[mt][2 * kk][0], x[mt][2 * kk][1]);
+            a[mt][kk][1] = pack_bf16(x[mt][2 * kk][2], x[mt][2 * kk][3]);
+            a[mt][kk][2] = pack_bf16(x[mt][2 * kk + 1][0], x[mt][2 * kk + 1][1]);
+            a[mt][kk][3] = pack_bf16(x[mt][2 * kk + 1][2], x[mt][2 * kk + 1][3]);
+        }
+}
+// fragments of the transposed matrix: 8 x 8 block B[rb][cb] of the source sits in a[rb >> 1][cb >> 1][(rb & 1) + 2 * (cb & 1)]
+__device__ __forceinline__ void t32_afrag_t(const uint32_t (&a)[2][2][4], uint32_t (&at)[2][2][4]) {
+#pragma unroll
+    for (int kt = 0; kt < 2; ++kt)          // row tile of the transpose = column (key) tile of the source
+#pragma unroll
+        for (int qs = 0; qs < 2; ++qs) {    // k-step of the transpose = row (query) tile of the source
+            at[kt][qs][0] = movmatrix_trans(a[qs][kt][0]);   // B[2qs][2kt]
+            at[kt][qs][1] = movmatrix_trans(a[qs][kt][2]);   // B[2qs][2kt+1]
+            at[kt][qs][2] = movmatrix_trans(a[qs][kt][1]);   // B[2qs+1][2kt]
+            at[kt][qs][3] = movmatrix_trans(a[qs][kt][3]);   // B[2qs+1][2kt+1]
+        }
+}
+__device__ __forceinline__ bool t32_problem(int warp, int wpb, int B, int n, int heads, int& h0, int64_t& row0) {
+    const int64_t idx = (int64_t)blockIdx.x * wpb + warp;
+    if (idx >= (int64_t)B * n * heads) return false;
+    h0 = (int)(idx % heads);
+    const int tok = (int)((idx / heads) % n);
+    const int b = (int)(idx / ((int64_t)heads * n));
+    row0 = (int64_t)b * 32 * n + tok;
+    return true;
+}
+
+__global__ void __launch_bounds__(64) attn_temporal32_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o, int B, int n,
+                                                                     int heads) {
+    pdl_grid_sync();
+    extern __shared__ __align__(16) uint8_t smraw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int h0;
+    int64_t row0;
+    if (!t32_problem(warp, 2, B, n, heads, h0, row0)) return;
+    const int D = heads * HD, ld = 3 * D;
+    bf16* sQ = reinterpret_cast<bf16*>(smraw) + warp * 3 * T32_TILE;
+    bf16* sK = sQ + T32_TILE;
+    bf16* sV = sK + T32_TILE;
+    const bf16* base = qkv + row0 * ld + h0 * HD;
+    const int64_t fs = (int64_t)n * ld;
+    t32_load(sQ, base, fs, lane);
+    t32_load(sK, base + D, fs, lane);
+    t32_load(sV, base + 2 * D, fs, lane);
+    cp_async_wait_all();
+    __syncwarp();
+    float s[2][4][4];
+    t32_scores(s, sQ, sK, lane);
+    t32_softmax(s);
+    uint32_t pf[2][2][4];
+    t32_afrag(s, pf);
+    float acc[2][8][4];
+    t32_apply(acc, pf, sV, lane);
+    t32_store(sQ, o + row0 * D + h0 * HD, (int64_t)n * D, acc, lane);
+}
+
+__global__ void __launch_bounds__(64) attn_temporal32_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o,
+                                                                     bf16* __restrict__ d_qkv, int B, int n, int heads) {
+    pdl_grid_sync();
+    extern __shared__ __align__(16) uint8_t smraw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int h0;
+    int64_t row0;
+    if (!t32_problem(warp, 2, B, n, heads, h0, row0)) return;
+    const int D = heads * HD, ld = 3 * D;
+    bf16* sQ = reinterpret_cast<bf16*>(smraw) + warp * 4 * T32_TILE;
+    bf16* sK = sQ + T32_TILE;
+    bf16* sV = sK + T32_TILE;
+    bf16* sG = sV + T32_TILE;
+    const bf16* base = qkv + row0 * ld + h0 * HD;
+    const int64_t fs = (int64_t)n * ld;
+    t32_load(sQ, base, fs, lane);
+    t32_load(sK, base + D, fs, lane);
+    t32_load(sV, base + 2 * D, fs, lane);
+    t32_load(sG, d_o + row0 * D + h0 * HD, (int64_t)n * D, lane);
+    cp_async_wait_all();
+    __syncwarp();
+    float p[2][4][4], dp[2][4][4];
+    t32_scores(p, sQ, sK, lane);                 // S = Q K^T -> P
+    t32_softmax(p);
+    t32_scores(dp, sG, sV, lane);                // dP = dO V^T
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {            // dS = P (dP - rowsum(P dP)) / 8, in place over dp
+            float dl = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) dl += p[mt][nt][2 * h] * dp[mt][nt][2 * h] + p[mt][nt][2 * h + 1] * dp[mt][nt][2 * h + 1];
+            dl += __shfl_xor_sync(0xffffffffu, dl, 1);
+            dl += __shfl_xor_sync(0xffffffffu, dl, 2);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) dp[mt][nt][2 * h + j] = p[mt][nt][2 * h + j] * (dp[mt][nt][2 * h + j] - dl) * 0.125f;
+        }
+    uint32_t pf[2][2][4], dsf[2][2][4], tf[2][2][4];
+    t32_afrag(p, pf);
+    t32_afrag(dp, dsf);
+    bf16* dbase = d_qkv + row0 * ld + h0 * HD;
+    float acc[2][8][4];
+    t32_apply(acc, dsf, sK, lane);               // dQ = dS K        (sV is free after dP: staging tile)
+    t32_store(sV, dbase, fs, acc, lane);
+    t32_afrag_t(dsf, tf);
+    t32_apply(acc, tf, sQ, lane);                // dK = dS^T Q
+    t32_store(sV, dbase + D, fs, acc, lane);
+    t32_afrag_t(pf, tf);
+    t32_apply(acc, tf, sG, lane);                // dV = P^T dO
+    t32_store(sV, dbase + 2 * D, fs, acc, lane);
+}
+
+// T = 8 (heads paired, heads must be even), T = 16 or T = 32
 int attn_temporal_fwd_mma(const void* qkv, void* o, int B, int T, int n, int heads, cudaStream_t s) {
+    if (T == 32) {
+        const int64_t probs32 = (int64_t)B * n * heads;
+        launch_k(attn_temporal32_fwd_mma_kernel, dim3((unsigned)((probs32 + 1) / 2)), dim3(64), (size_t)2 * 3 * T32_TILE * 2, s,
+                 (const bf16*)qkv, (bf16*)o, B, n, heads);
+        AIMB_CHECK_LAUNCH();
+        return AIMB_OK;
+    }
     const int64_t probs = (int64_t)B * n * (T == 8 ? heads / 2 : heads);
     const size_t smem = (size_t)4 * 3 * TT_TILE * 2;
     const dim3 grid((unsigned)((probs + 3) / 4));
@@ -700,6 +926,13 @@ int attn_temporal_fwd_mma(const void* qkv, void* o, int B, int T, int n, int hea
     return AIMB_OK;
 }
 int attn_temporal_bwd_mma(const void* qkv, const void* d_o, void* d_qkv, int B, int T, int n, int heads, cudaStream_t s) {
+    if (T == 32) {
+        const int64_t probs32 = (int64_t)B * n * heads;
+        launch_k(attn_temporal32_bwd_mma_kernel, dim3((unsigned)((probs32 + 1) / 2)), dim3(64), (size_t)2 * 4 * T32_TILE * 2, s,
+                 (const bf16*)qkv, (const bf16*)d_o, (bf16*)d_qkv, B, n, heads);
+        AIMB_CHECK_LAUNCH();
+        return AIMB_OK;
+    }
     const int64_t probs = (int64_t)B * n * (T == 8 ? heads / 2 : heads);
     const size_t smem = (size_t)4 * 4 * TT_TILE * 2;
     const dim3 grid((unsigned)((probs + 3) / 4));

@@ -545,7 +545,7 @@ extern "C" int aimb_attn_temporal_fwd(const void* qkv, void* o, int32_t B, int32
     if (!qkv || !o || B < 0 || T <= 0 || n <= 0 || heads <= 0) return AIMB_ERR_ARG;
     if (B == 0) return AIMB_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    if (dtype == AIMB_BF16 && ((T == 8 && heads % 2 == 0) || T == 16) && !g_temporal_simt) return attn_temporal_fwd_mma(qkv, o, B, T, n, heads, s);
+    if (dtype == AIMB_BF16 && ((T == 8 && heads % 2 == 0) || T == 16 || T == 32) && !g_temporal_simt) return attn_temporal_fwd_mma(qkv, o, B, T, n, heads, s);
     if (dtype == AIMB_BF16) return temporal_fwd_T<bf16>(qkv, o, B, T, n, heads, s);
     if (dtype == AIMB_F32) return temporal_fwd_T<float>(qkv, o, B, T, n, heads, s);
     return AIMB_ERR_ARG;
@@ -556,7 +556,7 @@ extern "C" int aimb_attn_temporal_bwd(const void* qkv, const void* d_o, void* d_
     if (!qkv || !d_o || !d_qkv || B < 0 || T <= 0 || n <= 0 || heads <= 0) return AIMB_ERR_ARG;
     if (B == 0) return AIMB_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    if (dtype == AIMB_BF16 && ((T == 8 && heads % 2 == 0) || T == 16) && !g_temporal_simt) return attn_temporal_bwd_mma(qkv, d_o, d_qkv, B, T, n, heads, s);
+    if (dtype == AIMB_BF16 && ((T == 8 && heads % 2 == 0) || T == 16 || T == 32) && !g_temporal_simt) return attn_temporal_bwd_mma(qkv, d_o, d_qkv, B, T, n, heads, s);
     if (dtype == AIMB_BF16) return temporal_bwd_T<bf16>(qkv, d_o, d_qkv, B, T, n, heads, s);
     if (dtype == AIMB_F32) return temporal_bwd_T<float>(qkv, d_o, d_qkv, B, T, n, heads, s);
     return AIMB_ERR_ARG;

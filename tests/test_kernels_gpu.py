@@ -312,7 +312,7 @@ def test_attn_spatial_fwd_bwd(dt, impl, frames, n, heads):
 
 
 @pytest.mark.parametrize("dt", ["f32", "bf16"])
-@pytest.mark.parametrize("B,T,n,heads", [(2, 8, 197, 2), (1, 16, 17, 1), (1, 32, 5, 2), (2, 4, 17, 2), (1, 8, 33, 12), (2, 8, 9, 3), (2, 16, 50, 3)])
+@pytest.mark.parametrize("B,T,n,heads", [(2, 8, 197, 2), (1, 16, 17, 1), (1, 32, 5, 2), (2, 4, 17, 2), (1, 8, 33, 12), (2, 8, 9, 3), (2, 16, 50, 3), (2, 32, 33, 3)])
 def test_attn_temporal_fwd_bwd(dt, B, T, n, heads):
     lib = _lib()
     Tt = DT[dt]
