@@ -169,7 +169,7 @@ class Trainer:
         self.hw = (0.01 * torch.randn(NUM_CLASSES, MODEL["width"], generator=g)).to(device).requires_grad_(True)
         self.hb = torch.zeros(NUM_CLASSES).to(device).requires_grad_(True)   # I3DHead init (i3d_head.py:49-51)
         self.world = world
-        self.sync = aimb200.GradSync(bucket_blocks=3) if world > 1 else None
+        self.sync = aimb200.GradSync(bucket_blocks=int(os.environ.get("AIMB200_BUCKET_BLOCKS", "3"))) if world > 1 else None
         if self.sync is not None:
             self.backbone.attach_grad_sync(self.sync)
         decay = [p for n, p in self.backbone.named_parameters() if p.requires_grad and "Adapter" in n and n.endswith("weight")]
