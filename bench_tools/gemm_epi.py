@@ -59,6 +59,9 @@ def t(N, K, kind, mode, bn=0, iters=12, do_flush=True, skip=0):
 
 modes = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [1, 3]
 skips = [int(x) for x in os.environ.get('SKIPS', '0').split(',')]
+if os.environ.get('DIRECT'):   # 0 never / 1 auto (K >= 512) / 2 always: the register-store epilogue
+    L.aimb_debug_direct_epilogue.argtypes = [ctypes.c_int]
+    L.aimb_debug_direct_epilogue(int(os.environ['DIRECT']))
 bns = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0]
 cases = [(2304, 768, "bias"), (768, 768, "bias"), (768, 768, "res1"), (768, 768, "none"), (3072, 768, "qgelu+pre"), (3072, 768, "dqgelu"),
          (768, 3072, "res1"), (768, 3072, "none"), (768, 2304, "none"), (192, 768, "gelu+pre"), (192, 768, "dgelu+cs"), (768, 192, "res1"),
