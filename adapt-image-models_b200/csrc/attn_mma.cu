@@ -475,7 +475,10 @@ int attn_spatial_bwd_mma(const void* qkv, const void* o, const void* d_o, const 
     static const int dbg_nw = getenv("AIMB200_ATTN_BWD_NW") ? atoi(getenv("AIMB200_ATTN_BWD_NW")) : 0;   // bench_tools only
     if (dbg_nw == 7) return bwd_launch<7>(qkv, o, d_o, lse, d_qkv, frames, n, heads, smem, s);
     if (dbg_nw == 9) return bwd_launch<9>(qkv, o, d_o, lse, d_qkv, frames, n, heads, smem, s);
-    if (nwarps <= 13) return bwd_launch<13>(qkv, o, d_o, lse, d_qkv, frames, n, heads, smem, s);
+    // 9..13 row tiles (n = 197): 7 warps x 2 passes with the full 255-register budget measured 168 us vs 172 us for 13
+    // warps capped at 128 registers (the kernel's time is set by ldmatrix + HMMA + issue work, not by occupancy)
+    if (dbg_nw == 13) return bwd_launch<13>(qkv, o, d_o, lse, d_qkv, frames, n, heads, smem, s);
+    if (nwarps <= 13) return bwd_launch<7>(qkv, o, d_o, lse, d_qkv, frames, n, heads, smem, s);
     return bwd_launch<9>(qkv, o, d_o, lse, d_qkv, frames, n, heads, smem, s);   // two passes (three beyond n = 288)
 }
 
