@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libaimb200.so")
 
 F32, BF16, U8 = 0, 1, 2
 ACT_NONE, ACT_QUICKGELU, ACT_GELU = 0, 1, 2
-IMPL_AUTO, IMPL_SIMT = 0, 1
+IMPL_AUTO, IMPL_SIMT, IMPL_MMA = 0, 1, 2
 
 _ERR = {-1: "AIMB_ERR_ARG (bad shape/alignment/null)", -2: "AIMB_ERR_CUDA", -3: "AIMB_ERR_UNSUPPORTED",
         -4: "AIMB_ERR_DRIVER (cuTensorMapEncodeTiled)"}
@@ -88,6 +88,10 @@ def load():
     lib.aimb_debug_cta_mode.restype = None
     lib.aimb_debug_set_pdl.argtypes = [C.c_int]
     lib.aimb_debug_set_pdl.restype = None
+    lib.aimb_debug_attn_mode.argtypes = [C.c_int]
+    lib.aimb_debug_attn_mode.restype = None
+    if os.environ.get("AIMB200_ATTN", "tc") == "mma":       # A/B switch: legacy mma.sync spatial attention
+        lib.aimb_debug_attn_mode(1)
     # programmatic dependent launch: every kernel implements the protocol (tests pass with it), but inside the captured
     # step it measured neutral (17.12 vs 17.09 ms) -> opt-in
     lib.aimb_debug_set_pdl(1 if os.environ.get("AIMB200_PDL", "0") == "1" else 0)

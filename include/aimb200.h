@@ -40,6 +40,7 @@ extern "C" {
 
 #define AIMB_IMPL_AUTO 0 /* bf16 -> tensor-core kernels, f32 -> SIMT kernels */
 #define AIMB_IMPL_SIMT 1 /* force the SIMT kernel (debug / cross-check) */
+#define AIMB_IMPL_MMA 2  /* attention only: force the mma.sync kernel instead of the tcgen05 one (cross-check) */
 
 /* GEMM epilogue, applied per output element (m, n) of the fp32 accumulator `acc`:
  *   v = acc + bias[n] * (bias_rowscaled ? row_scale[m % row_mod] : 1)
