@@ -12,6 +12,7 @@ int attn_spatial_bwd_mma(const void* qkv, const void* o, const void* d_o, const 
 // attn_tc.cu: tcgen05 / TMEM / TMA kernels (n <= 256)
 bool attn_spatial_tc_supported(int n, int heads);
 int attn_spatial_fwd_tc(const void* qkv, void* o, float* lse, int frames, int n, int heads, cudaStream_t s);
+void attn_tc_set_timeline(long long* p);
 }  // namespace aimb
 
 namespace aimb { int g_pdl_enabled = 1; }
@@ -21,6 +22,8 @@ using namespace aimb;
 extern "C" void aimb_debug_set_pdl(int on) { g_pdl_enabled = on; }
 static int g_attn_mode = 0;   // 0: tcgen05 kernels where they apply, 1: mma.sync kernels only (cross-check / A-B timing)
 extern "C" void aimb_debug_attn_mode(int mode) { g_attn_mode = mode; }
+// bench_tools only: device buffer (>= 16 int64 per unit of CTA 0) that receives clock64 stamps of the pipeline events
+extern "C" void aimb_debug_attn_timeline(void* dev_buf) { attn_tc_set_timeline((long long*)dev_buf); }
 
 extern "C" int aimb_version(void) { return 100; }
 

@@ -57,16 +57,22 @@ struct FwdBars {
 
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, bf16* __restrict__ o, float* __restrict__ lse, const int n,
-                   const int heads, const int D, const int nprob, const int MT, const int NKP, const int NST) {
+                   const int heads, const int D, const int nprob, const int MT, const int NKP, const int NST, long long* __restrict__ tl) {
     pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
     const int KB = (NKP + BOXR - 1) / BOXR;                 // 64-row boxes of K (and of V)
     const int STAGE_B = MT * QTILE_B + 2 * KB * BOXB;
+    // bench_tools only: event timeline of CTA 0 (clock64 per unit and event), see bench_tools/attn_tc_timeline.py
+    auto mark = [&](int u, int ev) { if (tl && blockIdx.x == 0 && (threadIdx.x & 31) == 0) tl[u * 16 + ev] = clock64(); };
     FwdBars* bars = reinterpret_cast<FwdBars*>(smem + NST * STAGE_B);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = ptx::warp_id_uniform(), lane = threadIdx.x & 31;
     const int nloc = (nprob - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // problems of this CTA
     const int U = nloc * MT;                                                             // units of this CTA
+    // TMEM columns: S / P of warpgroup g at g * RS; O in its own 64 columns when both score regions leave room for it
+    // (then the next S may be issued without waiting for the output to be read), else in columns 128..191 of the region
+    const bool OSEP = 2 * NKP + HD <= 512;
+    const int RS = OSEP ? NKP : 256;
     if (threadIdx.x == 0) {
         ptx::prefetch_tmap(&tm);
         for (int i = 0; i < 2; ++i) {
@@ -81,69 +87,74 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, bf16* __restrict__ o,
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
-    const uint32_t tmem_base = bars->tmem_ptr;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, bars->tmem_ptr, 0);      // warp-uniform for the MMA issue path
     pdl_wait();
     if (warp == 0) {
-        if (lane == 0) {
-            for (int k = 0; k < nloc; ++k) {
-                const int pi = blockIdx.x + k * gridDim.x;
-                const int f = pi / heads, h = pi - f * heads;
-                const int st = k % NST;
-                const uint32_t r = (uint32_t)(k / NST) & 1u;
-                uint8_t* sq = smem + st * STAGE_B;
-                uint8_t* sk = sq + MT * QTILE_B;
-                uint8_t* sv = sk + KB * BOXB;
-                ptx::mbar_wait(&bars->qk_empty[st], r ^ 1u);
-                ptx::mbar_arrive_expect_tx(&bars->qk_full[st], (uint32_t)((2 * MT + KB) * BOXB));
-                for (int b = 0; b < KB; ++b) ptx::tma_load_3d(sk + b * BOXB, &tm, &bars->qk_full[st], D + h * HD, b * BOXR, f);
-                for (int b = 0; b < 2 * MT; ++b) ptx::tma_load_3d(sq + b * BOXB, &tm, &bars->qk_full[st], h * HD, b * BOXR, f);
-                ptx::mbar_wait(&bars->v_empty[st], r ^ 1u);
-                ptx::mbar_arrive_expect_tx(&bars->v_full[st], (uint32_t)(KB * BOXB));
-                for (int b = 0; b < KB; ++b) ptx::tma_load_3d(sv + b * BOXB, &tm, &bars->v_full[st], 2 * D + h * HD, b * BOXR, f);
-            }
+        // ---- TMA producer (all lanes run the loop, one elected lane issues: see ptx.cuh "warp-uniform issue")
+        for (int k = 0; k < nloc; ++k) {
+            const int pi = blockIdx.x + k * gridDim.x;
+            const int f = pi / heads, h = pi - f * heads;
+            const int st = k % NST;
+            const uint32_t r = (uint32_t)(k / NST) & 1u;
+            uint8_t* sq = smem + st * STAGE_B;
+            uint8_t* sk = sq + MT * QTILE_B;
+            uint8_t* sv = sk + KB * BOXB;
+            ptx::mbar_wait(&bars->qk_empty[st], r ^ 1u);
+            ptx::mbar_arrive_expect_tx_e(&bars->qk_full[st], (uint32_t)((2 * MT + KB) * BOXB));
+            for (int b = 0; b < KB; ++b) ptx::tma_load_3d_e(sk + b * BOXB, &tm, &bars->qk_full[st], D + h * HD, b * BOXR, f);
+            for (int b = 0; b < 2 * MT; ++b) ptx::tma_load_3d_e(sq + b * BOXB, &tm, &bars->qk_full[st], h * HD, b * BOXR, f);
+            ptx::mbar_wait(&bars->v_empty[st], r ^ 1u);
+            ptx::mbar_arrive_expect_tx_e(&bars->v_full[st], (uint32_t)(KB * BOXB));
+            for (int b = 0; b < KB; ++b) ptx::tma_load_3d_e(sv + b * BOXB, &tm, &bars->v_full[st], 2 * D + h * HD, b * BOXR, f);
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc_s = ptx::umma_idesc_bf16(128, NKP);
-            const uint32_t idesc_o = ptx::umma_idesc_bf16(128, HD, 0, 1);
-            const int KS = NKP / 16;
-            auto issue_s = [&](int u) {
-                const int k = u / MT, mt = u - k * MT, st = k % NST, g = u & 1, it = u >> 1;
-                if (it > 0) ptx::mbar_wait(&bars->o_empty[g], (uint32_t)(it - 1) & 1u);   // region g drained by its warpgroup
-                if (mt == 0) ptx::mbar_wait(&bars->qk_full[st], (uint32_t)(k / NST) & 1u);
-                ptx::tc_fence_after();
-                const uint32_t sq = ptx::smem_u32(smem + st * STAGE_B);
-                const uint64_t adesc = ptx::umma_desc_kmajor_sw128(sq + mt * QTILE_B);
-                const uint64_t bdesc = ptx::umma_desc_kmajor_sw128(sq + MT * QTILE_B);
-                const uint32_t d_tmem = tmem_base + g * 256;
+        // ---- MMA issuer (warp-uniform)
+        const uint32_t idesc_s = ptx::umma_idesc_bf16(128, NKP);
+        const uint32_t idesc_o = ptx::umma_idesc_bf16(128, HD, 0, 1);
+        const int KS = NKP / 16;
+        const uint32_t smem0 = ptx::smem_u32(smem);
+        auto issue_s = [&](int u) {
+            const int k = u / MT, mt = u - k * MT, st = k % NST, g = u & 1, it = u >> 1;
+            if (!OSEP && it > 0) ptx::mbar_wait(&bars->o_empty[g], (uint32_t)(it - 1) & 1u);   // O(u-2) lives inside this region
+            if (mt == 0) ptx::mbar_wait(&bars->qk_full[st], (uint32_t)(k / NST) & 1u);
+            ptx::tc_fence_after();
+            const uint32_t sq = smem0 + st * STAGE_B;
+            const uint64_t adesc = ptx::umma_desc_kmajor_sw128(sq + mt * QTILE_B);
+            const uint64_t bdesc = ptx::umma_desc_kmajor_sw128(sq + MT * QTILE_B);
+            const uint32_t d_tmem = tmem_base + g * RS;
 #pragma unroll
-                for (int kk = 0; kk < HD / 16; ++kk) ptx::umma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc_s, kk ? 1u : 0u);
-                ptx::umma_commit(&bars->s_full[g]);
-                if (mt == MT - 1) ptx::umma_commit(&bars->qk_empty[st]);
-            };
-            auto issue_pv = [&](int u) {
-                const int k = u / MT, mt = u - k * MT, st = k % NST, g = u & 1, it = u >> 1;
-                ptx::mbar_wait(&bars->p_full[g], (uint32_t)it & 1u);
-                if (mt == 0) ptx::mbar_wait(&bars->v_full[st], (uint32_t)(k / NST) & 1u);
-                ptx::tc_fence_after();
-                const uint32_t sv = ptx::smem_u32(smem + st * STAGE_B + MT * QTILE_B + KB * BOXB);
-                const uint32_t p_tmem = tmem_base + g * 256;
-                const uint32_t d_tmem = p_tmem + 128;
-                for (int j = 0; j < KS; ++j)
-                    ptx::umma_bf16_ts(d_tmem, p_tmem + j * 8, ptx::umma_desc_mnmajor_sw128(sv + j * 2048, BOXB), idesc_o, j ? 1u : 0u);
-                ptx::umma_commit(&bars->o_full[g]);
-                if (mt == MT - 1) ptx::umma_commit(&bars->v_empty[st]);
-            };
-            if (U > 0) issue_s(0);
-            if (U > 1) issue_s(1);
-            for (int u = 0; u < U; ++u) {
-                issue_pv(u);
-                if (u + 2 < U) issue_s(u + 2);
-            }
+            for (int kk = 0; kk < HD / 16; ++kk) ptx::umma_bf16_e(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc_s, kk ? 1u : 0u);
+            ptx::umma_commit_e(&bars->s_full[g]);
+            mark(u, 10);
+            if (mt == MT - 1) ptx::umma_commit_e(&bars->qk_empty[st]);
+        };
+        auto issue_pv = [&](int u) {
+            const int k = u / MT, mt = u - k * MT, st = k % NST, g = u & 1, it = u >> 1;
+            ptx::mbar_wait(&bars->p_full[g], (uint32_t)it & 1u);
+            mark(u, 8);
+            if (OSEP && u > 0) ptx::mbar_wait(&bars->o_empty[g ^ 1], (uint32_t)((u - 1) >> 1) & 1u);   // shared O columns drained
+            if (mt == 0) ptx::mbar_wait(&bars->v_full[st], (uint32_t)(k / NST) & 1u);
+            ptx::tc_fence_after();
+            const uint64_t vdesc = ptx::umma_desc_mnmajor_sw128(smem0 + st * STAGE_B + MT * QTILE_B + KB * BOXB, BOXB);
+            const uint32_t p_tmem = tmem_base + g * RS;
+            const uint32_t d_tmem = OSEP ? tmem_base + 448 : p_tmem + 128;
+#pragma unroll 4
+            for (int j = 0; j < KS; ++j)       // 16 keys per MMA: +8 TMEM columns of P, +2048 B of V (two 8-row swizzle atoms)
+                ptx::umma_bf16_ts_e(d_tmem, p_tmem + j * 8, vdesc + (uint64_t)(j * 128), idesc_o, j ? 1u : 0u);
+            ptx::umma_commit_e(&bars->o_full[g]);
+            mark(u, 9);
+            if (mt == MT - 1) ptx::umma_commit_e(&bars->v_empty[st]);
+        };
+        if (U > 0) issue_s(0);
+        if (U > 1) issue_s(1);
+        for (int u = 0; u < U; ++u) {
+            issue_pv(u);
+            if (u + 2 < U) issue_s(u + 2);
         }
     } else if (warp >= 4) {
         const int g = (warp - 4) >> 2, wq = warp & 3;
-        const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16) + g * 256;
+        const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16) + g * RS;
+        const uint32_t orow = tmem_base + ((uint32_t)(wq * 32) << 16) + (OSEP ? 448 : g * RS + 128);
         const int NCH = (n + 31) >> 5;
         for (int it = 0;; ++it) {
             const int u = 2 * it + g;
@@ -155,48 +166,60 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, bf16* __restrict__ o,
             const bool active = (mt * 128 + wq * 32) < n;        // warp-uniform: does this warp own any real query row
             ptx::mbar_wait(&bars->s_full[g], (uint32_t)it & 1u);
             ptx::tc_fence_after();
+            if (wq == 0) mark(u, 0);
             float mx = -INFINITY, sum = 0.f;
             uint32_t va[32], vb[32];
             if (active) {
-                // ---- pass 1: row maximum
+                // ---- pass 1: row maximum (tail chunk: only the 8-column groups that hold real keys)
+                auto rmax = [&](const uint32_t (&v)[32], int c) {
+                    if ((c + 1) * 32 <= n) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if (c * 32 + q * 8 < n) {
+#pragma unroll
+                                for (int j = q * 8; j < q * 8 + 8; ++j) if (c * 32 + j < n) mx = fmaxf(mx, __uint_as_float(v[j]));
+                            }
+                        }
+                    }
+                };
                 ptx::tmem_ld_32x32b_x32(trow, va);
                 for (int c = 0; c < NCH; c += 2) {
                     ptx::tmem_wait_ld();
                     if (c + 1 < NCH) ptx::tmem_ld_32x32b_x32(trow + (c + 1) * 32, vb);
-                    if ((c + 1) * 32 <= n) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(va[j]));
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) if (c * 32 + j < n) mx = fmaxf(mx, __uint_as_float(va[j]));
-                    }
+                    rmax(va, c);
                     if (c + 1 < NCH) {
                         ptx::tmem_wait_ld();
                         if (c + 2 < NCH) ptx::tmem_ld_32x32b_x32(trow + (c + 2) * 32, va);
-                        if ((c + 2) * 32 <= n) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(vb[j]));
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) if ((c + 1) * 32 + j < n) mx = fmaxf(mx, __uint_as_float(vb[j]));
-                        }
+                        rmax(vb, c + 1);
                     }
                 }
+                if (wq == 0) mark(u, 1);
                 // ---- pass 2: p = exp2((s - max) * scale * log2 e); P (bf16) overwrites the consumed S columns
                 const float mb = mx * SCALE_LOG2;
                 uint32_t pk[16];
                 auto expo = [&](const uint32_t (&v)[32], int c) {
                     const bool tail = (c + 1) * 32 > n;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float p0 = ex2_ftz(fmaf(__uint_as_float(v[2 * j]), SCALE_LOG2, -mb));
-                        float p1 = ex2_ftz(fmaf(__uint_as_float(v[2 * j + 1]), SCALE_LOG2, -mb));
-                        if (tail) {
-                            if (c * 32 + 2 * j >= n) p0 = 0.f;
-                            if (c * 32 + 2 * j + 1 >= n) p1 = 0.f;
+                    for (int q = 0; q < 4; ++q) {
+                        if (tail && c * 32 + q * 8 >= n) {           // warp-uniform: nothing but padding in this group
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) pk[q * 4 + j] = 0u;
+                            continue;
                         }
-                        sum += p0 + p1;
-                        pk[j] = pack_bf16(p0, p1);
+#pragma unroll
+                        for (int j = q * 4; j < q * 4 + 4; ++j) {
+                            float p0 = ex2_ftz(fmaf(__uint_as_float(v[2 * j]), SCALE_LOG2, -mb));
+                            float p1 = ex2_ftz(fmaf(__uint_as_float(v[2 * j + 1]), SCALE_LOG2, -mb));
+                            if (tail) {
+                                if (c * 32 + 2 * j >= n) p0 = 0.f;
+                                if (c * 32 + 2 * j + 1 >= n) p1 = 0.f;
+                            }
+                            sum += p0 + p1;
+                            pk[j] = pack_bf16(p0, p1);
+                        }
                     }
                     ptx::tmem_st_32x32b_x16(trow + c * 16, pk);
                 };
@@ -216,17 +239,20 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, bf16* __restrict__ o,
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&bars->p_full[g]);
-            // ---- O = P V is accumulated into columns 128..191 of this region
+            if (wq == 0) mark(u, 2);
+            // ---- O = P V
             ptx::mbar_wait(&bars->o_full[g], (uint32_t)it & 1u);
             ptx::tc_fence_after();
+            if (wq == 0) mark(u, 3);
             if (active) {
-                ptx::tmem_ld_32x32b_x32(trow + 128, va);
-                ptx::tmem_ld_32x32b_x32(trow + 160, vb);
+                ptx::tmem_ld_32x32b_x32(orow, va);
+                ptx::tmem_ld_32x32b_x32(orow + 32, vb);
                 ptx::tmem_wait_ld();
             }
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&bars->o_empty[g]);      // the region may take the next S while we store
+            if (lane == 0) ptx::mbar_arrive(&bars->o_empty[g]);      // the output columns may be rewritten while we store
+            if (wq == 0) mark(u, 4);
             if (active && row < n) {
                 const float inv = __fdividef(1.f, sum);
                 uint32_t ob[32];
@@ -240,6 +266,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, bf16* __restrict__ o,
                 for (int q = 0; q < 4; ++q) st_global_v8(op + q * 16, ob + q * 8);
                 if (lse) lse[((int64_t)f * heads + h) * n + row] = mx * SCALE + __logf(sum);
             }
+            if (wq == 0) mark(u, 5);
         }
     }
     ptx::tc_fence_before();
@@ -324,6 +351,9 @@ static int sm_count() {
 
 }  // namespace atc
 
+static long long* g_attn_timeline = nullptr;
+void attn_tc_set_timeline(long long* p) { g_attn_timeline = p; }
+
 bool attn_spatial_tc_supported(int n, int heads) { return n >= 1 && n <= 256 && heads >= 1; }
 
 int attn_spatial_fwd_tc(const void* qkv, void* o, float* lse, int frames, int n, int heads, cudaStream_t s) {
@@ -353,7 +383,7 @@ int attn_spatial_fwd_tc(const void* qkv, void* o, float* lse, int frames, int n,
     const int sms = sm_count();
     const int waves = (nprob + sms - 1) / sms;
     const int grid = (nprob + waves - 1) / waves;
-    launch_k(attn_fwd_tc_kernel, dim3(grid), dim3(FWD_THREADS), (size_t)smem, s, tm, (bf16*)o, lse, n, heads, D, nprob, MT, NKP, NST);
+    launch_k(attn_fwd_tc_kernel, dim3(grid), dim3(FWD_THREADS), (size_t)smem, s, tm, (bf16*)o, lse, n, heads, D, nprob, MT, NKP, NST, g_attn_timeline);
     AIMB_CHECK_LAUNCH();
     return AIMB_OK;
 }

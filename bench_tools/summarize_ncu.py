@@ -74,5 +74,31 @@ def traffic(path):
     print(json.dumps({"source": " ".join(sys.argv[3:]) or path, "avg_dram_bytes_per_launch": avg, "launches": launches}, indent=1))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and sys.argv[1] in ("list", "full", "traffic"):
     {"list": launch_list, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])
+
+
+def stalls(path, top=40):
+    """Per-SASS-instruction stall samples of the first kernel in the report (needs --import-source on)."""
+    out = subprocess.run(['ncu', '-i', path, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hi = [i for i, r in enumerate(rows) if r and r[0] == 'Address'][0]
+    hdr = rows[hi]
+    ix = {h: i for i, h in enumerate(hdr)}
+    data = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+    reasons = [h for h in hdr if h.startswith('stall_') and 'Not Issued' not in h]
+    tot = sum(int(r[ix['# Samples']] or 0) for r in data)
+    print(f"# {rows[0][1][:100]}: {tot} samples, {len(data)} SASS instructions\n")
+    agg = {k: sum(int(r[ix[k]] or 0) for r in data) for k in reasons}
+    print("stall totals: " + ", ".join(f"{k[6:]} {100 * v / max(1, sum(agg.values())):.1f}%" for k, v in sorted(agg.items(), key=lambda kv: -kv[1]) if v))
+    print("\n| # | samples | % | executed | top stall | SASS |\n|---:|---:|---:|---:|---|---|")
+    order = sorted(range(len(data)), key=lambda i: -int(data[i][ix['# Samples']] or 0))[:top]
+    for i in sorted(order):
+        r = data[i]
+        s = int(r[ix['# Samples']] or 0)
+        best = max(reasons, key=lambda k: int(r[ix[k]] or 0))
+        print(f"| {i} | {s} | {100 * s / max(1, tot):.1f} | {r[ix['Instructions Executed']]} | {best[6:]} | `{r[ix['Source']].strip()[:70]}` |")
+
+
+if __name__ == "__main__" and sys.argv[1] == "stalls":
+    stalls(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 40)
