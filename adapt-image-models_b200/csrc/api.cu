@@ -13,6 +13,8 @@ int attn_spatial_bwd_mma(const void* qkv, const void* o, const void* d_o, const 
 bool attn_spatial_tc_supported(int n, int heads);
 int attn_spatial_fwd_tc(const void* qkv, void* o, float* lse, int frames, int n, int heads, cudaStream_t s);
 void attn_tc_set_timeline(long long* p);
+int attn_spatial_bwd_tc(const void* qkv, const void* o, const void* d_o, const float* lse, void* d_qkv, int frames, int n,
+                        int heads, cudaStream_t s);
 }  // namespace aimb
 
 namespace aimb { int g_pdl_enabled = 1; }
@@ -51,6 +53,8 @@ extern "C" int aimb_attn_spatial_bwd(const void* qkv, const void* o, const void*
     if (!qkv || !o || !d_o || !lse || !d_qkv || frames < 0 || n <= 0 || heads <= 0) return AIMB_ERR_ARG;
     if (frames == 0) return AIMB_OK;
     cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == AIMB_BF16 && impl == AIMB_IMPL_AUTO && g_attn_mode == 0 && attn_spatial_tc_supported(n, heads))
+        return attn_spatial_bwd_tc(qkv, o, d_o, lse, d_qkv, frames, n, heads, s);
     if (dtype == AIMB_BF16 && (impl == AIMB_IMPL_AUTO || impl == AIMB_IMPL_MMA))
         return attn_spatial_bwd_mma(qkv, o, d_o, lse, d_qkv, frames, n, heads, s);
     return attn_spatial_bwd_simt_dispatch(qkv, o, d_o, lse, d_qkv, frames, n, heads, dtype, s);

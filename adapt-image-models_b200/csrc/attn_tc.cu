@@ -277,6 +277,315 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, bf16* __restrict__ o,
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------ backward
+// attn_bwd_tc_kernel: one (frame, head) problem at a time per persistent CTA, keys on the TMEM lanes ("transposed"
+// score layout), so that both dV = P^T dO and dK = dS^T Q take their left operand without a transpose:
+//   S^T  = K_kb Q_h^T       (SS, 128 keys x Nh queries x 64)      TMEM columns   0..127
+//   dP^T = V_kb dO_h^T      (SS)                                  TMEM columns 128..255
+//   math : p = exp2(s * scale * log2e - lse2[q]),  ds = p * (dp - delta[q])      (thread = one key lane)
+//          P^T (bf16) -> TMEM columns 0..63 (over S^T);  dS^T (bf16) -> shared memory, 128B-swizzled [key][64 q] boxes
+//   dV_kb += P^T dO_h       (TS: A = P^T from TMEM, B = dO MN-major)               columns 256..319
+//   dK_kb += dS^T Q_h       (SS: A = the dS^T boxes read K-major,  B = Q MN-major)  columns 320..383
+//   dQ_h  += dS K_kb        (SS: A = the SAME dS^T boxes read MN-major, B = K MN-major)   columns 384 + 64 h
+// for the key blocks kb (128 lanes each) and query halves h (Nh = 128, then the rest) of the problem: all 512 TMEM
+// columns are in use, nothing is reduced through global memory and there are no atomics.  delta = rowsum(dO o O) and
+// lse * log2e of the NEXT problem are prepared by two otherwise idle warps while the current problem computes; K, Q
+// and dO are double-buffered in shared memory (V single): 7 x 26 KB + 32 KB of dS^T at n = 197.
+constexpr int BWD_THREADS = 384;
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct BwdBars {
+    uint64_t in_full[2], in_empty[2], v_full, v_empty, dl_full[2];
+    uint64_t sdp_full, pds_full, dvk_full, acc_empty, dq_full, dq_empty;
+    uint32_t tmem_ptr;
+};
+
+__device__ __forceinline__ float dot8(const uint4& a, const uint4& b) {
+    const __nv_bfloat162* x = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* y = reinterpret_cast<const __nv_bfloat162*>(&b);
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 u = __bfloat1622float2(x[j]), v = __bfloat1622float2(y[j]);
+        acc = fmaf(u.x, v.x, acc);
+        acc = fmaf(u.y, v.y, acc);
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                   const bf16* __restrict__ o, const float* __restrict__ lse, bf16* __restrict__ dqkv, const int n,
+                   const int heads, const int D, const int nprob, const int NQP, const int NSTG) {
+    pdl_trigger();
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int MATB = NQP * 128;                       // one [NQP rows][64] bf16 operand
+    const int BR = NQP >> 1;                          // TMA box rows (two boxes per operand)
+    const int KBL = (n + 127) >> 7;                   // key blocks (TMEM lane blocks)
+    const int NH = (NQP + 127) >> 7;                  // query halves
+    // shared memory: K[NSTG] Q[NSTG] dO[NSTG] V dS^T(32 KB) dl[2][2][256] barriers   (NSTG = 2 while it fits: n <= 208)
+    uint8_t* sK = smem;
+    uint8_t* sQ = smem + NSTG * MATB;
+    uint8_t* sG = smem + 2 * NSTG * MATB;
+    uint8_t* sV = smem + 3 * NSTG * MATB;
+    uint8_t* sS = smem + (3 * NSTG + 1) * MATB;
+    auto stage_of = [&](int k) { return NSTG == 2 ? (k & 1) : 0; };
+    auto phase_of = [&](int k) { return (uint32_t)(NSTG == 2 ? (k >> 1) : k) & 1u; };
+    float* dl = reinterpret_cast<float*>(sS + 32768);
+    BwdBars* bars = reinterpret_cast<BwdBars*>(sS + 32768 + 4096);
+    const int warp = ptx::warp_id_uniform(), lane = threadIdx.x & 31;
+    const int nloc = (nprob - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    if (threadIdx.x == 0) {
+        ptx::prefetch_tmap(&tmQKV);
+        ptx::prefetch_tmap(&tmDO);
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&bars->in_full[i], 1); ptx::mbar_init(&bars->in_empty[i], 1); ptx::mbar_init(&bars->dl_full[i], 2);
+        }
+        ptx::mbar_init(&bars->v_full, 1); ptx::mbar_init(&bars->v_empty, 1);
+        ptx::mbar_init(&bars->sdp_full, 1); ptx::mbar_init(&bars->pds_full, 8);
+        ptx::mbar_init(&bars->dvk_full, 1); ptx::mbar_init(&bars->acc_empty, 8);
+        ptx::mbar_init(&bars->dq_full, 1); ptx::mbar_init(&bars->dq_empty, 8);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) ptx::tmem_alloc<512>(&bars->tmem_ptr);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tb = __shfl_sync(0xffffffffu, bars->tmem_ptr, 0);
+    pdl_wait();
+    if (warp == 0) {
+        // ---- TMA producer
+        for (int k = 0; k < nloc; ++k) {
+            const int pi = blockIdx.x + k * gridDim.x;
+            const int f = pi / heads, h = pi - f * heads;
+            const int st = stage_of(k);
+            ptx::mbar_wait(&bars->in_empty[st], phase_of(k) ^ 1u);
+            ptx::mbar_arrive_expect_tx_e(&bars->in_full[st], (uint32_t)(3 * MATB));
+            for (int b = 0; b < 2; ++b) {
+                ptx::tma_load_3d_e(sK + st * MATB + b * BR * 128, &tmQKV, &bars->in_full[st], D + h * HD, b * BR, f);
+                ptx::tma_load_3d_e(sQ + st * MATB + b * BR * 128, &tmQKV, &bars->in_full[st], h * HD, b * BR, f);
+                ptx::tma_load_3d_e(sG + st * MATB + b * BR * 128, &tmDO, &bars->in_full[st], h * HD, b * BR, f);
+            }
+            ptx::mbar_wait(&bars->v_empty, ((uint32_t)k & 1u) ^ 1u);
+            ptx::mbar_arrive_expect_tx_e(&bars->v_full, (uint32_t)MATB);
+            for (int b = 0; b < 2; ++b)
+                ptx::tma_load_3d_e(sV + b * BR * 128, &tmQKV, &bars->v_full, 2 * D + h * HD, b * BR, f);
+        }
+    } else if (warp == 1) {
+        // ---- MMA issuer (warp-uniform)
+        const uint32_t idesc_acc = ptx::umma_idesc_bf16(128, HD, 0, 1);     // dV, dK: A K-major (TMEM / smem), B MN-major
+        const uint32_t idesc_dq = ptx::umma_idesc_bf16(128, HD, 1, 1);      // dQ: A and B MN-major
+        const uint32_t aK = ptx::smem_u32(sK), aQ = ptx::smem_u32(sQ), aG = ptx::smem_u32(sG), aV = ptx::smem_u32(sV),
+                       aS = ptx::smem_u32(sS);
+        uint32_t s = 0, c = 0;                                              // step and key-block counters (barrier phases)
+        for (int k = 0; k < nloc; ++k) {
+            const int st = stage_of(k);
+            ptx::mbar_wait(&bars->in_full[st], phase_of(k));
+            for (int kb = 0; kb < KBL; ++kb) {
+                const int KSkb = (min(128, NQP - kb * 128)) >> 4;           // 16-key steps of this key block
+                for (int h = 0; h < NH; ++h, ++s) {
+                    const int Nh = min(128, NQP - h * 128);
+                    const int KSh = Nh >> 4;
+                    const uint32_t idesc_s = ptx::umma_idesc_bf16(128, Nh);
+                    ptx::tc_fence_after();
+                    {   // S^T = K_kb Q_h^T, dP^T = V_kb dO_h^T
+                        const uint64_t ka = ptx::umma_desc_kmajor_sw128(aK + st * MATB + kb * 16384);
+                        const uint64_t qb = ptx::umma_desc_kmajor_sw128(aQ + st * MATB + h * 16384);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) ptx::umma_bf16_e(tb, ka + 2 * kk, qb + 2 * kk, idesc_s, kk ? 1u : 0u);
+                        if (kb == 0 && h == 0) { ptx::mbar_wait(&bars->v_full, (uint32_t)k & 1u); ptx::tc_fence_after(); }
+                        const uint64_t va = ptx::umma_desc_kmajor_sw128(aV + kb * 16384);
+                        const uint64_t gb = ptx::umma_desc_kmajor_sw128(aG + st * MATB + h * 16384);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) ptx::umma_bf16_e(tb + 128, va + 2 * kk, gb + 2 * kk, idesc_s, kk ? 1u : 0u);
+                        ptx::umma_commit_e(&bars->sdp_full);
+                    }
+                    ptx::mbar_wait(&bars->pds_full, s & 1u);                 // P^T in TMEM, dS^T in shared memory
+                    if (h == 0 && c > 0) ptx::mbar_wait(&bars->acc_empty, (c - 1) & 1u);      // dV / dK columns drained
+                    if (kb == 0 && h == 0 && k > 0) ptx::mbar_wait(&bars->dq_empty, (uint32_t)(k - 1) & 1u);
+                    ptx::tc_fence_after();
+                    const uint64_t g_mn = ptx::umma_desc_mnmajor_sw128(aG + st * MATB + h * 16384, 16384);
+                    const uint64_t q_mn = ptx::umma_desc_mnmajor_sw128(aQ + st * MATB + h * 16384, 16384);
+                    const uint64_t k_mn = ptx::umma_desc_mnmajor_sw128(aK + st * MATB + kb * 16384, 16384);
+                    const uint64_t s_k = ptx::umma_desc_kmajor_sw128(aS);
+                    const uint64_t s_mn = ptx::umma_desc_mnmajor_sw128(aS, 16384);
+#pragma unroll 4
+                    for (int j = 0; j < KSh; ++j)        // dV_kb += P^T dO_h : 16 queries per MMA
+                        ptx::umma_bf16_ts_e(tb + 256, tb + j * 8, g_mn + (uint64_t)(j * 128), idesc_acc, (h | j) ? 1u : 0u);
+#pragma unroll 4
+                    for (int j = 0; j < KSh; ++j)        // dK_kb += dS^T Q_h : A = dS^T boxes, K-major (64 queries per box)
+                        ptx::umma_bf16_e(tb + 320, s_k + (uint64_t)((j >> 2) * 1024 + (j & 3) * 2), q_mn + (uint64_t)(j * 128),
+                                         idesc_acc, (h | j) ? 1u : 0u);
+#pragma unroll 4
+                    for (int j = 0; j < KSkb; ++j)       // dQ_h += dS K_kb : A = the same boxes, MN-major (16 keys per MMA)
+                        ptx::umma_bf16_e(tb + 384 + h * 64, s_mn + (uint64_t)(j * 128), k_mn + (uint64_t)(j * 128), idesc_dq,
+                                         (kb | j) ? 1u : 0u);
+                    if (h == NH - 1) { ptx::umma_commit_e(&bars->dvk_full); ++c; }
+                }
+            }
+            ptx::umma_commit_e(&bars->dq_full);
+            ptx::umma_commit_e(&bars->in_empty[st]);
+            ptx::umma_commit_e(&bars->v_empty);
+        }
+    } else if (warp < 4) {
+        // ---- delta / lse warps: delta[q] = sum_d dO[q,d] O[q,d] and lse2[q] = lse[q] * log2(e) of problem k (one ahead)
+        const int t = (warp - 2) * 32 + lane;
+        for (int k = 0; k < nloc; ++k) {
+            const int pi = blockIdx.x + k * gridDim.x;
+            const int f = pi / heads, h = pi - f * heads;
+            const int st = stage_of(k);
+            ptx::mbar_wait(&bars->in_full[st], phase_of(k));
+            const uint8_t* g = sG + st * MATB;
+            float* l2 = dl + (k & 1) * 512;
+            for (int q = t; q < NQP; q += 64) {
+                float acc = 0.f, lv = INFINITY;           // padded queries: lse2 = +inf -> p = 0
+                if (q < n) {
+                    const uint4* op = reinterpret_cast<const uint4*>(o + ((int64_t)f * n + q) * D + h * HD);
+                    uint4 ov[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) ov[i] = op[i];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        acc += dot8(*reinterpret_cast<const uint4*>(g + q * 128 + ((i ^ (q & 7)) << 4)), ov[i]);
+                    lv = lse[((int64_t)f * heads + h) * n + q] * LOG2E;
+                }
+                l2[q] = lv;
+                l2[256 + q] = acc;
+            }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&bars->dl_full[k & 1]);
+        }
+    } else {
+        // ---- math warps: warp%4 = TMEM lane quadrant, (warp-4)/4 = which half of the query chunks
+        const int wq = warp & 3, ch = (warp - 4) >> 2;
+        const uint32_t trow = tb + ((uint32_t)(wq * 32) << 16);
+        const int r = wq * 32 + lane;                                     // key row inside the key block
+        const uint32_t sS_row = ptx::smem_u32(sS) + r * 128;
+        uint32_t s = 0, c = 0;
+        for (int k = 0; k < nloc; ++k) {
+            const int pi = blockIdx.x + k * gridDim.x;
+            const int f = pi / heads, h_ = pi - f * heads;
+            const float* l2 = dl + (k & 1) * 512;
+            ptx::mbar_wait(&bars->dl_full[k & 1], (uint32_t)(k >> 1) & 1u);
+            for (int kb = 0; kb < KBL; ++kb) {
+                const int key = kb * 128 + r;
+                const bool kvalid = key < n;
+                for (int h = 0; h < NH; ++h, ++s) {
+                    const int Nh = min(128, NQP - h * 128);
+                    const int NC = Nh >> 4;                               // 16-query chunks of this half
+                    const int c0 = ch ? (NC + 1) >> 1 : 0, c1 = ch ? NC : (NC + 1) >> 1;
+                    ptx::mbar_wait(&bars->sdp_full, s & 1u);
+                    ptx::tc_fence_after();
+                    uint32_t pk[4][8];
+#pragma unroll
+                    for (int ci = 0; ci < 4; ++ci) {
+                        const int cc = c0 + ci;
+                        if (cc < c1) {
+                            uint32_t sv[16], dv[16];
+                            ptx::tmem_ld_32x32b_x16(trow + cc * 16, sv);
+                            ptx::tmem_ld_32x32b_x16(trow + 128 + cc * 16, dv);
+                            const float* lq = l2 + h * 128 + cc * 16;
+                            float lv[16], dd[16];
+#pragma unroll
+                            for (int m = 0; m < 4; ++m) {
+                                *reinterpret_cast<float4*>(lv + 4 * m) = *reinterpret_cast<const float4*>(lq + 4 * m);
+                                *reinterpret_cast<float4*>(dd + 4 * m) = *reinterpret_cast<const float4*>(lq + 256 + 4 * m);
+                            }
+                            ptx::tmem_wait_ld();
+                            uint32_t dsp[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                float p0 = ex2_ftz(fmaf(__uint_as_float(sv[2 * j]), SCALE_LOG2, -lv[2 * j]));
+                                float p1 = ex2_ftz(fmaf(__uint_as_float(sv[2 * j + 1]), SCALE_LOG2, -lv[2 * j + 1]));
+                                float d0 = p0 * (__uint_as_float(dv[2 * j]) - dd[2 * j]);
+                                float d1 = p1 * (__uint_as_float(dv[2 * j + 1]) - dd[2 * j + 1]);
+                                if (!kvalid) { p0 = p1 = d0 = d1 = 0.f; }           // padded keys contribute nothing
+                                pk[ci][j] = pack_bf16(p0, p1);
+                                dsp[j] = pack_bf16(d0, d1);
+                            }
+                            // dS^T -> shared memory: box (cc*16)/64 of 64 queries, row r, two 16-byte chunks (128B swizzle)
+                            const uint32_t base = sS_row + ((cc >> 2) << 14);
+                            const int i0 = (cc & 3) * 2;
+                            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(base + (((i0) ^ (r & 7)) << 4)), "r"(dsp[0]),
+                                         "r"(dsp[1]), "r"(dsp[2]), "r"(dsp[3]) : "memory");
+                            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(base + (((i0 + 1) ^ (r & 7)) << 4)), "r"(dsp[4]),
+                                         "r"(dsp[5]), "r"(dsp[6]), "r"(dsp[7]) : "memory");
+                        }
+                    }
+                    // every math warp has read its S^T columns: P^T may now overwrite them
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+                    for (int ci = 0; ci < 4; ++ci)
+                        if (c0 + ci < c1) ptx::tmem_st_32x32b_x8(trow + (c0 + ci) * 8, pk[ci]);
+                    ptx::tmem_wait_st();
+                    ptx::fence_proxy_async();
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&bars->pds_full);
+                    if (h == NH - 1) {
+                        // ---- dV_kb, dK_kb complete: this thread stores 32 of the 64 columns of its key row
+                        ptx::mbar_wait(&bars->dvk_full, c & 1u);
+                        ++c;
+                        ptx::tc_fence_after();
+                        uint32_t a[32], b[32];
+                        ptx::tmem_ld_32x32b_x32(trow + 256 + ch * 32, a);
+                        ptx::tmem_ld_32x32b_x32(trow + 320 + ch * 32, b);
+                        ptx::tmem_wait_ld();
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(&bars->acc_empty);
+                        if (kvalid) {
+                            uint32_t ov[16], ok[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                ov[j] = pack_bf16(__uint_as_float(a[2 * j]), __uint_as_float(a[2 * j + 1]));
+                                ok[j] = pack_bf16(__uint_as_float(b[2 * j]) * SCALE, __uint_as_float(b[2 * j + 1]) * SCALE);
+                            }
+                            bf16* row = dqkv + ((int64_t)f * n + key) * (3 * D) + h_ * HD + ch * 32;
+                            st_global_v8(row + D, ok);
+                            st_global_v8(row + D + 16, ok + 8);
+                            st_global_v8(row + 2 * D, ov);
+                            st_global_v8(row + 2 * D + 16, ov + 8);
+                        }
+                    }
+                }
+            }
+            // ---- dQ of the whole problem
+            ptx::mbar_wait(&bars->dq_full, (uint32_t)k & 1u);
+            ptx::tc_fence_after();
+            uint32_t qa[32], qb2[32];
+            ptx::tmem_ld_32x32b_x32(trow + 384 + ch * 32, qa);
+            if (NH > 1) ptx::tmem_ld_32x32b_x32(trow + 448 + ch * 32, qb2);
+            ptx::tmem_wait_ld();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&bars->dq_empty);
+#pragma unroll
+            for (int hb = 0; hb < 2; ++hb) {
+                const int q = hb * 128 + r;
+                if (hb < NH && q < n) {
+                    uint32_t oq[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const uint32_t x0 = hb ? qb2[2 * j] : qa[2 * j], x1 = hb ? qb2[2 * j + 1] : qa[2 * j + 1];
+                        oq[j] = pack_bf16(__uint_as_float(x0) * SCALE, __uint_as_float(x1) * SCALE);
+                    }
+                    bf16* row = dqkv + ((int64_t)f * n + q) * (3 * D) + h_ * HD + ch * 32;
+                    st_global_v8(row, oq);
+                    st_global_v8(row + 16, oq + 8);
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        ptx::tmem_dealloc<512>(tb);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -295,8 +604,10 @@ static EncodeTiledFn encode_fn() {
 }
 
 struct Key3 {
-    const void* ptr; int64_t slabs, rows, cols;
-    bool operator==(const Key3& o) const { return ptr == o.ptr && slabs == o.slabs && rows == o.rows && cols == o.cols; }
+    const void* ptr; int64_t slabs, rows, cols; int box_rows;
+    bool operator==(const Key3& o) const {
+        return ptr == o.ptr && slabs == o.slabs && rows == o.rows && cols == o.cols && box_rows == o.box_rows;
+    }
 };
 struct Key3Hash {
     size_t operator()(const Key3& k) const {
@@ -304,15 +615,16 @@ struct Key3Hash {
         h = h * 1000003u ^ std::hash<int64_t>()(k.slabs);
         h = h * 1000003u ^ std::hash<int64_t>()(k.rows);
         h = h * 1000003u ^ std::hash<int64_t>()(k.cols);
+        h = h * 1000003u ^ std::hash<int>()(k.box_rows);
         return h;
     }
 };
 
-// bf16 [slabs, rows, cols] contiguous; box = 64 columns x 64 rows x 1 slab, 128B swizzle, zero fill out of bounds
-static int make_tmap3(CUtensorMap* out, const void* ptr, int64_t slabs, int64_t rows, int64_t cols) {
+// bf16 [slabs, rows, cols] contiguous; box = 64 columns x box_rows rows x 1 slab, 128B swizzle, zero fill out of bounds
+static int make_tmap3(CUtensorMap* out, const void* ptr, int64_t slabs, int64_t rows, int64_t cols, int box_rows = BOXR) {
     static std::mutex mu;
     static std::unordered_map<Key3, CUtensorMap, Key3Hash> cache;
-    Key3 key{ptr, slabs, rows, cols};
+    Key3 key{ptr, slabs, rows, cols, box_rows};
     {
         std::lock_guard<std::mutex> g(mu);
         auto it = cache.find(key);
@@ -322,7 +634,7 @@ static int make_tmap3(CUtensorMap* out, const void* ptr, int64_t slabs, int64_t 
     if (!fn) return AIMB_ERR_DRIVER;
     cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)slabs};
     cuuint64_t gstr[2] = {(cuuint64_t)cols * 2, (cuuint64_t)rows * cols * 2};
-    cuuint32_t box[3] = {64, (cuuint32_t)BOXR, 1};
+    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUtensorMap tmap;
     CUresult r = fn(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstr, box, estr,
@@ -384,6 +696,40 @@ int attn_spatial_fwd_tc(const void* qkv, void* o, float* lse, int frames, int n,
     const int waves = (nprob + sms - 1) / sms;
     const int grid = (nprob + waves - 1) / waves;
     launch_k(attn_fwd_tc_kernel, dim3(grid), dim3(FWD_THREADS), (size_t)smem, s, tm, (bf16*)o, lse, n, heads, D, nprob, MT, NKP, NST, g_attn_timeline);
+    AIMB_CHECK_LAUNCH();
+    return AIMB_OK;
+}
+
+
+int attn_spatial_bwd_tc(const void* qkv, const void* o, const void* d_o, const float* lse, void* d_qkv, int frames, int n,
+                        int heads, cudaStream_t s) {
+    using namespace atc;
+    if (!attn_spatial_tc_supported(n, heads)) return AIMB_ERR_UNSUPPORTED;
+    const int D = heads * HD;
+    if (((uintptr_t)qkv & 15) || ((uintptr_t)o & 15) || ((uintptr_t)d_o & 15) || ((uintptr_t)d_qkv & 31)) return AIMB_ERR_ARG;
+    const int NQP = (n + 15) & ~15;
+    CUtensorMap tq, tg;
+    int rc = make_tmap3(&tq, qkv, frames, n, 3 * (int64_t)D, NQP / 2);
+    if (rc) return rc;
+    rc = make_tmap3(&tg, d_o, frames, n, D, NQP / 2);
+    if (rc) return rc;
+    const int NSTG = (7 * NQP * 128 + 32768 + 4096 + 256 + 1024 <= 227 * 1024) ? 2 : 1;
+    const int smem = (3 * NSTG + 1) * NQP * 128 + 32768 + 4096 + 256 + 1024;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return AIMB_ERR_UNSUPPORTED;
+    if (!attr_set[dev]) {
+        if (cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+            return AIMB_ERR_CUDA;
+        attr_set[dev] = true;
+    }
+    const int nprob = frames * heads;
+    const int sms = sm_count();
+    const int waves = (nprob + sms - 1) / sms;
+    const int grid = (nprob + waves - 1) / waves;
+    launch_k(attn_bwd_tc_kernel, dim3(grid), dim3(BWD_THREADS), (size_t)smem, s, tq, tg, (const bf16*)o, lse, (bf16*)d_qkv, n,
+             heads, D, nprob, NQP, NSTG);
     AIMB_CHECK_LAUNCH();
     return AIMB_OK;
 }

@@ -242,6 +242,13 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
 }
 
 
+
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+
 // ---- warp-uniform issue -------------------------------------------------------------------------------------
 // tcgen05.mma / tcgen05.commit / TMA are uniform-datapath instructions: their operands must sit in uniform registers.
 // Issued from a divergent `if (lane == 0)` region, every operand is first moved there (R2UR) inside a per-thread
