@@ -295,7 +295,7 @@ constexpr int BWD_THREADS = 384;
 constexpr float LOG2E = 1.4426950408889634f;
 
 struct BwdBars {
-    uint64_t in_full[2], in_empty[2], v_full, v_empty, dl_full[2];
+    uint64_t in_full[2], in_empty[2], v_full[2], v_empty[2], dl_full[2];
     uint64_t sdp_full, pds_full, dvk_full, acc_empty, dq_full, dq_empty;
     uint32_t tmem_ptr;
 };
@@ -315,9 +315,11 @@ __device__ __forceinline__ float dot8(const uint4& a, const uint4& b) {
 
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                   const bf16* __restrict__ o, const float* __restrict__ lse, bf16* __restrict__ dqkv, const int n,
-                   const int heads, const int D, const int nprob, const int NQP, const int NSTG) {
+                   const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmV1,
+                   const __grid_constant__ CUtensorMap tmOUT, const bf16* __restrict__ o, const float* __restrict__ lse, const int n,
+                   const int heads, const int D, const int nprob, const int NQP, const int NSTG, long long* __restrict__ tl) {
     pdl_trigger();
+    auto mark = [&](uint32_t s, int ev) { if (tl && blockIdx.x == 0 && (threadIdx.x & 31) == 0) tl[s * 16 + ev] = clock64(); };
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
     const int MATB = NQP * 128;                       // one [NQP rows][64] bf16 operand
@@ -339,10 +341,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     if (threadIdx.x == 0) {
         ptx::prefetch_tmap(&tmQKV);
         ptx::prefetch_tmap(&tmDO);
+        ptx::prefetch_tmap(&tmOUT);
+        ptx::prefetch_tmap(&tmV0);
         for (int i = 0; i < 2; ++i) {
-            ptx::mbar_init(&bars->in_full[i], 1); ptx::mbar_init(&bars->in_empty[i], 1); ptx::mbar_init(&bars->dl_full[i], 2);
+            // in_empty: the MMA warp's commit + the storer thread, once the dQ TMA store has read the boxes staged in K / Q
+            ptx::mbar_init(&bars->in_full[i], 1); ptx::mbar_init(&bars->in_empty[i], 2); ptx::mbar_init(&bars->dl_full[i], 2);
         }
-        ptx::mbar_init(&bars->v_full, 1); ptx::mbar_init(&bars->v_empty, 1);
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&bars->v_full[i], 1); ptx::mbar_init(&bars->v_empty[i], 1); }
         ptx::mbar_init(&bars->sdp_full, 1); ptx::mbar_init(&bars->pds_full, 8);
         ptx::mbar_init(&bars->dvk_full, 1); ptx::mbar_init(&bars->acc_empty, 8);
         ptx::mbar_init(&bars->dq_full, 1); ptx::mbar_init(&bars->dq_empty, 8);
@@ -367,10 +372,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
                 ptx::tma_load_3d_e(sQ + st * MATB + b * BR * 128, &tmQKV, &bars->in_full[st], h * HD, b * BR, f);
                 ptx::tma_load_3d_e(sG + st * MATB + b * BR * 128, &tmDO, &bars->in_full[st], h * HD, b * BR, f);
             }
-            ptx::mbar_wait(&bars->v_empty, ((uint32_t)k & 1u) ^ 1u);
-            ptx::mbar_arrive_expect_tx_e(&bars->v_full, (uint32_t)MATB);
-            for (int b = 0; b < 2; ++b)
-                ptx::tma_load_3d_e(sV + b * BR * 128, &tmQKV, &bars->v_full, 2 * D + h * HD, b * BR, f);
+            // V is single-buffered, in two halves (the 128-row key blocks): half kb is dead after the last dP^T of key block
+            // kb of the previous problem, so its successor streams in one to three steps before it is needed
+            ptx::mbar_wait(&bars->v_empty[0], ((uint32_t)k & 1u) ^ 1u);
+            ptx::mbar_arrive_expect_tx_e(&bars->v_full[0], (uint32_t)(min(NQP, 128) * 128));
+            ptx::tma_load_3d_e(sV, &tmV0, &bars->v_full[0], 2 * D + h * HD, 0, f);
+            if (KBL > 1) {
+                ptx::mbar_wait(&bars->v_empty[1], ((uint32_t)k & 1u) ^ 1u);
+                ptx::mbar_arrive_expect_tx_e(&bars->v_full[1], (uint32_t)((NQP - 128) * 128));
+                ptx::tma_load_3d_e(sV + 16384, &tmV1, &bars->v_full[1], 2 * D + h * HD, 128, f);
+            }
         }
     } else if (warp == 1) {
         // ---- MMA issuer (warp-uniform)
@@ -394,14 +405,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
                         const uint64_t qb = ptx::umma_desc_kmajor_sw128(aQ + st * MATB + h * 16384);
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) ptx::umma_bf16_e(tb, ka + 2 * kk, qb + 2 * kk, idesc_s, kk ? 1u : 0u);
-                        if (kb == 0 && h == 0) { ptx::mbar_wait(&bars->v_full, (uint32_t)k & 1u); ptx::tc_fence_after(); }
+                        if (h == 0) { ptx::mbar_wait(&bars->v_full[kb], (uint32_t)k & 1u); ptx::tc_fence_after(); }
                         const uint64_t va = ptx::umma_desc_kmajor_sw128(aV + kb * 16384);
                         const uint64_t gb = ptx::umma_desc_kmajor_sw128(aG + st * MATB + h * 16384);
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) ptx::umma_bf16_e(tb + 128, va + 2 * kk, gb + 2 * kk, idesc_s, kk ? 1u : 0u);
                         ptx::umma_commit_e(&bars->sdp_full);
+                        if (h == NH - 1) ptx::umma_commit_e(&bars->v_empty[kb]);    // last use of this half of V
+                        mark(s, 8);
                     }
-                    ptx::mbar_wait(&bars->pds_full, s & 1u);                 // P^T in TMEM, dS^T in shared memory
+                    ptx::mbar_wait(&bars->pds_full, s & 1u);
+                    mark(s, 9);                 // P^T in TMEM, dS^T in shared memory
                     if (h == 0 && c > 0) ptx::mbar_wait(&bars->acc_empty, (c - 1) & 1u);      // dV / dK columns drained
                     if (kb == 0 && h == 0 && k > 0) ptx::mbar_wait(&bars->dq_empty, (uint32_t)(k - 1) & 1u);
                     ptx::tc_fence_after();
@@ -411,8 +425,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
                     const uint64_t s_k = ptx::umma_desc_kmajor_sw128(aS);
                     const uint64_t s_mn = ptx::umma_desc_mnmajor_sw128(aS, 16384);
 #pragma unroll 4
-                    for (int j = 0; j < KSh; ++j)        // dV_kb += P^T dO_h : 16 queries per MMA
-                        ptx::umma_bf16_ts_e(tb + 256, tb + j * 8, g_mn + (uint64_t)(j * 128), idesc_acc, (h | j) ? 1u : 0u);
+                    for (int j = 0; j < KSh; ++j) {      // dV_kb += P^T dO_h : 16 queries per MMA; P^T chunk j sits where its math warp put it
+                        const int csplit = (KSh + 1) >> 1;
+                        const uint32_t p_col = j < csplit ? 8 * j : 16 * csplit + 8 * (j - csplit);
+                        ptx::umma_bf16_ts_e(tb + 256, tb + p_col, g_mn + (uint64_t)(j * 128), idesc_acc, (h | j) ? 1u : 0u);
+                    }
 #pragma unroll 4
                     for (int j = 0; j < KSh; ++j)        // dK_kb += dS^T Q_h : A = dS^T boxes, K-major (64 queries per box)
                         ptx::umma_bf16_e(tb + 320, s_k + (uint64_t)((j >> 2) * 1024 + (j & 3) * 2), q_mn + (uint64_t)(j * 128),
@@ -421,12 +438,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
                     for (int j = 0; j < KSkb; ++j)       // dQ_h += dS K_kb : A = the same boxes, MN-major (16 keys per MMA)
                         ptx::umma_bf16_e(tb + 384 + h * 64, s_mn + (uint64_t)(j * 128), k_mn + (uint64_t)(j * 128), idesc_dq,
                                          (kb | j) ? 1u : 0u);
+                    mark(s, 10);
                     if (h == NH - 1) { ptx::umma_commit_e(&bars->dvk_full); ++c; }
                 }
             }
             ptx::umma_commit_e(&bars->dq_full);
             ptx::umma_commit_e(&bars->in_empty[st]);
-            ptx::umma_commit_e(&bars->v_empty);
         }
     } else if (warp < 4) {
         // ---- delta / lse warps: delta[q] = sum_d dO[q,d] O[q,d] and lse2[q] = lse[q] * log2(e) of problem k (one ahead)
@@ -462,48 +479,81 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         const uint32_t trow = tb + ((uint32_t)(wq * 32) << 16);
         const int r = wq * 32 + lane;                                     // key row inside the key block
         const uint32_t sS_row = ptx::smem_u32(sS) + r * 128;
+        const bool storer = threadIdx.x == 128;                           // issues (and drains) the TMA stores
+        bool st_pending = false;                                          // a TMA store may still be reading the dS^T buffer
         uint32_t s = 0, c = 0;
+        // results leave through the (then idle) dS^T buffer: a thread writes its row as swizzled 16-byte chunks and the two
+        // [128 rows][64] boxes go out as TMA stores whose tensor map clips rows >= n (padded keys / queries are never
+        // written).  (Plain st.global from 256 threads measured 3-4x slower here: the CTAs run in lockstep and their store
+        // bursts collide; the asynchronous stores are absorbed.)
+        auto stage_row = [&](int box, const uint32_t (&v)[16]) {          // 32 columns (ch-th half) of row r of box `box`
+            const uint32_t base = sS_row + (box << 14);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(base + (((ch * 4 + i) ^ (r & 7)) << 4)), "r"(v[4 * i]),
+                             "r"(v[4 * i + 1]), "r"(v[4 * i + 2]), "r"(v[4 * i + 3]) : "memory");
+        };
+        int release_stage = -1;                                           // operand stage whose K / Q buffers carry a dQ store
+        auto drain_store = [&]() {                                        // before anything rewrites the dS^T buffer
+            if (st_pending) {
+                if (storer) {
+                    ptx::bulk_wait_read0();
+                    if (release_stage >= 0) ptx::mbar_arrive(&bars->in_empty[release_stage]);
+                }
+                release_stage = -1;
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                st_pending = false;
+            }
+        };
         for (int k = 0; k < nloc; ++k) {
             const int pi = blockIdx.x + k * gridDim.x;
             const int f = pi / heads, h_ = pi - f * heads;
             const float* l2 = dl + (k & 1) * 512;
             ptx::mbar_wait(&bars->dl_full[k & 1], (uint32_t)(k >> 1) & 1u);
             for (int kb = 0; kb < KBL; ++kb) {
-                const int key = kb * 128 + r;
-                const bool kvalid = key < n;
+                const bool kvalid = kb * 128 + r < n;
                 for (int h = 0; h < NH; ++h, ++s) {
                     const int Nh = min(128, NQP - h * 128);
                     const int NC = Nh >> 4;                               // 16-query chunks of this half
                     const int c0 = ch ? (NC + 1) >> 1 : 0, c1 = ch ? NC : (NC + 1) >> 1;
                     ptx::mbar_wait(&bars->sdp_full, s & 1u);
                     ptx::tc_fence_after();
-                    uint32_t pk[4][8];
+                    if (warp == 4) mark(s, 0);
+                    uint32_t sv[2][16], dv[2][16];
+                    if (c0 < c1) {
+                        ptx::tmem_ld_32x32b_x16(trow + c0 * 16, sv[0]);
+                        ptx::tmem_ld_32x32b_x16(trow + 128 + c0 * 16, dv[0]);
+                    }
 #pragma unroll
                     for (int ci = 0; ci < 4; ++ci) {
                         const int cc = c0 + ci;
                         if (cc < c1) {
-                            uint32_t sv[16], dv[16];
-                            ptx::tmem_ld_32x32b_x16(trow + cc * 16, sv);
-                            ptx::tmem_ld_32x32b_x16(trow + 128 + cc * 16, dv);
+                            const uint32_t (&sc)[16] = sv[ci & 1];
+                            const uint32_t (&dc)[16] = dv[ci & 1];
                             const float* lq = l2 + h * 128 + cc * 16;
-                            float lv[16], dd[16];
+                            float lv[16], dd[16];                       // per-query constants: broadcast reads, issued under the TMEM loads
 #pragma unroll
                             for (int m = 0; m < 4; ++m) {
                                 *reinterpret_cast<float4*>(lv + 4 * m) = *reinterpret_cast<const float4*>(lq + 4 * m);
                                 *reinterpret_cast<float4*>(dd + 4 * m) = *reinterpret_cast<const float4*>(lq + 256 + 4 * m);
                             }
                             ptx::tmem_wait_ld();
-                            uint32_t dsp[8];
+                            if (ci < 3 && cc + 1 < c1) {                  // next chunk's scores are in flight while this one computes
+                                ptx::tmem_ld_32x32b_x16(trow + (cc + 1) * 16, sv[(ci + 1) & 1]);
+                                ptx::tmem_ld_32x32b_x16(trow + 128 + (cc + 1) * 16, dv[(ci + 1) & 1]);
+                            }
+                            uint32_t dsp[8], pkc[8];
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                float p0 = ex2_ftz(fmaf(__uint_as_float(sv[2 * j]), SCALE_LOG2, -lv[2 * j]));
-                                float p1 = ex2_ftz(fmaf(__uint_as_float(sv[2 * j + 1]), SCALE_LOG2, -lv[2 * j + 1]));
-                                float d0 = p0 * (__uint_as_float(dv[2 * j]) - dd[2 * j]);
-                                float d1 = p1 * (__uint_as_float(dv[2 * j + 1]) - dd[2 * j + 1]);
+                                float p0 = ex2_ftz(fmaf(__uint_as_float(sc[2 * j]), SCALE_LOG2, -lv[2 * j]));
+                                float p1 = ex2_ftz(fmaf(__uint_as_float(sc[2 * j + 1]), SCALE_LOG2, -lv[2 * j + 1]));
+                                float d0 = p0 * (__uint_as_float(dc[2 * j]) - dd[2 * j]);
+                                float d1 = p1 * (__uint_as_float(dc[2 * j + 1]) - dd[2 * j + 1]);
                                 if (!kvalid) { p0 = p1 = d0 = d1 = 0.f; }           // padded keys contribute nothing
-                                pk[ci][j] = pack_bf16(p0, p1);
+                                pkc[j] = pack_bf16(p0, p1);
                                 dsp[j] = pack_bf16(d0, d1);
                             }
+                            if (ci == 0) drain_store();     // the previous results' TMA store has finished reading the buffer
                             // dS^T -> shared memory: box (cc*16)/64 of 64 queries, row r, two 16-byte chunks (128B swizzle)
                             const uint32_t base = sS_row + ((cc >> 2) << 14);
                             const int i0 = (cc & 3) * 2;
@@ -511,23 +561,26 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
                                          "r"(dsp[1]), "r"(dsp[2]), "r"(dsp[3]) : "memory");
                             asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(base + (((i0 + 1) ^ (r & 7)) << 4)), "r"(dsp[4]),
                                          "r"(dsp[5]), "r"(dsp[6]), "r"(dsp[7]) : "memory");
+                            // P^T (bf16) over S^T columns that THIS warp has already consumed: the first half of the chunks
+                            // packs from column 0, the second half from the first column of its own range (see p_col)
+                            ptx::tmem_st_32x32b_x8(trow + (ch ? 16 * c0 + 8 * (cc - c0) : 8 * cc), pkc);
+                        } else if (ci == 0) {
+                            drain_store();                  // warps without a chunk (tiny n) still take part in the barrier
                         }
                     }
-                    // every math warp has read its S^T columns: P^T may now overwrite them
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
-#pragma unroll
-                    for (int ci = 0; ci < 4; ++ci)
-                        if (c0 + ci < c1) ptx::tmem_st_32x32b_x8(trow + (c0 + ci) * 8, pk[ci]);
+                    if (warp == 4) mark(s, 1);
                     ptx::tmem_wait_st();
                     ptx::fence_proxy_async();
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&bars->pds_full);
+                    if (warp == 4) mark(s, 2);
                     if (h == NH - 1) {
-                        // ---- dV_kb, dK_kb complete: this thread stores 32 of the 64 columns of its key row
+                        // ---- dV_kb, dK_kb complete (and the MMAs that read the dS^T buffer with them)
                         ptx::mbar_wait(&bars->dvk_full, c & 1u);
                         ++c;
                         ptx::tc_fence_after();
+                        if (warp == 4) mark(s, 3);
                         uint32_t a[32], b[32];
                         ptx::tmem_ld_32x32b_x32(trow + 256 + ch * 32, a);
                         ptx::tmem_ld_32x32b_x32(trow + 320 + ch * 32, b);
@@ -535,25 +588,30 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
                         ptx::tc_fence_before();
                         __syncwarp();
                         if (lane == 0) ptx::mbar_arrive(&bars->acc_empty);
-                        if (kvalid) {
-                            uint32_t ov[16], ok[16];
+                        uint32_t ov[16], ok[16];
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                ov[j] = pack_bf16(__uint_as_float(a[2 * j]), __uint_as_float(a[2 * j + 1]));
-                                ok[j] = pack_bf16(__uint_as_float(b[2 * j]) * SCALE, __uint_as_float(b[2 * j + 1]) * SCALE);
-                            }
-                            bf16* row = dqkv + ((int64_t)f * n + key) * (3 * D) + h_ * HD + ch * 32;
-                            st_global_v8(row + D, ok);
-                            st_global_v8(row + D + 16, ok + 8);
-                            st_global_v8(row + 2 * D, ov);
-                            st_global_v8(row + 2 * D + 16, ov + 8);
+                        for (int j = 0; j < 16; ++j) {
+                            ov[j] = pack_bf16(__uint_as_float(a[2 * j]), __uint_as_float(a[2 * j + 1]));
+                            ok[j] = pack_bf16(__uint_as_float(b[2 * j]) * SCALE, __uint_as_float(b[2 * j + 1]) * SCALE);
                         }
+                        stage_row(0, ok);
+                        stage_row(1, ov);
+                        ptx::fence_proxy_async();
+                        asm volatile("bar.sync 2, 256;" ::: "memory");
+                        if (storer) {
+                            ptx::tma_store_3d(&tmOUT, ptx::smem_u32(sS), D + h_ * HD, kb * 128, f);
+                            ptx::tma_store_3d(&tmOUT, ptx::smem_u32(sS) + 16384, 2 * D + h_ * HD, kb * 128, f);
+                            ptx::bulk_commit();
+                        }
+                        st_pending = true;
+                        if (warp == 4) mark(s, 4);
                     }
                 }
             }
             // ---- dQ of the whole problem
             ptx::mbar_wait(&bars->dq_full, (uint32_t)k & 1u);
             ptx::tc_fence_after();
+            if (warp == 4) mark(s - 1, 5);
             uint32_t qa[32], qb2[32];
             ptx::tmem_ld_32x32b_x32(trow + 384 + ch * 32, qa);
             if (NH > 1) ptx::tmem_ld_32x32b_x32(trow + 448 + ch * 32, qb2);
@@ -561,22 +619,39 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&bars->dq_empty);
+            // dQ is staged in the K and Q buffers of this problem's operand stage (dead once dq_full has arrived) so that it
+            // does not wait for the dK / dV store that has just been issued from the dS^T buffer; the stage goes back to the
+            // producer when the store has read it (deferred to the next drain, or at once when there is a single stage)
+            const int st = stage_of(k);
+            const uint32_t sq0 = ptx::smem_u32(sK + st * MATB) + r * 128, sq1 = ptx::smem_u32(sQ + st * MATB) + r * 128;
 #pragma unroll
             for (int hb = 0; hb < 2; ++hb) {
-                const int q = hb * 128 + r;
-                if (hb < NH && q < n) {
+                if (hb < NH) {
                     uint32_t oq[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const uint32_t x0 = hb ? qb2[2 * j] : qa[2 * j], x1 = hb ? qb2[2 * j + 1] : qa[2 * j + 1];
                         oq[j] = pack_bf16(__uint_as_float(x0) * SCALE, __uint_as_float(x1) * SCALE);
                     }
-                    bf16* row = dqkv + ((int64_t)f * n + q) * (3 * D) + h_ * HD + ch * 32;
-                    st_global_v8(row, oq);
-                    st_global_v8(row + 16, oq + 8);
+                    const uint32_t base = hb ? sq1 : sq0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(base + (((ch * 4 + i) ^ (r & 7)) << 4)), "r"(oq[4 * i]),
+                                     "r"(oq[4 * i + 1]), "r"(oq[4 * i + 2]), "r"(oq[4 * i + 3]) : "memory");
                 }
             }
+            ptx::fence_proxy_async();
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            if (storer) {
+                ptx::tma_store_3d(&tmOUT, ptx::smem_u32(sK + st * MATB), h_ * HD, 0, f);
+                if (NH > 1) ptx::tma_store_3d(&tmOUT, ptx::smem_u32(sQ + st * MATB), h_ * HD, 128, f);
+                ptx::bulk_commit();
+                if (NSTG == 1) { ptx::bulk_wait_read0(); ptx::mbar_arrive(&bars->in_empty[st]); }
+            }
+            st_pending = true;
+            release_stage = NSTG == 1 ? -1 : st;
         }
+        if (storer) ptx::bulk_wait0();              // shared memory must outlive the last TMA store
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -713,6 +788,16 @@ int attn_spatial_bwd_tc(const void* qkv, const void* o, const void* d_o, const f
     if (rc) return rc;
     rc = make_tmap3(&tg, d_o, frames, n, D, NQP / 2);
     if (rc) return rc;
+    CUtensorMap to, tv0, tv1;
+    rc = make_tmap3(&to, d_qkv, frames, n, 3 * (int64_t)D, 128);
+    if (rc) return rc;
+    rc = make_tmap3(&tv0, qkv, frames, n, 3 * (int64_t)D, NQP < 128 ? NQP : 128);
+    if (rc) return rc;
+    tv1 = tv0;
+    if (NQP > 128) {
+        rc = make_tmap3(&tv1, qkv, frames, n, 3 * (int64_t)D, NQP - 128);
+        if (rc) return rc;
+    }
     const int NSTG = (7 * NQP * 128 + 32768 + 4096 + 256 + 1024 <= 227 * 1024) ? 2 : 1;
     const int smem = (3 * NSTG + 1) * NQP * 128 + 32768 + 4096 + 256 + 1024;
     static bool attr_set[64] = {false};
@@ -728,8 +813,8 @@ int attn_spatial_bwd_tc(const void* qkv, const void* o, const void* d_o, const f
     const int sms = sm_count();
     const int waves = (nprob + sms - 1) / sms;
     const int grid = (nprob + waves - 1) / waves;
-    launch_k(attn_bwd_tc_kernel, dim3(grid), dim3(BWD_THREADS), (size_t)smem, s, tq, tg, (const bf16*)o, lse, (bf16*)d_qkv, n,
-             heads, D, nprob, NQP, NSTG);
+    launch_k(attn_bwd_tc_kernel, dim3(grid), dim3(BWD_THREADS), (size_t)smem, s, tq, tg, tv0, tv1, to, (const bf16*)o, lse, n, heads, D,
+             nprob, NQP, NSTG, g_attn_timeline);
     AIMB_CHECK_LAUNCH();
     return AIMB_OK;
 }

@@ -249,6 +249,13 @@ __device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t
                  : "memory");
 }
 
+// TMA store of one 3-D box (shared -> global), bulk-group completion; elements outside the tensor are not written
+__device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t smem_src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+                 "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
 // ---- warp-uniform issue -------------------------------------------------------------------------------------
 // tcgen05.mma / tcgen05.commit / TMA are uniform-datapath instructions: their operands must sit in uniform registers.
 // Issued from a divergent `if (lane == 0)` region, every operand is first moved there (R2UR) inside a per-thread

@@ -27,8 +27,29 @@ L.aimb_debug_attn_timeline(None)
 t = tl.cpu().view(64, 16)
 t0 = int(t[t > 0].min())
 names = ["s_full seen", "pass1 done", "p_full arrive", "o_full seen", "O loaded", "stored", "", "", "mma: p_full seen", "mma: PV issued", "mma: S issued"]
+print("== forward")
 print("unit wg | " + " | ".join(f"{x:>16s}" for x in names if x))
 for u in range(64):
     if int(t[u].max()) == 0:
         continue
     print(f"{u:4d} {u & 1:2d} | " + " | ".join(f"{(int(t[u, e]) - t0) if int(t[u, e]) else -1:16d}" for e, x in enumerate(names) if x))
+
+# ---- backward: one row per step (key block x query half) of CTA 0
+d_o = torch.randn(frames * n, D, device="cuda").bfloat16()
+d_qkv = torch.empty_like(qkv)
+for _ in range(2):
+    lib.attn_spatial_bwd(qkv, o, d_o, lse, d_qkv, frames, n, heads)
+tl.zero_()
+L.aimb_debug_attn_timeline(tl.data_ptr())
+lib.attn_spatial_bwd(qkv, o, d_o, lse, d_qkv, frames, n, heads)
+torch.cuda.synchronize()
+L.aimb_debug_attn_timeline(None)
+t = tl.cpu().view(64, 16)
+t0 = int(t[t > 0].min())
+names = ["sdp_full seen", "math done", "pds arrive", "dvk_full seen", "dv/dk stored", "dq_full seen", "acc loaded", "staged+bar", "mma: S,dP issued", "mma: pds seen", "mma: dV,dK,dQ iss"]
+print("== backward")
+print("step | " + " | ".join(f"{x:>17s}" for x in names if x))
+for u in range(64):
+    if int(t[u].max()) == 0:
+        continue
+    print(f"{u:4d} | " + " | ".join(f"{(int(t[u, e]) - t0) if int(t[u, e]) else -1:17d}" for e, x in enumerate(names) if x))
