@@ -772,7 +772,7 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = ptx::warp_id_uniform(), lane = threadIdx.x & 31;   // provably uniform: the producer / MMA loops stay in the uniform datapath
     const int n_tiles = N / BN;
     const int m_tiles = (M + BM - 1) / BM;
     const int total = n_tiles * m_tiles;
@@ -788,25 +788,27 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
     pdl_wait();
+    // Producer and MMA warps: every lane runs the loop, one elected lane issues (ptx.cuh "warp-uniform issue": issued from
+    // an `if (lane == 0)` region each tcgen05.mma costs ~100 clk of operand moves, which a 128 x 192 MMA (96 clk) cannot hide)
     if (warp == 0) {
-        if (lane == 0) {
+        {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
                 const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
                 for (int kb = 0; kb < KB; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                    ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    ptx::mbar_arrive_expect_tx_e(&full_bar[stage], Cfg::STAGE_BYTES);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-                    ptx::tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
-                    ptx::tma_load_2d(sa + A_STAGE_BYTES, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+                    ptx::tma_load_2d_e(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+                    ptx::tma_load_2d_e(sa + A_STAGE_BYTES, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN);
             int stage = 0; uint32_t phase = 0;
             int it = 0;
@@ -824,9 +826,9 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const uint64_t bdesc = ptx::umma_desc_kmajor_sw128(sa + A_STAGE_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k)
-                        ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                    ptx::umma_commit(&empty_bar[stage]);
-                    if (kb == KB - 1) ptx::umma_commit(&tfull_bar[as]);
+                        ptx::umma_bf16_e(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    ptx::umma_commit_e(&empty_bar[stage]);
+                    if (kb == KB - 1) ptx::umma_commit_e(&tfull_bar[as]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -1915,7 +1917,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* done_bar = empty_bar + STAGES;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done_bar + 1);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = ptx::warp_id_uniform(), lane = threadIdx.x & 31;
     const int mt = blockIdx.x;
     const int kb0 = blockIdx.y * kb_per_split;
     const int kb1 = (kb0 + kb_per_split < KB) ? kb0 + kb_per_split : KB;
@@ -1931,25 +1933,25 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
     pdl_wait();      // barrier init, TMEM allocation, descriptor prefetch above overlapped the previous kernel's tail
-    if (warp == 0) {
-        if (lane == 0) {
+    if (warp == 0) {           // producer and MMA warps run warp-uniformly, one elected lane issues (ptx.cuh)
+        {
             int stage = 0; uint32_t phase = 0;
             for (int kb = kb0; kb < kb1; ++kb) {
                 ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                ptx::mbar_arrive_expect_tx(&full_bar[stage], STG);
+                ptx::mbar_arrive_expect_tx_e(&full_bar[stage], STG);
                 uint8_t* sa = smem + stage * STG;
-                ptx::tma_load_2d(sa, &tmP, &full_bar[stage], mt * 128, kb * 64);
-                ptx::tma_load_2d(sa + BOX, &tmP, &full_bar[stage], mt * 128 + 64, kb * 64);
+                ptx::tma_load_2d_e(sa, &tmP, &full_bar[stage], mt * 128, kb * 64);
+                ptx::tma_load_2d_e(sa + BOX, &tmP, &full_bar[stage], mt * 128 + 64, kb * 64);
 #pragma unroll
                 for (int j = 0; j < NS / 64; ++j)
-                    ptx::tma_load_2d(sa + A_BYTES + j * BOX, &tmQ, &full_bar[stage], j * 64, kb * 64);
+                    ptx::tma_load_2d_e(sa + A_BYTES + j * BOX, &tmQ, &full_bar[stage], j * 64, kb * 64);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, NS, 1, 1);
             int stage = 0; uint32_t phase = 0;
             for (int kb = kb0; kb < kb1; ++kb) {
@@ -1960,10 +1962,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
                 for (int k = 0; k < 4; ++k) {   // 16 contraction rows per MMA = two 8-row swizzle atoms = 2048 B
                     const uint64_t adesc = ptx::umma_desc_mnmajor_sw128(sa + k * 2048, BOX);
                     const uint64_t bdesc = ptx::umma_desc_mnmajor_sw128(sa + A_BYTES + k * 2048, BOX);
-                    ptx::umma_bf16(tmem_base, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    ptx::umma_bf16_e(tmem_base, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                 }
-                ptx::umma_commit(&empty_bar[stage]);
-                if (kb == kb1 - 1) ptx::umma_commit(done_bar);
+                ptx::umma_commit_e(&empty_bar[stage]);
+                if (kb == kb1 - 1) ptx::umma_commit_e(done_bar);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
