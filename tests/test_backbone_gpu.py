@@ -202,3 +202,85 @@ def test_inference_three_views_sharded_like_recognizer3d():
     ref = O.head_logits(O.backbone(O.fixture_state_dict(cfg), vids.reshape(-1, 3, 4, 64, 64), cfg), hw, hb)
     ref = torch.softmax(ref, -1).reshape(4, 3, -1).mean(1)
     assert O.normalised_max_err(full, ref) < 2e-2
+
+
+# ---------------------------------------------------------------------------------------------- full-depth configs
+# BASELINE.json cfg2 (training batch), cfg4 (ViT-L/14 3-view inference) and cfg5 (ViT-L/14 32 frames) at their FULL
+# depth against the live CPU oracle: the bf16 residual stream accumulates rounding with depth, so the 2e-2 / 6e-2 gates
+# are checked exactly where they are at risk.  The oracle legs take 10 s - 2 min of host time each (cached per config).
+_ORACLE_CACHE = {}
+
+
+def _oracle_full(name):
+    if name in _ORACLE_CACHE:
+        return _ORACLE_CACHE[name]
+    if name == "cfg4":      # configs/recognition/vit/vitclip_large_k400.py:6 with 8 frames, 1 video x 3 views, eval
+        cfg = O.OracleCfg(input_resolution=224, num_frames=8, patch_size=14, width=1024, layers=24, heads=16)
+        x = O.fixture_clip(cfg, 3)
+        hw, hb = O.fixture_head(cfg, 400)
+        with torch.no_grad():
+            ref = O.logits(O.fixture_state_dict(cfg), x, cfg, hw, hb)
+        out = (cfg, x, hw, hb, ref)
+    elif name == "cfg5":    # ViT-L/14, 32 frames, one clip, training step
+        cfg = O.OracleCfg(input_resolution=224, num_frames=32, patch_size=14, width=1024, layers=24, heads=16)
+        x = O.fixture_clip(cfg, 1)
+        hw, hb = O.fixture_head(cfg, 400)
+        labels = torch.tensor([5])
+        out = (cfg, x, hw, hb, labels) + tuple(O.loss_and_grads(O.fixture_state_dict(cfg), x, labels, cfg, hw, hb))
+    else:
+        raise KeyError(name)
+    _ORACLE_CACHE[name] = out
+    return out
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_cfg4_vitl14_24_layers_three_views(mode):
+    cfg, x, hw, hb, ref = _oracle_full("cfg4")
+    m = _build(cfg, mode).eval()
+    with torch.no_grad():
+        lg = O.head_logits(m(x.cuda()), hw.cuda(), hb.cuda()).cpu()
+    err = O.normalised_max_err(lg, ref)
+    prob = torch.softmax(lg, -1).mean(0)                    # average_clips='prob' over the 3 views (recognizers/base.py:186-192)
+    prob_ref = torch.softmax(ref, -1).mean(0)
+    print(f"[cfg4 full depth {mode}] logits err {err:.3e}, prob err {O.normalised_max_err(prob, prob_ref):.3e}")
+    assert err < (1e-3 if mode == "fp32" else 2e-2)
+    assert torch.equal(lg.argmax(1), ref.argmax(1)) and int(prob.argmax()) == int(prob_ref.argmax())
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_cfg5_vitl14_24_layers_32_frames_train(mode):
+    cfg, x, hw, hb, labels, ref_loss, ref_lg, ref_g = _oracle_full("cfg5")
+    m = _build(cfg, mode)
+    lg, loss, grads = _cuda_logits_and_grads(m, cfg, x, hw, hb, labels)
+    err = O.normalised_max_err(lg, ref_lg)
+    worst = max(O.normalised_max_err(grads[k], ref_g[k]) for k in grads)
+    print(f"[cfg5 full depth {mode}] logits err {err:.3e}, worst gradient err over {len(grads)} tensors {worst:.3e}")
+    assert err < (1e-3 if mode == "fp32" else 2e-2)
+    assert int(lg.argmax()) == int(ref_lg.argmax())
+    assert worst < (1e-3 if mode == "fp32" else 6e-2)
+
+
+def test_cfg2_batch8_droppath_all_gradients():
+    """The bench configuration itself: ViT-B/16 8x224, 8 clips, drop_path_rate 0.2 (vitclip_base_k400.py:6), training
+    mode; the masks drawn by the module are fed to the oracle, all 147 gradients are compared."""
+    cfg = O.OracleCfg(block="aim")
+    m = _build(cfg, "bf16", drop_path_rate=0.2).train()
+    x = O.fixture_clip(cfg, 8, seed=7)
+    hw, hb = O.fixture_head(cfg, 400)
+    labels = torch.arange(8) * 37 % 400
+    torch.manual_seed(11)
+    masks = m._drop_masks(m._dims(8), torch.device("cuda"))
+    torch.manual_seed(11)                                                   # the forward below draws the same masks
+    hwc, hbc = hw.cuda().requires_grad_(True), hb.cuda().requires_grad_(True)
+    lg = O.head_logits(m(x.cuda()), hwc, hbc)
+    F.cross_entropy(lg, labels.cuda()).backward()
+    grads = {k: p.grad.detach().cpu() for k, p in m.named_parameters() if p.requires_grad}
+    om = [(None, None) if a is None else (a.cpu(), b.cpu()) for a, b in masks]
+    assert any(a is not None and float(a.min()) == 0.0 for a, _ in om)
+    _, ref_lg, ref_g = O.loss_and_grads(O.fixture_state_dict(cfg), x, labels, cfg, hw, hb, drop_masks=om)
+    err = O.normalised_max_err(lg.detach().cpu(), ref_lg)
+    worst = max(O.normalised_max_err(grads[k], ref_g[k]) for k in grads)
+    print(f"[cfg2 B=8 DropPath 0.2 bf16] logits err {err:.3e}, worst gradient err over {len(grads)} tensors {worst:.3e}")
+    assert len(grads) == 147
+    assert err < 2e-2 and torch.equal(lg.detach().cpu().argmax(1), ref_lg.argmax(1))
+    assert worst < 6e-2
