@@ -358,7 +358,7 @@ class ViT_CLIP(nn.Module):
         masks = self._drop_masks(d, x.device) if training else None
         if training:
             self._step_ctx = (W, WT, d)
-        return self._engine.forward(x.contiguous(), W, d, training, masks)
+        return self._engine.forward(x.contiguous(), W, d, training, masks, WT)
 
     def _run_backward(self, dfeat: torch.Tensor):
         W, WT, d = self._step_ctx

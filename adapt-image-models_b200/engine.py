@@ -64,6 +64,13 @@ class Engine:
         self.saved: Optional[dict] = None
         self.attn_impl = lib.IMPL_AUTO
         self.gemm_impl = lib.IMPL_AUTO
+        # T_Adapter has no skip and is the only consumer of the temporal out_proj (vitclip_aim.py:203-204), so
+        # D_fc1(out_proj(o)) = o (W1 Wo)^T + (W1 bo + b1): the temporal out_proj GEMM and its dgrad need not be launched.
+        # Built, parity-green (tests/test_backbone_gpu.py with AIMB200_FUSE_T_OUTPROJ=1) and measured: the 24 removed
+        # 12608 x 768 x 768 GEMMs (-0.48 ms) cost less than the 36 + 60 tiny per-step launches that form W1 Wo, its
+        # transpose and dW1 = (d_h^T o) Wo^T + db1 (x) bo (675 vs 709 clips/s) -> opt-in until those are one grouped launch
+        self.fuse_t_outproj = os.environ.get("AIMB200_FUSE_T_OUTPROJ", "0") == "1"
+        self.t_fused = False
         self.fuse_adapters = os.environ.get("AIMB200_FUSE_ADAPTERS", "0") == "1"   # opt-in: measured on par at M = 12608
         # adapter weight-gradient kernels are off the critical path of backward: they run on a side stream (captured
         # into the step graph as parallel branches) and fill the SMs the small dgrad GEMMs / kernel tails leave idle
@@ -139,7 +146,7 @@ class Engine:
 
     # ------------------------------------------------------------------ forward
     def forward(self, x: torch.Tensor, W: Dict[str, torch.Tensor], d: Dims, training: bool,
-                drop_masks: Optional[List] = None) -> torch.Tensor:
+                drop_masks: Optional[List] = None, WT: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
         """x [B,3,T,H,W] (fp32 / bf16 / uint8) -> feat fp32 [B, D, T].  W: weights in compute dtype.
         drop_masks[i] = (mask_t, mask_m): fp32 [n] DropPath multipliers (0 or 1/keep) or None."""
         M, D, r, n, BT = d.M, d.D, d.r, d.n, d.BT
@@ -158,6 +165,10 @@ class Engine:
                              W["ln_pre.weight"], W["ln_pre.bias"], z, xcur, mean0, rstd0, d.B, d.T, n)
         if training:
             sv["z"], sv["ln_pre"] = z, (mean0, rstd0)
+        self.t_fused = (self.fuse_t_outproj and d.block == "aim" and d.num_tadapter == 1 and WT is not None
+                        and self.dtype == torch.bfloat16)
+        if self.t_fused:
+            self._prep_t_fused(W, WT, d, training)
         for i in range(d.L):
             masks = drop_masks[i] if (drop_masks is not None) else (None, None)
             if d.block == "fork":
@@ -173,6 +184,23 @@ class Engine:
             sv["x_last"], sv["tail"] = xcur, (tm, tr)
             self.saved = sv
         return feat
+
+    def _prep_t_fused(self, W, WT, d, training):
+        """Per step (D_fc1 is trainable): W1o = W1 Wo [r, D], b1o = W1 bo + b1, and W1o^T for the dgrad."""
+        r, D = d.r, d.D
+        for i in range(d.L):
+            pre = f"transformer.resblocks.{i}."
+            w1, b1 = W[pre + "T_Adapter.D_fc1.weight"], W[pre + "T_Adapter.D_fc1.bias"]
+            woT, bo = WT[pre + "attn.out_proj.weight"], W[pre + "attn.out_proj.bias"]
+            w1o = self.buf("t_w1o", (r, D), key=i)
+            self.gemm(w1, woT, w1o)                                  # [r, D_in] = sum_j W1[r, j] Wo[j, i]
+            b1o = self.buf("t_b1o", (1, r), key=i)
+            self.gemm(bo.view(1, D), w1, b1o, bias=b1)               # W1 bo + b1
+            W[pre + "T_Adapter.w1o"], W[pre + "T_Adapter.b1o"] = w1o, b1o.view(r)
+            if training:
+                w1oT = self.buf("t_w1oT", (D, r), key=i)
+                self.gemm(woT, w1, w1oT)                             # [D_in, r]: the N x K operand of d_o = d_h W1o
+                W[pre + "T_Adapter.w1oT"] = w1oT
 
     def _adapter_fwd(self, name, pre, a, W, d, bk, training, rs, alpha, res1, res2, out):
         """out = res1 + res2 + alpha * rs * (fc2(gelu(fc1(a))))   (rs folded into the hidden, see backward)."""
@@ -247,10 +275,19 @@ class Engine:
         self.gemm(qkv_in, Wqkv, qkv_t, bias=bqkv)
         o_t = self.buf("o_t", (M, D), key=bk)
         lib.attn_temporal_fwd(qkv_t, o_t, d.B, d.T, n, d.heads)
-        a_t = self.buf("a_t", (M, D), key=bk)
-        self.gemm(o_t, Wo, a_t, bias=bo)
         x1 = self.buf("x1", (M, D), key=bk)
-        h_t, g_t = self._adapter_fwd("T_Adapter", pre, a_t, W, d, bk, training, mask_t, 1.0, x, None, x1)
+        if self.t_fused:
+            a_t = None
+            h_t = self.buf("T_Adapter_h", (M, r), key=bk) if training else None
+            g_t = self.buf("T_Adapter_g", (M, r), key=bk)
+            self.gemm(o_t, W[pre + "T_Adapter.w1o"], g_t, bias=W[pre + "T_Adapter.b1o"], act=lib.ACT_GELU, out_pre=h_t,
+                      row_scale=mask_t)
+            self.gemm(g_t, W[pre + "T_Adapter.D_fc2.weight"], x1, bias=W[pre + "T_Adapter.D_fc2.bias"], row_scale=mask_t,
+                      bias_rowscaled=mask_t is not None, res1=x)
+        else:
+            a_t = self.buf("a_t", (M, D), key=bk)
+            self.gemm(o_t, Wo, a_t, bias=bo)
+            h_t, g_t = self._adapter_fwd("T_Adapter", pre, a_t, W, d, bk, training, mask_t, 1.0, x, None, x1)
         # ---------------- spatial adaptation (:208)
         xn_s = self.buf("xn", (M, D))
         m2, r2 = self.buf("ln1s_m", (M,), f32, bk), self.buf("ln1s_r", (M,), f32, bk)
@@ -442,6 +479,40 @@ class Engine:
             self._join_side()
         return d_a_out
 
+    def _t_fused_bwd(self, pre, dy, S, W, WT, grads, d, rs, d_o_out):
+        """Backward of x1 = x + rs * fc2(gelu(o W1o^T + b1o)) without the out_proj activation a = o Wo^T + bo:
+        d_o = d_h W1o;  dW1 = d_h^T a = (d_h^T o) Wo^T + colsum(d_h) (x) bo;  db1 = colsum(d_h).  The fc2 bias gradient was
+        fused into the LayerNorm backward that produced dy.  Weight gradients run on the side stream."""
+        M, r, D = dy.shape[0], d.r, d.D
+        k1w, k1b, k2w = pre + "T_Adapter.D_fc1.weight", pre + "T_Adapter.D_fc1.bias", pre + "T_Adapter.D_fc2.weight"
+        h, g, o = S["h_t"], S["g_t"], S["o_t"]
+        self._join_side()
+        side = self.wgrad_side
+        if side:
+            with torch.cuda.stream(self._side_begin()):
+                lib.gemm_wgrad(dy, g, grads[k2w])
+        else:
+            lib.gemm_wgrad(dy, g, grads[k2w])
+        d_h = self.buf("d_h", (M, r))
+        self.gemm(dy, WT[k2w], d_h, dact_src=h, dact=lib.ACT_GELU, row_scale=rs, colsum_out=grads[k1b])
+
+        def _w1_grad():
+            G = self.buf("t_G", (r, D), torch.float32)
+            lib.gemm_wgrad(d_h, o, G)                                           # d_h^T o, fp32
+            Gb = self.buf("t_Gb", (r, D))
+            Gb.copy_(G)
+            Gw = self.buf("t_Gw", (r, D))
+            self.gemm(Gb, W[pre + "attn.out_proj.weight"], Gw)                          # (d_h^T o) Wo^T on the tensor cores
+            grads[k1w].copy_(Gw)
+            grads[k1w].addr_(grads[k1b], W[pre + "attn.out_proj.bias"].float())        # + db1 (x) bo
+
+        if side:
+            with torch.cuda.stream(self._side_begin()):       # ordered after the d_h GEMM (and its fused db1 column sums)
+                _w1_grad()
+        self.gemm(d_h, W[pre + "T_Adapter.w1oT"], d_o_out)
+        if not side:
+            _w1_grad()
+
     def _block_bwd(self, i, dx, W, WT, grads, d, S, prev_mask_m=None):
         M, D, n = d.M, d.D, d.n
         pre = f"transformer.resblocks.{i}."
@@ -467,11 +538,14 @@ class Engine:
         self._ln_bwd(d_xn1, S["x1"], m2, r2, W[pre + "ln_1.weight"], dx2, dx1,
                      colsum_out=grads[pre + "T_Adapter.D_fc2.bias"], colsum_row_scale=mask_t)
         # ---------------- temporal: x1 = x + mask_t * T_Adapter(attn(ln_1(x)))
-        d_at = self.buf("d_a", (M, D))
-        self._adapter_bwd("T_Adapter", pre, dx1, S["a_t"], S["h_t"], S["g_t"], W, WT, grads, d, mask_t, 1.0, d_at, None,
-                          db2_fused=True, lazy_join=True)
         d_ot = self.buf("d_o", (M, D))
-        self.gemm(d_at, WT[pre + "attn.out_proj.weight"], d_ot)
+        if self.t_fused:
+            self._t_fused_bwd(pre, dx1, S, W, WT, grads, d, mask_t, d_ot)
+        else:
+            d_at = self.buf("d_a", (M, D))
+            self._adapter_bwd("T_Adapter", pre, dx1, S["a_t"], S["h_t"], S["g_t"], W, WT, grads, d, mask_t, 1.0, d_at, None,
+                              db2_fused=True, lazy_join=True)
+            self.gemm(d_at, WT[pre + "attn.out_proj.weight"], d_ot)
         lib.attn_temporal_bwd(S["qkv_t"], d_ot, d_qkv, d.B, d.T, n, d.heads)
         d_xn1t = self.buf("d_xn", (M, D))
         if d.num_tadapter == 2:
