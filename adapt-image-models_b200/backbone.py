@@ -10,6 +10,8 @@ No CPU / eager fallback: calling ``forward`` with a CPU tensor or without the bu
 """
 from __future__ import annotations
 
+import contextlib
+import logging
 import math
 import os
 from collections import OrderedDict
@@ -21,6 +23,9 @@ import torch.nn as nn
 from . import lib
 from .engine import Dims, Engine
 from .registry import BACKBONES
+
+_log = logging.getLogger("aimb200")
+_warned_default_block = False
 
 
 class LayerNorm(nn.LayerNorm):
@@ -84,11 +89,21 @@ class _BackboneFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mod, x, *params):
         ctx.mod = mod
-        return mod._run_forward(x, training=True)
+        out = mod._run_forward(x, training=True)
+        ctx.gen = mod._gen                  # which training forward's activations this node owns
+        return out
 
     @staticmethod
     def backward(ctx, dfeat):
         mod = ctx.mod
+        if ctx.gen != mod._gen or mod._step_ctx is None:
+            # one set of saved activations per module (stable pointers, CUDA-graph friendly): a later grad-enabled
+            # forward has overwritten the ones this backward needs
+            raise lib.AimbError(
+                "aimb200.ViT_CLIP keeps ONE training forward in flight: backward() of forward #%d was called after forward "
+                "#%d overwrote its saved activations.  Run backward before the next grad-enabled forward (batch the views "
+                "/ clips into one call, as Recognizer3D does), or use torch.no_grad() for forwards that need no gradient."
+                % (ctx.gen, mod._gen))
         grads = mod._run_backward(dfeat)
         return (None, None) + tuple(grads)
 
@@ -99,6 +114,15 @@ class ViT_CLIP(nn.Module):
                  drop_path_rate, num_tadapter=1, adapter_scale=0.5, pretrained=None, shift=False, checkpoint=False,
                  block: Optional[str] = None, compute_dtype: Optional[str] = None):
         super().__init__()
+        global _warned_default_block
+        if block is None and "AIMB200_BLOCK" not in os.environ and type(self).__name__ == "ViT_CLIP" and not _warned_default_block:
+            _warned_default_block = True
+            # The literal in-tree class of this name (vit_clip.py:199-288) is the fork block; the upstream AIM math that
+            # north_star / README GFLOPs / every vitclip_*.py config (num_tadapter) describe lives in the reference as class
+            # `AIM` (vitclip_aim.py).  Both are built here; say which one a bare `type='ViT_CLIP'` gets.
+            _log.warning("aimb200.ViT_CLIP: block not given -> 'aim' (upstream AIM block = reference class AIM, "
+                         "vitclip_aim.py:196-211).  Checkpoints trained with the in-tree vit_clip.py::ViT_CLIP need "
+                         "block='fork' (or AIMB200_BLOCK=fork); type='AIM' always selects the upstream block.")
         block = os.environ.get("AIMB200_BLOCK", block or "aim")
         if block not in ("aim", "fork"):
             raise ValueError("block must be 'aim' (upstream AIM math, vitclip_aim.py:196-211) or 'fork' (vit_clip.py:199-288)")
@@ -143,6 +167,8 @@ class ViT_CLIP(nn.Module):
         self._grad_sync = None
         self._input_norm = None
         self._step_ctx = None
+        self._gen = 0
+        self._norm_dev = None
 
     # ------------------------------------------------------------------ reference API
     def init_weights(self, pretrained=None):
@@ -202,6 +228,7 @@ class ViT_CLIP(nn.Module):
     def set_input_normalization(self, mean, std):
         """Fuse GPUNormalize (mmaction/utils/module_hooks.py:35-87) into the patch load: uint8 clips in."""
         self._input_norm = (torch.tensor(mean, dtype=torch.float32), torch.tensor(std, dtype=torch.float32))
+        self._norm_dev = None            # device copies are made once per device (no per-forward H2D: graph capturable)
 
     def attach_grad_sync(self, sync):
         """sync: object with ``bucket_done(flat_grad, lo, hi)`` and ``finish()`` (see parallel.GradSync)."""
@@ -327,7 +354,9 @@ class ViT_CLIP(nn.Module):
                 WT[n] = flat_t[o:o + k].view(c, r)
         if self._input_norm is not None:
             dev = self._flat.device
-            W["input_mean"], W["input_std"] = self._input_norm[0].to(dev), self._input_norm[1].to(dev)
+            if self._norm_dev is None or self._norm_dev[0] != dev:
+                self._norm_dev = (dev, self._input_norm[0].to(dev), self._input_norm[1].to(dev))
+            W["input_mean"], W["input_std"] = self._norm_dev[1], self._norm_dev[2]
         return W, WT
 
     # ------------------------------------------------------------------ forward / backward
@@ -358,7 +387,11 @@ class ViT_CLIP(nn.Module):
         masks = self._drop_masks(d, x.device) if training else None
         if training:
             self._step_ctx = (W, WT, d)
-        return self._engine.forward(x.contiguous(), W, d, training, masks, WT)
+            self._gen += 1
+        if x.dtype == torch.float16:      # apex O1 / auto_fp16 callers (recognizers/base.py:141): exact in fp32 mode, and the
+            x = x.to(self.compute_dtype)  # patch GEMM reads bf16 anyway in bf16 mode
+        with torch.cuda.device(x.device):     # kernels and streams follow the tensors, not the caller's current device
+            return self._engine.forward(x.contiguous(), W, d, training, masks, WT)
 
     def _run_backward(self, dfeat: torch.Tensor):
         W, WT, d = self._step_ctx
@@ -384,7 +417,8 @@ class ViT_CLIP(nn.Module):
                 sync.bucket_done(flat_grad, lo, done_hi[0])
                 done_hi[0] = lo
 
-        self._engine.backward(dfeat.reshape(d.B, d.D, d.T).float(), W, WT, grads, on_done)
+        with torch.cuda.device(flat_grad.device) if flat_grad.is_cuda else contextlib.nullcontext():
+            self._engine.backward(dfeat.reshape(d.B, d.D, d.T).float(), W, WT, grads, on_done)
         if sync is not None:
             if done_hi[0] > 0:
                 sync.bucket_done(flat_grad, 0, done_hi[0])
@@ -419,3 +453,20 @@ class ViT_CLIP(nn.Module):
         else:
             feat = self._run_forward(x, training=False)
         return feat.view(B, self.width, T, 1, 1)
+
+
+@BACKBONES.register_module()
+class AIM(ViT_CLIP):
+    """Registry name of the reference's upstream-math class (vitclip_aim.py:340-344, default path wind_attn=False):
+    same parameter tree, always block='aim'.  The window-attention / prompt options of that class are research variants
+    outside the built path and are rejected rather than silently ignored."""
+
+    def __init__(self, input_resolution: int, num_frames: int, patch_size: int, width: int, layers: int, heads: int,
+                 drop_path_rate, num_tadapter=1, adapter_scale=0.5, pretrained=None, prompt=True, wind_attn=False,
+                 window_size=(32, 2, 2), not_shift=True, compute_dtype: Optional[str] = None):
+        if wind_attn:
+            raise NotImplementedError("AIM(wind_attn=True) (3-D shifted-window path, vitclip_aim.py:212-287) is outside the "
+                                      "built path; wind_attn=False is the upstream AIM block")
+        super().__init__(input_resolution, num_frames, patch_size, width, layers, heads, drop_path_rate,
+                         num_tadapter=num_tadapter, adapter_scale=adapter_scale, pretrained=pretrained, block="aim",
+                         compute_dtype=compute_dtype)

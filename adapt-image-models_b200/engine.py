@@ -61,6 +61,9 @@ class Engine:
         self.dtype = dtype
         self.device = device
         self._bufs: Dict[tuple, torch.Tensor] = {}
+        self._buf_mode: Dict[tuple, str] = {}      # which mode ("train" / "eval") created a buffer
+        self._mode_sig: Dict[str, tuple] = {}      # problem size last seen per mode
+        self._cur_mode = "eval"
         self.saved: Optional[dict] = None
         self.attn_impl = lib.IMPL_AUTO
         self.gemm_impl = lib.IMPL_AUTO
@@ -91,7 +94,20 @@ class Engine:
         if t is None:
             t = torch.empty(shape, dtype=dtype, device=self.device)
             self._bufs[k] = t
+            self._buf_mode[k] = self._cur_mode
         return t
+
+    def _enter_mode(self, mode: str, d: "Dims"):
+        """Buffers are cached by exact shape (stable pointers for TMA descriptors / CUDA graphs).  When the batch size of
+        a mode changes (last partial batch, a different number of views), the old set is dropped instead of living next
+        to the new one: at 32-frame ViT-L sizes a second set of saved activations is tens of GB."""
+        self._cur_mode = mode
+        sig = (d.B, d.T, d.n, d.D, d.L)
+        if self._mode_sig.get(mode) not in (None, sig):
+            for k in [k for k, m in self._buf_mode.items() if m == mode]:
+                del self._bufs[k]
+                del self._buf_mode[k]
+        self._mode_sig[mode] = sig
 
     # ------------------------------------------------------------------ side stream for the weight-gradient kernels
     def _side_begin(self):
@@ -139,6 +155,8 @@ class Engine:
 
     def release(self):
         self._bufs.clear()
+        self._buf_mode.clear()
+        self._mode_sig.clear()
         self.saved = None
 
     def gemm(self, a, w, out, **kw):
@@ -152,6 +170,7 @@ class Engine:
         M, D, r, n, BT = d.M, d.D, d.r, d.n, d.BT
         sv = {"d": d, "blocks": []} if training else None
         key = "train" if training else "eval"
+        self._enter_mode(key, d)
         # ---- stem
         cols = self.buf("cols", (BT * d.G * d.G, d.kpad))
         lib.im2col(x, cols, d.patch, W.get("input_mean"), W.get("input_std"))
@@ -415,8 +434,10 @@ class Engine:
         on_block_done(i) is called after block i's gradients are complete (i = L for ln_post, -1 for
         temporal_embedding) so the caller can start that bucket's all-reduce."""
         sv = self.saved
-        assert sv is not None, "backward() without a training forward"
+        if sv is None:
+            raise lib.AimbError("Engine.backward() without a pending training forward")
         d: Dims = sv["d"]
+        self._cur_mode = "train"
         M, D, n = d.M, d.D, d.n
         dx = self.buf("dx", (M, D))
         tm, tr = sv["tail"]

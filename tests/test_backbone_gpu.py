@@ -284,3 +284,79 @@ def test_cfg2_batch8_droppath_all_gradients():
     assert len(grads) == 147
     assert err < 2e-2 and torch.equal(lg.detach().cpu().argmax(1), ref_lg.argmax(1))
     assert worst < 6e-2
+
+
+# ---------------------------------------------------------------------------------------------- module-level behaviour
+def test_second_inflight_forward_raises_clear_error():
+    """One set of saved activations per module: backward of an overwritten forward is a clear AimbError, not a wrong
+    gradient (the reference has no such limit; Recognizer3D batches views into one call, recognizer3d.py:16)."""
+    from aimb200 import lib
+    cfg = O.OracleCfg(**TINY, block="aim")
+    m = _build(cfg, "bf16").train()
+    x = O.fixture_clip(cfg, 2).cuda()
+    f1 = m(x)
+    f2 = m(x)
+    f2.sum().backward()                                   # the latest forward is fine
+    with pytest.raises(lib.AimbError, match="ONE training forward in flight"):
+        f1.sum().backward()
+    f3 = m(x)                                             # and the module keeps working afterwards
+    f3.sum().backward()
+    with torch.no_grad():                                 # forwards without grad never disturb a pending one
+        f4 = m(x)
+        m(x)
+    assert torch.isfinite(f4).all()
+
+
+def test_fp16_input_accepted():
+    """auto_fp16 / apex O1 callers hand the backbone half-precision clips (recognizers/base.py:141)."""
+    cfg = O.OracleCfg(**TINY, block="aim")
+    x = O.fixture_clip(cfg, 2)
+    for mode, tol in (("fp32", 2e-3), ("bf16", 2e-2)):
+        m = _build(cfg, mode).eval()
+        with torch.no_grad():
+            a = m(x.half().cuda()).cpu()
+            b = m(x.half().float().cuda()).cpu()
+        assert O.normalised_max_err(a, b) < (1e-6 if mode == "fp32" else 5e-3)
+        ref = O.backbone(O.fixture_state_dict(cfg), x.half().float(), cfg)
+        assert O.normalised_max_err(a, ref) < tol
+
+
+def test_batch_size_change_drops_the_old_buffer_set():
+    cfg = O.OracleCfg(**TINY, block="aim")
+    m = _build(cfg, "bf16").eval()
+    with torch.no_grad():
+        m(O.fixture_clip(cfg, 4).cuda())
+        n4 = sum(t.numel() * t.element_size() for t in m._engine._bufs.values())
+        m(O.fixture_clip(cfg, 2).cuda())
+        n2 = sum(t.numel() * t.element_size() for t in m._engine._bufs.values())
+        out = m(O.fixture_clip(cfg, 3).cuda())
+    assert n2 < n4 and out.shape[0] == 3
+
+
+def test_distributed_data_parallel_wrapper_sees_ordinary_grads():
+    """stock (MM)DistributedDataParallel around the recognizer (apis/train.py:106-110).  World size 1 on
+    this box: what is checked is that DDP's autograd hooks, bucket copies and the flat-buffer parameter views coexist."""
+    import torch.distributed as dist
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    cfg = O.OracleCfg(**TINY, block="aim")
+    x = O.fixture_clip(cfg, 2).cuda()
+    ref = _build(cfg, "bf16").train()
+    ref(x).square().mean().backward()
+    want = {k: p.grad.clone() for k, p in ref.named_parameters() if p.requires_grad}
+    own_pg = not dist.is_initialized()
+    if own_pg:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("nccl", rank=0, world_size=1)
+    try:
+        m = DDP(_build(cfg, "bf16").train(), device_ids=[0], broadcast_buffers=False, find_unused_parameters=False)
+        for _ in range(2):                                # second step: the flat-buffer views are already in place
+            m.zero_grad(set_to_none=True)
+            m(x).square().mean().backward()
+        got = {k: p.grad for k, p in m.module.named_parameters() if p.requires_grad}
+        assert sorted(got) == sorted(want)
+        for k in want:
+            assert torch.allclose(got[k], want[k], rtol=1e-4, atol=1e-7), k
+    finally:
+        if own_pg:
+            dist.destroy_process_group()
