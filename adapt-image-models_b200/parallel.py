@@ -71,3 +71,29 @@ def allreduce_mean_(tensors: List[torch.Tensor], group=None):
         k = t.numel()
         t.copy_(flat[o:o + k].view_as(t))
         o += k
+
+
+# ------------------------------------------------------------------------------------------------ inference sharding
+# Multi-GPU test of the reference: DistributedSampler(shuffle=False) hands rank r the items r, r+W, r+2W, ... (padded by
+# wrapping around so that every rank gets the same count, datasets/samplers/distributed_sampler.py:27-43), every rank
+# scores its share, and collect_results_gpu (apis/test.py:159-199) pickles the per-rank lists, all_gathers the bytes,
+# interleaves them back and drops the padding.  Here the payload is what it always is on this path - fp32 class scores -
+# so it is one fixed-shape all_gather of [k, classes] and an interleave on the device: no pickle, no second collective.
+def shard_indices(n_items: int, rank: int, world: int) -> List[int]:
+    """Indices of rank `rank` (rank-strided, padded by wrap-around to ceil(n_items / world) per rank)."""
+    if n_items <= 0:
+        return []
+    per = -(-n_items // world)
+    return [(rank + j * world) % n_items for j in range(per)]
+
+
+def gather_scores(local: torch.Tensor, n_items: int, group=None) -> torch.Tensor:
+    """local [k, C] = scores of this rank's shard_indices(n_items, rank, world) -> [n_items, C] in dataset order, on every
+    rank (apis/test.py:186-199: `ordered_results.extend(zip(*part_list))`, then `[:size]`)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local[:n_items]
+    world = dist.get_world_size(group)
+    parts = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(parts, local.contiguous(), group=group)
+    inter = torch.stack(parts, dim=1).reshape(-1, local.shape[-1])        # item j of rank r -> position j * world + r
+    return inter[:n_items]

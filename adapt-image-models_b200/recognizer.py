@@ -85,6 +85,27 @@ class Recognizer3D(nn.Module):
         scores = [self.cls_head(self.backbone(imgs[i:i + step])) for i in range(0, imgs.shape[0], step)]
         return self.average_clip(torch.cat(scores), num_segs)
 
+    @torch.no_grad()
+    def forward_test_sharded(self, imgs: torch.Tensor, n_videos: int, shard: str = "videos", group=None) -> torch.Tensor:
+        """Multi-GPU test (apis/test.py:54-97 + 159-199).  `imgs` is THIS rank's share:
+        shard='videos': [k, views, C, T, H, W] for the videos parallel.shard_indices(n_videos, rank, world); every rank
+                        averages its own views and the [k, classes] scores are gathered.
+        shard='views' : fewer videos than GPUs - the n_videos * views (video, view) pairs are dealt out the same way,
+                        imgs is [k, C, T, H, W]; the raw class scores are gathered first and `average_clip` runs on the
+                        gathered [n_videos * views, classes] (softmax-mean needs all views of a video).
+        Returns [n_videos, classes] on every rank."""
+        from .parallel import gather_scores
+        if shard == "videos":
+            return gather_scores(self.forward_test(imgs), n_videos, group)
+        if shard != "views":
+            raise ValueError("shard must be 'videos' or 'views'")
+        num_segs = self._views_per_video
+        step = self.max_testing_views or imgs.shape[0]
+        raw = torch.cat([self.cls_head(self.backbone(imgs[i:i + step])) for i in range(0, imgs.shape[0], step)])
+        return self.average_clip(gather_scores(raw, n_videos * num_segs, group), num_segs)
+
+    _views_per_video = 3          # 3-view testing of the K400 configs (vitclip_base_k400.py: ThreeCrop); set per dataset
+
     def forward(self, imgs, label=None, return_loss=True):
         if return_loss:
             if label is None:

@@ -1,13 +1,18 @@
 #!/usr/bin/env python
-"""bench.py — AIM ViT-B/16 8x224 training step (cfg2 of BASELINE.json) on N B200s, one process per GPU.
+"""bench.py — the AIM ViT_CLIP hot path on N B200s, one process per GPU.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg2|cfg3|cfg4|cfg5]
 
-A "step" = one pass of the hot path over one batch of synthetic clips: backbone forward, I3D head,
-cross-entropy, adapter-only backward, gradient all-reduce (N>1), AdamW.  8 clips per GPU (weak
-scaling; global batch 64 at N=8, the reference recipe, configs/recognition/vit/vitclip_base_k400.py:66-67).
-Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle port of the reference path on
-the host cores (the reference is pure Python/PyTorch-CPU; `/root/reference` does not travel to the GPU box).
+Default workload = cfg2 of BASELINE.json, the configuration the metric is quoted on: ViT-B/16 8x224 training step, 8
+clips per GPU (weak scaling; global batch 64 at N=8, the reference recipe, vitclip_base_k400.py:66-67).  A "step" = one
+pass of the hot path over one batch of synthetic clips: backbone forward, I3D head, cross-entropy, adapter-only backward,
+gradient all-reduce (N>1), AdamW.  cfg3 (16 frames) and cfg5 (ViT-L/14, 32 frames) are the same step on other shapes;
+cfg4 is the ViT-L/14 3-view inference (videos sharded over the ranks, class scores all-gathered every step).
+Clips are uint8 (as the reference's GPUNormalize pipeline delivers them, utils/module_hooks.py:35-87); the normalisation is
+fused into the patch load.  Prints ONE JSON line (rank 0).
+
+`--impl reference` times the UNMODIFIED reference backbone (vitclip_aim.py::AIM from the git-ignored baseline/_ref copy
+that __graft_entry__.build() stages; the oracle port only if that copy is missing) on the host cores with all threads.
 """
 from __future__ import annotations
 
@@ -27,35 +32,51 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 import torch.nn.functional as F  # noqa: E402
 
-METRIC = "AIM ViT-B/16 8x224 train clips/s"
-UNIT = "clips/s"
-CLIPS_PER_GPU = 8
 NUM_CLASSES = 400
-MODEL = dict(input_resolution=224, patch_size=16, num_frames=8, width=768, layers=12, heads=12, drop_path_rate=0.2,
-             num_tadapter=1, adapter_scale=0.5)       # vitclip_base_k400.py:5-8 with num_frames 32 -> 8 (k700 :6)
-TFLOP_PER_CLIP_STEP = 0.858    # BASELINE.md §2 (algorithmic: fwd 0.404 + bwd 1.12x)
-TFLOP_PER_CLIP_FWD = 0.404
+MEAN, STD = [122.769, 116.74, 104.04], [68.493, 66.63, 70.321]          # vitclip_base_k400.py:17-18
+VITB = dict(input_resolution=224, patch_size=16, width=768, layers=12, heads=12)
+VITL = dict(input_resolution=224, patch_size=14, width=1024, layers=24, heads=16)          # vitclip_large_k400.py:6
+ADAPT = dict(drop_path_rate=0.2, num_tadapter=1, adapter_scale=0.5)                       # vitclip_base_k400.py:5-8
+# TFLOP per clip (algorithmic): forward / training step
+CONFIGS = {
+    "cfg2": dict(model=dict(VITB, num_frames=8, **ADAPT), train=True, per_gpu=8, tflop=0.858, unit="clips/s",
+                 metric="AIM ViT-B/16 8x224 train clips/s",
+                 workload="AIM ViT-B/16 8x224 K400-shape training step (cfg2): 8 clips/GPU, fwd + I3D head + CE + "
+                          "adapter-only bwd + grad all-reduce + AdamW"),
+    "cfg3": dict(model=dict(VITB, num_frames=16, **ADAPT), train=True, per_gpu=8, tflop=1.719, unit="clips/s",
+                 metric="AIM ViT-B/16 16x224 train clips/s",
+                 workload="AIM ViT-B/16 16x224 training step (cfg3): 8 clips/GPU"),
+    "cfg5": dict(model=dict(VITL, num_frames=32, **ADAPT), train=True, per_gpu=int(os.environ.get("AIMB200_CFG5_CLIPS", "14")),
+                 tflop=15.94, unit="clips/s", metric="AIM ViT-L/14 32x224 train clips/s",
+                 workload="AIM ViT-L/14 32x224 bf16 training step (cfg5), batch sized for 180 GB HBM"),
+    "cfg4": dict(model=dict(VITL, num_frames=8, **ADAPT), train=False, per_gpu=8, views=3, tflop=5.60, unit="videos/s",
+                 metric="AIM ViT-L/14 8x224 3-view inference videos/s",
+                 workload="AIM ViT-L/14 8x224 inference (cfg4): 8 videos x 3 views per GPU per step, videos sharded over "
+                          "the ranks, 'prob' average over views, class scores all-gathered every step"),
+}
 
 
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
         d = json.load(open(p))
-        return d.get("bf16_tflops_sustained", 1389.8), d.get("hbm_gbs", 6542.1), "measured (MEASURED_PEAKS.json, sustained)"
-    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+        return (d.get("bf16_tflops_sustained", 1389.8), d.get("bf16_tflops", 1639.4), d.get("hbm_gbs", 6542.1),
+                "measured (MEASURED_PEAKS.json)")
+    return 1400.0, 1590.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, period_ms: int = 20):
         self.rows = []
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
-                                          "20", "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          str(period_ms), "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                         text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -73,7 +94,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
+        sm, pw, mx, reasons = [], [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             f = [c.strip() for c in r.split(",")]
@@ -82,48 +103,68 @@ class ClockSampler:
             try:
                 sm.append(float(f[0]))
                 mx = float(f[1])
+                if len(f) > 6:
+                    pw.append(float(f[6]))
             except ValueError:
                 continue
             for nme, v in zip(names, f[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(nme)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_max": max(pw) if pw else None}
 
 
 # ----------------------------------------------------------------------------------------------- CPU reference arm
-def cpu_reference_step_rate(steps: int, warmup: int, clips: int = 1):
-    """Training step of the oracle port on the host cores: fwd + CE + bwd (trainable set) + AdamW, `clips` per step."""
+def cpu_reference_rate(cfg_name: str, steps: int, warmup: int, items: int):
+    """One step of the same workload on the host cores, all threads.  Real reference class (vitclip_aim.py::AIM loaded
+    unmodified through oracle/ref_loader.py's stand-ins for timm / mmcv) when the baseline/_ref copy or the mounted tree
+    is there, else the oracle port.  Returns (items/s, s/step, cores, kind, detail)."""
     from oracle import aim_oracle as O
+    from oracle import ref_loader
+    C = CONFIGS[cfg_name]
+    mc = C["model"]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = O.OracleCfg(input_resolution=224, num_frames=8, patch_size=16, width=768, layers=12, heads=12)
-    p = O.fixture_state_dict(cfg)
-    params = {k: v.clone().requires_grad_(O.is_trainable(k)) for k, v in p.items()}
+    cfg = O.OracleCfg(input_resolution=mc["input_resolution"], num_frames=mc["num_frames"], patch_size=mc["patch_size"],
+                      width=mc["width"], layers=mc["layers"], heads=mc["heads"])
+    sd = O.fixture_state_dict(cfg)
     hw, hb = O.fixture_head(cfg, NUM_CLASSES)
-    hw.requires_grad_(True), hb.requires_grad_(True)
-    train = [v for v in params.values() if v.requires_grad] + [hw, hb]
-    opt = torch.optim.AdamW(train, lr=3e-4, weight_decay=0.05)
-    x = O.fixture_clip(cfg, clips)
-    labels = torch.arange(clips) % NUM_CLASSES
+    views = C.get("views", 1)
     g = torch.Generator().manual_seed(0)
-    rates = torch.linspace(0, MODEL["drop_path_rate"], cfg.layers)
+    xu = torch.randint(0, 256, (items * views, 3, cfg.num_frames, 224, 224), dtype=torch.uint8, generator=g)
+    mean, std = torch.tensor(MEAN).view(1, 3, 1, 1, 1), torch.tensor(STD).view(1, 3, 1, 1, 1)
+    labels = torch.arange(items) % NUM_CLASSES
+    if ref_loader.available():
+        kind, detail = "reference", f"vitclip_aim.py::AIM ({ref_loader.source()}), torch CPU fp32"
+        net = ref_loader.reference_module(cfg, sd, drop_path_rate=mc["drop_path_rate"])
+        net.train(C["train"])
+        head = torch.nn.Linear(cfg.width, NUM_CLASSES)
+        with torch.no_grad():
+            head.weight.copy_(hw), head.bias.copy_(hb)
+        params = [p for p in net.parameters() if p.requires_grad] + list(head.parameters())
+        fwd = lambda x: net(x)                                                   # noqa: E731
+    else:
+        kind, detail = "port", "oracle port (oracle/aim_oracle.py), torch CPU fp32"
+        pr = {k: v.clone().requires_grad_(O.is_trainable(k) and C["train"]) for k, v in sd.items()}
+        hw.requires_grad_(C["train"]), hb.requires_grad_(C["train"])
+        head = lambda t: t @ hw.T + hb                                           # noqa: E731
+        params = [v for v in pr.values() if v.requires_grad] + [hw, hb]
+        fwd = lambda x: O.backbone(pr, x, cfg)                                   # noqa: E731
+    opt = torch.optim.AdamW(params, lr=3e-4, weight_decay=0.05) if C["train"] else None
 
     def step():
-        masks = []
-        for i in range(cfg.layers):
-            keep = 1 - float(rates[i])
-            if keep == 1.0:
-                masks.append((None, None))
-            else:
-                masks.append(tuple((torch.rand(cfg.tokens, generator=g) < keep).float() / keep for _ in range(2)))
-        feat = O.backbone(params, x, cfg, masks)
-        lg = F.dropout(feat.mean(dim=(2, 3, 4)), 0.5, True) @ hw.T + hb
-        loss = F.cross_entropy(lg, labels)
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        opt.step()
-        return float(loss)
+        x = (xu.float() - mean) / std                                            # GPUNormalize (module_hooks.py:35-87)
+        if C["train"]:
+            feat = fwd(x)
+            lg = head(F.dropout(feat.mean(dim=(2, 3, 4)), 0.5, True))
+            loss = F.cross_entropy(lg, labels)
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+            return float(loss)
+        with torch.no_grad():
+            lg = head(fwd(x).mean(dim=(2, 3, 4)))
+            return float(F.softmax(lg.view(items, views, -1), dim=2).mean(dim=1).sum())
 
     for _ in range(warmup):
         step()
@@ -131,22 +172,27 @@ def cpu_reference_step_rate(steps: int, warmup: int, clips: int = 1):
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    return clips * steps / dt, dt / steps, cores
+    return items * steps / dt, dt / steps, cores, kind, detail
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 10)), max(0, min(args.warmup, 2))
-    v, spstep, cores = cpu_reference_step_rate(steps, warmup, clips=1)
-    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+    C = CONFIGS[args.config]
+    items = C["per_gpu"] if args.config in ("cfg2", "cfg3") else (2 if args.config == "cfg4" else 1)
+    steps, warmup = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))
+    v, spstep, cores, kind, detail = cpu_reference_rate(args.config, steps, warmup, items)
+    same = items == C["per_gpu"]
+    out = {"impl": "reference", "metric": C["metric"], "value": v, "unit": C["unit"], "n_gpus": args.gpus, "steps": steps,
            "warmup": warmup, "ms_per_step": spstep * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "AIM ViT-B/16 8x224 training step (fwd+CE+bwd adapters+AdamW), 1 clip per step (bounded sample of the 8-clips/GPU workload)"},
-           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                            "sample": f"{steps} steps x 1 clip, torch CPU fp32, {cores} threads"},
-           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+           "config": {"workload": C["workload"] + (" [reference arm: the same step on the host CPU]" if same else
+                                                   f" [reference arm: bounded sample, {items} per step]"),
+                      "per_step": items, "same_items_per_step_as_gpu_arm": same},
+           "cpu_baseline": {"value": v, "unit": C["unit"], "cores": cores, "kind": kind,
+                            "sample": f"{steps} steps x {items} {C['unit'].split('/')[0]} ({detail}, {cores} threads)"},
+           "e2e": {"value": v, "unit": C["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
 
@@ -154,31 +200,37 @@ def run_reference(args):
 class Trainer:
     """Minimal recognizer glue around the backbone: I3D head (T-mean, dropout .5, FC), CE, AdamW, grad sync."""
 
-    def __init__(self, device, world, dtype="bf16", seed=0):
+    def __init__(self, device, world, model_cfg, dtype="bf16", seed=0, train=True, views=1):
         import aimb200
         self.aimb = aimb200
         torch.manual_seed(seed)
-        m = aimb200.build_backbone(dict(type="ViT_CLIP", compute_dtype=dtype, **MODEL))
+        m = aimb200.build_backbone(dict(type="ViT_CLIP", block="aim", compute_dtype=dtype, **model_cfg))
         m.init_weights()                                   # random init (no CLIP weights offline) + freeze rule
+        m.set_input_normalization(MEAN, STD)               # uint8 clips in: GPUNormalize fused into the patch load
         g = torch.Generator().manual_seed(seed + 1)
         with torch.no_grad():                              # init_weights() zeroes D_fc2 / biases / temporal_embedding:
             for n, p in m.named_parameters():              # randomise them so the adapter paths do real work
                 if "D_fc2" in n or n.endswith("bias") or "temporal_embedding" in n:
                     p.copy_(0.02 * torch.randn(p.shape, generator=g))
-        self.backbone = m.to(device).train()
-        self.hw = (0.01 * torch.randn(NUM_CLASSES, MODEL["width"], generator=g)).to(device).requires_grad_(True)
-        self.hb = torch.zeros(NUM_CLASSES).to(device).requires_grad_(True)   # I3DHead init (i3d_head.py:49-51)
-        self.world = world
-        self.sync = aimb200.GradSync(bucket_blocks=int(os.environ.get("AIMB200_BUCKET_BLOCKS", "3"))) if world > 1 else None
-        if self.sync is not None:
-            self.backbone.attach_grad_sync(self.sync)
-        decay = [p for n, p in self.backbone.named_parameters() if p.requires_grad and "Adapter" in n and n.endswith("weight")]
-        nodecay = [p for n, p in self.backbone.named_parameters() if p.requires_grad and not ("Adapter" in n and n.endswith("weight"))]
-        self.opt = torch.optim.AdamW([{"params": decay + [self.hw], "weight_decay": 0.05},
-                                      {"params": nodecay + [self.hb], "weight_decay": 0.0}], lr=3e-4, fused=True,
-                                     capturable=True)
+        self.backbone = m.to(device).train(train)
+        W = model_cfg["width"]
+        self.hw = (0.01 * torch.randn(NUM_CLASSES, W, generator=g)).to(device).requires_grad_(train)
+        self.hb = torch.zeros(NUM_CLASSES).to(device).requires_grad_(train)   # I3DHead init (i3d_head.py:49-51)
+        self.world, self.views, self.train = world, views, train
+        self.sync = None
+        if train:
+            self.sync = aimb200.GradSync(bucket_blocks=int(os.environ.get("AIMB200_BUCKET_BLOCKS", "3"))) if world > 1 else None
+            if self.sync is not None:
+                self.backbone.attach_grad_sync(self.sync)
+            decay = [p for n, p in self.backbone.named_parameters() if p.requires_grad and "Adapter" in n and n.endswith("weight")]
+            nodecay = [p for n, p in self.backbone.named_parameters() if p.requires_grad and not ("Adapter" in n and n.endswith("weight"))]
+            self.opt = torch.optim.AdamW([{"params": decay + [self.hw], "weight_decay": 0.05},
+                                          {"params": nodecay + [self.hb], "weight_decay": 0.0}], lr=3e-4, fused=True,
+                                         capturable=True)
 
     def step(self, x, labels):
+        if not self.train:
+            return self.infer(x, labels)
         feat = self.backbone(x)
         pooled = F.dropout(feat.mean(dim=(2, 3, 4)), 0.5, True)
         logits = F.linear(pooled, self.hw, self.hb)
@@ -189,6 +241,17 @@ class Trainer:
             self.aimb.parallel.allreduce_mean_([self.hw.grad, self.hb.grad])
         self.opt.step()
         return loss
+
+    @torch.no_grad()
+    def infer(self, x, labels):
+        """cfg4: x [videos, views, 3, T, H, W] (this rank's share) -> 'prob' average over the views
+        (recognizers/base.py:186-192), scores of all ranks gathered (apis/test.py:159-199); returns the top-1 hit rate."""
+        n = x.shape[0]
+        feat = self.backbone(x.reshape((-1,) + x.shape[2:]))
+        lg = F.linear(feat.mean(dim=(2, 3, 4)), self.hw, self.hb)
+        prob = F.softmax(lg.view(n, self.views, -1), dim=2).mean(dim=1)
+        allp = self.aimb.gather_scores(prob, n * self.world)
+        return (allp[:n].argmax(1) == labels).float().mean()
 
 
 def run_ours(args):
@@ -205,10 +268,13 @@ def run_ours(args):
     import aimb200
     from aimb200 import lib
     lib.load()
-    tr = Trainer(dev, world, dtype=args.dtype)
-    B = CLIPS_PER_GPU
+    C = CONFIGS[args.config]
+    mc = C["model"]
+    B, views, T = C["per_gpu"], C.get("views", 1), mc["num_frames"]
+    tr = Trainer(dev, world, mc, dtype=args.dtype, train=C["train"], views=views)
     g = torch.Generator().manual_seed(2 + rank)
-    host_x = torch.randn(B, 3, 8, 224, 224, generator=g).pin_memory()      # synthetic clips, K400 shape
+    shape = (B, views, 3, T, 224, 224) if not C["train"] else (B, 3, T, 224, 224)
+    host_x = torch.randint(0, 256, shape, dtype=torch.uint8, generator=g).pin_memory()       # synthetic uint8 clips
     host_y = torch.randint(0, NUM_CLASSES, (B,), generator=g).pin_memory()
     dev_x, dev_y = host_x.to(dev), host_y.to(dev)
     l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -237,11 +303,10 @@ def run_ours(args):
     captured_launches = None
     if use_graph:
         l_before = lib.launches
-        try:     # the whole step (incl. the bucketed NCCL all-reduces at N>1) replayed as one CUDA graph
+        try:     # the whole step (incl. the bucketed NCCL all-reduces / the score all-gather at N>1) replayed as one CUDA graph
             graphed = aimb200.GraphedStep(tr.step, [dev_x, dev_y], warmup=3,
-                                          before_capture=lambda: tr.opt.zero_grad(set_to_none=True))
-            # launches recorded while capturing == launches replayed per step
-            captured_launches = (lib.launches - l_before) // 4
+                                          before_capture=(lambda: tr.opt.zero_grad(set_to_none=True)) if C["train"] else None)
+            captured_launches = (lib.launches - l_before) // 4          # 3 warm-up runs + the capture
             step_fn = graphed
         except Exception as e:   # noqa: BLE001  (capture unsupported by this NCCL/driver combination -> eager launches)
             if rank == 0:
@@ -258,8 +323,8 @@ def run_ours(args):
         return step_fn(dev_x, dev_y)
 
     losses = []
-    # ---- end-to-end: every step's clips come from pinned host memory and every step's loss is read back on the host.
-    # As a prefetching data loader + asynchronous logging would: the H2D copy of step k+1 runs on a copy stream while
+    # ---- end-to-end: every step's uint8 clips come from pinned host memory and every step's loss is read back on the
+    # host.  As a prefetching data loader + asynchronous logging would: the H2D copy of step k+1 runs on a copy stream while
     # step k computes, and the loss of step k-1 is read while step k runs (the reference syncs twice per iteration,
     # heads/base.py:90, recognizers/base.py:242).
     copy_stream = torch.cuda.Stream(device=dev)
@@ -297,7 +362,7 @@ def run_ours(args):
         prefetch(1 - slot)                                   # H2D of the next step's clips, overlapped with this step
         if k > 0:
             ev_done[1 - slot].synchronize()
-            losses.append(float(loss_pinned[1 - slot]))      # D2H read of the previous step's loss
+            losses.append(float(loss_pinned[1 - slot]))      # D2H read of the previous step's result
         e2e_state["k"] = k + 1
 
     for _ in range(max(3, args.warmup)):
@@ -317,87 +382,97 @@ def run_ours(args):
     losses.append(float(loss_pinned[(e2e_state["k"] - 1) % 2]))
     value = world * B / (ms_step / 1e3)
     e2e = world * B / (ms_e2e / 1e3)
+    peak_mem = torch.cuda.max_memory_allocated(dev) / 2 ** 30
 
-    # ---- roofline of the dominant kernel (tcgen05 GEMM): CUDA events around every GEMM launch, live, same steps
-    peak_tf, peak_hbm, peak_src = _peaks()
-    recs, other = [], []
+    # ---- sustained: the headline region is a fraction of a second at boost clocks; the same step for >= 5 s shows what the
+    # part holds under its power cap (MEASURED_PEAKS.json: ~1.33 GHz median under seconds-long tensor load)
+    sustained = None
+    if args.sustain_s > 0:
+        n_sus = max(args.steps, int(args.sustain_s * 1e3 / max(ms_step + flush_ms, 1e-3)) + 1)
+        s2 = ClockSampler(local, period_ms=100) if rank == 0 else None
+        ms_sus = timed(step_resident, n_sus) / n_sus - flush_ms
+        ck = s2.stop() if s2 else None
+        sustained = {"value": world * B / (ms_sus / 1e3), "unit": C["unit"], "ms_per_step": ms_sus, "steps": n_sus,
+                     "seconds": n_sus * (ms_sus + flush_ms) / 1e3, "clocks": ck}
+
+    # ---- roofline of the dominant kernel (tcgen05 GEMM).  The GEMM launches of one step are recorded (same operands, same
+    # buffers) and replayed back to back as ONE CUDA graph: device time of the GEMMs alone, without per-launch event or
+    # Python overhead (round-1 timed eager launches with an event pair each, which overstated kernel time by ~30 %).
+    peak_sus, peak_burst, peak_hbm, peak_src = _peaks()
+    calls = []
     orig = lib.gemm_nt
 
-    def timed_gemm(a, w, out, impl=lib.IMPL_AUTO, **kw):
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        r = orig(a, w, out, impl=impl, **kw)
-        e.record()
-        recs.append((s, e, 2.0 * a.shape[0] * w.shape[0] * a.shape[1]))
-        return r
+    def logging_gemm(a, w, out, impl=lib.IMPL_AUTO, **kw):
+        calls.append((a, w, out, impl, kw))
+        return orig(a, w, out, impl=impl, **kw)
 
-    # every other C-ABI call is timed the same way (events on the stream it is launched on), so that the GEMM's share
-    # of the step is a share of DEVICE time, comparable with the committed ncu launch list (profiles/r1_launch_list.md)
-    other_names = ["layernorm_fwd", "layernorm_bwd", "im2col", "stem_assemble_ln", "temb_grad", "tail_fwd", "tail_bwd",
-                   "gemm_wgrad", "adapter_fused", "colsum", "transpose", "transpose_batched", "attn_spatial_fwd",
-                   "attn_spatial_bwd", "attn_temporal_fwd", "attn_temporal_bwd"]
-    saved = {n: getattr(lib, n) for n in other_names if hasattr(lib, n)}
-
-    def mk(fn):
-        def f(*a, **k):
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            r = fn(*a, **k)
-            e.record()
-            other.append((s, e))
-            return r
-        return f
-
-    for n, fn in saved.items():
-        setattr(lib, n, mk(fn))
-    lib.gemm_nt = timed_gemm
     import aimb200.engine as eng
-    eng.lib.gemm_nt = timed_gemm
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    nprof = min(args.steps, 5)
-    for _ in range(nprof):
-        tr.step(dev_x, dev_y)
-    e1.record()
-    barrier()
+    lib.gemm_nt = logging_gemm
+    eng.lib.gemm_nt = logging_gemm
+    tr.step(dev_x, dev_y)
     lib.gemm_nt = orig
     eng.lib.gemm_nt = orig
-    for n, fn in saved.items():
-        setattr(lib, n, fn)
-    gemm_ms = sum(s.elapsed_time(e) for s, e, _ in recs)
-    other_ms = sum(s.elapsed_time(e) for s, e in other)
-    gemm_fl = sum(f for _, _, f in recs)
-    prof_ms = e0.elapsed_time(e1)
+    torch.cuda.synchronize()
+    gemm_fl = sum(2.0 * a.shape[0] * w.shape[0] * a.shape[1] for a, w, _, _, _ in calls)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for a, w, o_, impl, kw in calls:
+            orig(a, w, o_, impl=impl, **kw)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    gg = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gg):
+        for a, w, o_, impl, kw in calls:
+            orig(a, w, o_, impl=impl, **kw)
+
+    def gemm_replay():
+        l2_flush.zero_()
+        gg.replay()
+
+    for _ in range(2):
+        gemm_replay()
+    gemm_ms = timed(gemm_replay, 5) / 5 - flush_ms
     achieved = gemm_fl / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
-    if os.path.isfile(tp):      # dram__bytes_read+write per GEMM launch from the committed ncu --set full capture
-        traffic = json.load(open(tp)).get("avg_dram_bytes_per_launch")
-    roofline = {"bound": "tensor", "kernel": "gemm_tc4_kernel / gemm_tc_kernel (TMA + tcgen05/TMEM bf16 GEMM, fused epilogues)", "achieved": achieved,
-                "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic, "peak_source": peak_src,
-                "launches_per_step": len(recs) // nprof, "avg_launch_us": gemm_ms * 1e3 / max(1, len(recs)),
-                "share_of_step": gemm_ms / max(1e-9, gemm_ms + other_ms),
-                "share_basis": "device time of all aimb200 kernel launches in the profiled eager steps (CUDA events per launch)",
-                "share_of_eager_wall": gemm_ms / prof_ms,
-                "step_tflops_algorithmic": TFLOP_PER_CLIP_STEP * B / (ms_step / 1e3),
-                "step_frac_of_peak": TFLOP_PER_CLIP_STEP * B / (ms_step / 1e3) / peak_tf}
+
+    def prof(name, key=None):
+        p = os.path.join(ROOT, "profiles", name)
+        if not os.path.isfile(p):
+            return None
+        d = json.load(open(p))
+        return d.get(key) if key else d
+
+    tensor_pipe = prof("r2_step_tensor_pipe.json")
+    step_tf = C["tflop"] * B / (ms_step / 1e3)
+    roofline = {"bound": "tensor", "kernel": "gemm_tc4_kernel (TMA + tcgen05/TMEM bf16 GEMM, fused epilogues): every nn.Linear forward and dgrad",
+                "achieved": achieved, "peak": peak_sus, "unit": "TFLOP/s", "frac": achieved / peak_sus,
+                "peak_burst": peak_burst, "frac_of_burst_peak": achieved / peak_burst, "peak_source": peak_src,
+                "traffic": prof("r2_gemm_traffic.json", "avg_dram_bytes_per_launch") or prof("r1_gemm_traffic.json", "avg_dram_bytes_per_launch"),
+                "launches_per_step": len(calls), "avg_launch_us": gemm_ms * 1e3 / max(1, len(calls)),
+                "timing": "the step's GEMM launches replayed back to back as one CUDA graph (CUDA events around the replay, L2 flushed before it)",
+                "share_of_step": gemm_ms / ms_step,
+                "share_basis": "GEMM-only graph replay time / full step graph time (the step graph overlaps weight-gradient and reduction branches with the GEMM chain)",
+                "step_tflops_algorithmic": step_tf, "step_frac_of_sustained_peak": step_tf / peak_sus,
+                "step_frac_of_burst_peak": step_tf / peak_burst, "step_frac_of_nominal_2250": step_tf / 2250.0,
+                "tensor_pipe_time_weighted": tensor_pipe}
 
     if rank == 0:
-        v_cpu, sp, cores = cpu_reference_step_rate(2, 1, clips=1) if world == 1 else (None, None, None)
-        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-               "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-               "dtype": args.dtype, "data": "synthetic",
-               "config": {"workload": "AIM ViT-B/16 8x224 K400-shape training step (cfg2): 8 clips/GPU, fwd + I3D head + CE + "
-                          "adapter-only bwd + grad all-reduce + AdamW", "global_batch": world * B, "clips_per_gpu": B,
-                          "parallelism": f"dp{world}", "block": "aim", "cuda_graph": use_graph, "l2": "flushed between steps (256 MiB memset, its time subtracted)"},
-               "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": host_x.numel() * 4 + host_y.numel() * 8,
+        out = {"metric": C["metric"], "value": value, "unit": C["unit"], "n_gpus": world, "steps": args.steps,
+               "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+               "config": {"workload": C["workload"], "name": args.config, "global_batch": world * B, "per_gpu": B,
+                          "parallelism": f"dp{world}", "block": "aim", "input": "uint8 clips, GPUNormalize fused into the patch load",
+                          "cuda_graph": use_graph, "peak_hbm_gib": round(peak_mem, 1),
+                          "l2": "flushed between steps (256 MiB memset, its time subtracted)"},
+               "e2e": {"value": e2e, "unit": C["unit"], "h2d_bytes_per_step": host_x.numel() + host_y.numel() * 8,
                        "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
-               "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
+               "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks, "sustained": sustained,
                "loss_last": losses[-1] if losses else None}
-        if v_cpu is not None:
-            out["cpu_baseline"] = {"value": v_cpu, "unit": UNIT, "cores": cores, "kind": "port",
-                                   "sample": "2 training steps x 1 clip of the same model on the oracle port (torch CPU fp32)"}
+        if world == 1 and not args.no_cpu_baseline:
+            items = B if args.config in ("cfg2", "cfg3") else (2 if args.config == "cfg4" else 1)
+            v_cpu, sp, cores, kind, detail = cpu_reference_rate(args.config, 1, 1, items)
+            out["cpu_baseline"] = {"value": v_cpu, "unit": C["unit"], "cores": cores, "kind": kind,
+                                   "sample": f"1 step (after 1 warm-up) x {items} {C['unit'].split('/')[0]} of the same workload ({detail})"}
         print(json.dumps(out), flush=True)
     # Teardown: a captured graph that contains NCCL kernels must be destroyed before the communicator, and a
     # stuck communicator teardown must never hang the launcher: hard-exit after a grace period.
@@ -421,7 +496,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--sustain-s", type=float, default=5.0, help="length of the extra sustained-clock loop (0 = skip)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a captured CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -17,11 +17,20 @@ import types
 
 import torch.nn as nn
 
-REF_ROOT = "/root/reference/mmaction/models/backbones/"
+_SUB = "mmaction/models/backbones/"
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# the mounted reference tree (build container), else the git-ignored copy of the two backbone files that
+# __graft_entry__.build() leaves under baseline/_ref/ so that bench.py's reference arm can run on the GPU box
+_CANDIDATES = [os.path.join(os.environ.get("AIM_REFERENCE", "/root/reference"), _SUB), os.path.join(_REPO, "baseline", "_ref", _SUB)]
+REF_ROOT = next((c for c in _CANDIDATES if os.path.isfile(c + "vitclip_aim.py")), _CANDIDATES[0])
 
 
 def available() -> bool:
     return os.path.isfile(REF_ROOT + "vitclip_aim.py")
+
+
+def source() -> str:
+    return "mounted reference tree" if REF_ROOT == _CANDIDATES[0] else "baseline/_ref copy"
 
 
 class _DropPath(nn.Module):

@@ -96,3 +96,52 @@ def test_single_process_is_noop():
     s.bucket_done(g, 0, 10)
     s.finish()
     assert s.buckets_launched == 0 and torch.equal(g, torch.ones(10))
+
+
+# ---------------------------------------------------------------------------------------------- inference sharding
+def test_shard_indices_match_distributed_sampler():
+    from aimb200.parallel import shard_indices
+    # datasets/samplers/distributed_sampler.py:27-43 (shuffle=False): indices += indices[:pad]; indices[rank::world]
+    for n, world in [(10, 4), (8, 8), (3, 8), (17, 2), (1, 3)]:
+        idx = list(range(n))
+        total = -(-n // world) * world
+        padded = (idx * (total // n + 1))[:total]
+        for r in range(world):
+            assert shard_indices(n, r, world) == padded[r::world]
+
+
+def _gather_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from aimb200.parallel import gather_scores, shard_indices
+        import torch.nn.functional as F
+        C = 5
+        g = torch.Generator().manual_seed(0)
+        # (a) 7 videos over 2 ranks, scores already averaged per video
+        full = torch.randn(7, C, generator=g)
+        mine = full[shard_indices(7, rank, world)]
+        got = gather_scores(mine, 7)
+        ok = bool(torch.equal(got, full))
+        # (b) 1 video x 3 views over 2 ranks (fewer videos than ranks): raw scores gathered, then 'prob' average
+        raw = torch.randn(3, C, generator=g)
+        mine = raw[shard_indices(3, rank, world)]
+        gathered = gather_scores(mine, 3)
+        prob = F.softmax(gathered.view(1, 3, C), dim=2).mean(dim=1)
+        ok &= bool(torch.allclose(prob, F.softmax(raw.view(1, 3, C), dim=2).mean(dim=1)))
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_scores_two_ranks():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gather_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res)
