@@ -396,7 +396,7 @@ class ViT_CLIP(nn.Module):
     def _run_backward(self, dfeat: torch.Tensor):
         W, WT, d = self._step_ctx
         names = self.trainable_names()
-        flat_grad = torch.empty_like(self._flat)
+        flat_grad = torch.zeros_like(self._flat)      # ONE memset: the gradient kernels accumulate into it
         params = dict(self.named_parameters())
         grads = {}
         for n in names:
@@ -418,7 +418,7 @@ class ViT_CLIP(nn.Module):
                 done_hi[0] = lo
 
         with torch.cuda.device(flat_grad.device) if flat_grad.is_cuda else contextlib.nullcontext():
-            self._engine.backward(dfeat.reshape(d.B, d.D, d.T).float(), W, WT, grads, on_done)
+            self._engine.backward(dfeat.reshape(d.B, d.D, d.T).float(), W, WT, grads, on_done, grads_prezeroed=True)
         if sync is not None:
             if done_hi[0] > 0:
                 sync.bucket_done(flat_grad, 0, done_hi[0])

@@ -429,13 +429,8 @@ int attn_spatial_fwd_mma(const void* qkv, void* o, float* lse, int frames, int n
     split_rows(n, nsplit, wpc);
     const size_t smem = (size_t)2 * npad * LDS * 2;
     if (smem > 200 * 1024) return AIMB_ERR_UNSUPPORTED;
-    static bool attr_set = false;   // once: not a stream operation, keeps the launch path capture-safe
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(attn_fwd_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
-            cudaFuncSetAttribute(attn_fwd_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 75 * 1024) != cudaSuccess)
-            return AIMB_ERR_CUDA;
-        attr_set = true;
-    }
+    AIMB_SET_SMEM_ATTR(200 * 1024, attn_fwd_mma_kernel<2>);     // per device, not a stream operation: capture-safe
+    AIMB_SET_SMEM_ATTR(75 * 1024, attn_fwd_mma_kernel<3>);
     dim3 grid(frames * heads, nsplit);
     // three CTAs per SM (80 registers, no spills) when K and V of a head fit three times: 59.4 -> 55.3 us at n = 197;
     // at n = 257 only two fit and the 122-register build is the faster one (114.7 vs 124.9 us)
@@ -450,12 +445,7 @@ int attn_spatial_fwd_mma(const void* qkv, void* o, float* lse, int frames, int n
 template <int NW>
 static int bwd_launch(const void* qkv, const void* o, const void* d_o, const float* lse, void* d_qkv, int frames, int n,
                       int heads, size_t smem, cudaStream_t s) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(attn_bwd_mma_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-            return AIMB_ERR_CUDA;
-        attr_set = true;
-    }
+    AIMB_SET_SMEM_ATTR(227 * 1024, attn_bwd_mma_kernel<NW>);
     const int tiles = (n + 15) / 16;
     launch_k((attn_bwd_mma_kernel<NW>), dim3(frames * heads), dim3((tiles < NW ? tiles : NW) * 32), smem, s, (const bf16*)qkv, (const bf16*)o, (const bf16*)d_o,
                                                                             lse, (bf16*)d_qkv, n, heads);

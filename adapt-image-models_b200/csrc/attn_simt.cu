@@ -398,12 +398,7 @@ __global__ void __launch_bounds__(128) attn_temporal_bwd_kernel(const T* __restr
 template <typename T, int T_>
 static int temporal_fwd_launch(const void* qkv, void* o, int B, int n, int heads, cudaStream_t s) {
     constexpr size_t smem = (size_t)4 * (3 * T_ * TKS + T_ * (T_ + 4)) * 4;
-    static bool once = false;
-    if (!once) {
-        if (cudaFuncSetAttribute(attn_temporal_fwd_kernel<T, T_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return AIMB_ERR_CUDA;
-        once = true;
-    }
+    AIMB_SET_SMEM_ATTR((int)smem, attn_temporal_fwd_kernel<T, T_>);
     int64_t probs = (int64_t)B * n * heads;
     launch_k((attn_temporal_fwd_kernel<T, T_>), dim3((unsigned)((probs + 3) / 4)), dim3(128), smem, s, (const T*)qkv, (T*)o, B, n, heads);
     AIMB_CHECK_LAUNCH();
@@ -412,12 +407,7 @@ static int temporal_fwd_launch(const void* qkv, void* o, int B, int n, int heads
 template <typename T, int T_>
 static int temporal_bwd_launch(const void* qkv, const void* d_o, void* d_qkv, int B, int n, int heads, cudaStream_t s) {
     constexpr size_t smem = (size_t)4 * (4 * T_ * TKS + 2 * T_ * (T_ + 4)) * 4;
-    static bool once = false;
-    if (!once) {
-        if (cudaFuncSetAttribute(attn_temporal_bwd_kernel<T, T_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return AIMB_ERR_CUDA;
-        once = true;
-    }
+    AIMB_SET_SMEM_ATTR((int)smem, attn_temporal_bwd_kernel<T, T_>);
     int64_t probs = (int64_t)B * n * heads;
     launch_k((attn_temporal_bwd_kernel<T, T_>), dim3((unsigned)((probs + 3) / 4)), dim3(128), smem, s, (const T*)qkv, (const T*)d_o, (T*)d_qkv, B, n,
                                                                                    heads);
@@ -489,12 +479,7 @@ template <typename T>
 int spatial_fwd_simt_launch(const void* qkv, void* o, float* lse, int frames, int n, int heads, cudaStream_t s) {
     size_t smem = spatial_fwd_smem(n);
     if (smem > 227 * 1024) return AIMB_ERR_UNSUPPORTED;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(attn_spatial_fwd_simt<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-            return AIMB_ERR_CUDA;
-        attr_set = true;
-    }
+    AIMB_SET_SMEM_ATTR(227 * 1024, attn_spatial_fwd_simt<T>);
     launch_k((attn_spatial_fwd_simt<T>), dim3(frames * heads), dim3(256), smem, s, (const T*)qkv, (T*)o, lse, n, heads);
     AIMB_CHECK_LAUNCH();
     return AIMB_OK;
@@ -504,12 +489,7 @@ int spatial_bwd_simt_launch(const void* qkv, const void* o, const void* d_o, con
                             int n, int heads, cudaStream_t s) {
     size_t smem = spatial_bwd_smem(n);
     if (smem > 227 * 1024) return AIMB_ERR_UNSUPPORTED;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(attn_spatial_bwd_simt<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-            return AIMB_ERR_CUDA;
-        attr_set = true;
-    }
+    AIMB_SET_SMEM_ATTR(227 * 1024, attn_spatial_bwd_simt<T>);
     launch_k((attn_spatial_bwd_simt<T>), dim3(frames * heads), dim3(256), smem, s, (const T*)qkv, (const T*)o, (const T*)d_o, lse, (T*)d_qkv, n,
                                                                heads);
     AIMB_CHECK_LAUNCH();

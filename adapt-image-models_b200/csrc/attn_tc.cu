@@ -725,16 +725,7 @@ static int make_tmap3(CUtensorMap* out, const void* ptr, int64_t slabs, int64_t 
     return AIMB_OK;
 }
 
-static int sm_count() {
-    int dev = 0, n = 0;
-    cudaGetDevice(&dev);
-    static int cached[64] = {0};
-    if (dev >= 0 && dev < 64 && cached[dev]) return cached[dev];
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-    if (dev >= 0 && dev < 64) cached[dev] = n;
-    return n;
-}
+static int sm_count() { return device_sm_count(); }
 
 }  // namespace atc
 
@@ -757,15 +748,7 @@ int attn_spatial_fwd_tc(const void* qkv, void* o, float* lse, int frames, int n,
     const int STAGE_B = MT * QTILE_B + 2 * KB * BOXB;
     const int NST = (2 * STAGE_B + 2048 <= 227 * 1024) ? 2 : 1;
     const int smem = NST * STAGE_B + 1024 + 256;
-    static bool attr_set[64] = {false};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64) return AIMB_ERR_UNSUPPORTED;
-    if (!attr_set[dev]) {
-        if (cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-            return AIMB_ERR_CUDA;
-        attr_set[dev] = true;
-    }
+    AIMB_SET_SMEM_ATTR(227 * 1024, attn_fwd_tc_kernel);
     const int nprob = frames * heads;
     const int sms = sm_count();
     const int waves = (nprob + sms - 1) / sms;
@@ -800,15 +783,7 @@ int attn_spatial_bwd_tc(const void* qkv, const void* o, const void* d_o, const f
     }
     const int NSTG = (7 * NQP * 128 + 32768 + 4096 + 256 + 1024 <= 227 * 1024) ? 2 : 1;
     const int smem = (3 * NSTG + 1) * NQP * 128 + 32768 + 4096 + 256 + 1024;
-    static bool attr_set[64] = {false};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64) return AIMB_ERR_UNSUPPORTED;
-    if (!attr_set[dev]) {
-        if (cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-            return AIMB_ERR_CUDA;
-        attr_set[dev] = true;
-    }
+    AIMB_SET_SMEM_ATTR(227 * 1024, attn_bwd_tc_kernel);
     const int nprob = frames * heads;
     const int sms = sm_count();
     const int waves = (nprob + sms - 1) / sms;

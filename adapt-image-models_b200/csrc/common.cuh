@@ -42,6 +42,32 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel instantiation, device): a function attribute belongs to
+// the device's context, so a process that drives several GPUs must set it on each of them.  (`kernel` may contain commas.)
+#define AIMB_SET_SMEM_ATTR(bytes, ...)                                                                                  \
+    do {                                                                                                               \
+        static bool done__[64] = {false};                                                                              \
+        int dev__ = 0;                                                                                                 \
+        cudaGetDevice(&dev__);                                                                                         \
+        if (dev__ < 0 || dev__ >= 64) return AIMB_ERR_UNSUPPORTED;                                                     \
+        if (!done__[dev__]) {                                                                                          \
+            if (cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, (bytes)) != cudaSuccess) \
+                return AIMB_ERR_CUDA;                                                                                  \
+            done__[dev__] = true;                                                                                      \
+        }                                                                                                              \
+    } while (0)
+
+inline int device_sm_count() {
+    static int cached[64] = {0};
+    int dev = 0, n = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && cached[dev]) return cached[dev];
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+    if (dev >= 0 && dev < 64) cached[dev] = n;
+    return n;
+}
+
 template <typename T> struct DT;
 template <> struct DT<float> {
     static __device__ __forceinline__ float ld(const float* p) { return *p; }
@@ -115,6 +141,7 @@ struct EpiParams {
     int32_t accumulate;   // out += v (only with out_f32)
     int64_t ldo;          // leading dim of out/out_pre/res1/res2/dact_src (elements)
     float* colsum_out;    // [N] fp32: column sums of the stored values (atomically accumulated; zeroed by the host side)
+    int32_t colsum_accumulate;   // host side only: skip that zeroing
 };
 
 inline EpiParams make_epi(const aimb_epilogue_t* e, int64_t ld_default) {
@@ -125,6 +152,7 @@ inline EpiParams make_epi(const aimb_epilogue_t* e, int64_t ld_default) {
     p.bias_rowscaled = e->bias_rowscaled; p.out_f32 = e->out_f32; p.accumulate = e->accumulate;
     p.ldo = e->ldo > 0 ? e->ldo : ld_default;
     p.colsum_out = e->colsum_out;
+    p.colsum_accumulate = e->colsum_accumulate;
     return p;
 }
 

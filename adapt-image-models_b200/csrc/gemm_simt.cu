@@ -100,6 +100,6 @@ extern "C" int aimb_gemm_strided(const void* A, int64_t a_sm, int64_t a_sk, cons
                                  void* stream) {
     if (!A || !B || !epi_ok(epi) || M < 0 || N <= 0 || K <= 0) return AIMB_ERR_ARG;
     EpiParams p = make_epi(epi, N);
-    if (p.colsum_out && cudaMemsetAsync(p.colsum_out, 0, (size_t)N * 4, (cudaStream_t)stream) != cudaSuccess) return AIMB_ERR_CUDA;
+    if (p.colsum_out && !p.colsum_accumulate && cudaMemsetAsync(p.colsum_out, 0, (size_t)N * 4, (cudaStream_t)stream) != cudaSuccess) return AIMB_ERR_CUDA;
     return gemm_simt_launch(A, a_sm, a_sk, B, b_sn, b_sk, p, M, N, K, dtype, (cudaStream_t)stream);
 }

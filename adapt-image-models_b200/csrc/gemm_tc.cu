@@ -57,7 +57,11 @@ __device__ __forceinline__ void st8_bf16(bf16* p, const float* v) {
 // one lane: 4 row-groups x 16 bytes each.  They do not depend on the accumulator, so they are fetched one
 // chunk AHEAD (and before the accumulator-ready wait for the first chunk): their latency never sits on the
 // epilogue's critical path.
-__device__ int g_dbg_skip_epilogue = 0;   // debug: 1 = drain TMEM but skip the epilogue math / global traffic
+#ifdef AIMB_DEBUG_EPILOGUE            // bench_tools stage attribution only (nvcc -DAIMB_DEBUG_EPILOGUE); release kernels carry no switch
+__device__ int g_dbg_skip_epilogue = 0;   // 1 = drain TMEM but skip the epilogue math / global traffic, 4-6: see gemm_tc4_kernel
+#else
+constexpr int g_dbg_skip_epilogue = 0;
+#endif
 
 struct EpiExt {
     uint4 d[4], r1[4], r2[4];
@@ -409,235 +413,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
-
-
-// ---------------------------------------------------------------------------------------- wide epilogue (v4)
-// Same mainloop as gemm_tc_kernel, but the epilogue is spread over 4*(BN/64) warps (one 32-row x 64-column slab
-// each) working in 16-column chunks: 16-register TMEM loads, 2 x 16 B residual vectors per lane and chunk.  The
-// low register footprint is what allows 12-16 epilogue warps per CTA (ncu showed the 8-warp epilogue latency bound:
-// IPC 0.12 per warp, long-scoreboard + fixed-latency stalls), i.e. twice the memory/ALU latency tolerance per SM.
-struct EpiExt16 {
-    uint4 d[2], r1[2], r2[2];
-};
-template <int EXT>
-__device__ __forceinline__ void epi_prefetch16(const EpiParams& e, EpiExt16& x, int64_t row_base, int row_l, int n0, int M) {
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const int64_t row = row_base + i * 16 + row_l;
-        if (row < M) {
-            const int64_t off = row * e.ldo + n0;
-            if ((EXT & 1) && (EXT != 7 || e.dact_src)) x.d[i] = *reinterpret_cast<const uint4*>((const bf16*)e.dact_src + off);
-            if ((EXT & 2) && (EXT != 7 || e.res1)) x.r1[i] = *reinterpret_cast<const uint4*>((const bf16*)e.res1 + off);
-            if ((EXT & 4) && (EXT != 7 || e.res2)) x.r2[i] = *reinterpret_cast<const uint4*>((const bf16*)e.res2 + off);
-        }
-    }
-}
-constexpr int STG16_LD = 20;                                 // floats per staged row (16 + 4): conflict-free 128-bit access
-constexpr int STG16_WARP_FLOATS = 32 * STG16_LD + 64;        // + this warp's 64 bias values
-template <int BN> struct TileCfg3 {
-    static constexpr int EPI_W = 4 * (BN / 64);              // epilogue warps: 4 TMEM quadrants x (BN/64) column slabs
-    static constexpr int THREADS = 64 + 32 * EPI_W;
-    static constexpr int STG = EPI_W * STG16_WARP_FLOATS * 4 + 1024;
-    static constexpr int B_STAGE_BYTES = BN * BK * 2;
-    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    static constexpr int STAGES_RAW = (232448 - STG - 1024 - 256) / STAGE_BYTES;
-    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-    static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG + 1024 + 256;
-};
-
-template <int ACT, int DACT, int EXT, typename WaitFn>
-__device__ __forceinline__ void epilogue_slab64(const EpiParams& epi, float* stg, float* scol, int col_in_tile, uint32_t taddr,
-                                                int64_t row_base, int n_base, int M, int lane, WaitFn wait_acc) {
-    constexpr bool DB = (EXT != 7);
-    const int row_l = lane & 15, c0 = (lane >> 4) * 8;       // 16 rows x two 8-column vectors per pass, 2 passes per chunk
-    float* sbias = stg + 32 * STG16_LD;
-    if (epi.bias) {
-        sbias[lane] = __bfloat162float(((const bf16*)epi.bias)[n_base + lane]);
-        sbias[lane + 32] = __bfloat162float(((const bf16*)epi.bias)[n_base + lane + 32]);
-    }
-    EpiExt16 cur, nxt;
-    epi_prefetch16<EXT>(epi, cur, row_base, row_l, n_base + c0, M);
-    wait_acc();
-    uint32_t r[16];
-    const int dbg = g_dbg_skip_epilogue;     // bench_tools only: 1 = drain TMEM, 2 = + staging, 3 = all but global stores
-    EpiParams epi_l = epi;
-    if (dbg == 3) { epi_l.out = nullptr; epi_l.out_pre = nullptr; }
-    ptx::tmem_ld_32x32b_x16(taddr, r);
-#pragma unroll 1
-    for (int c = 0; c < 64; c += 16) {
-        ptx::tmem_wait_ld();
-        if (dbg == 1) {
-            if (r[0] == 0x7fc12345u && r[5] == 0x12345u) stg[lane] = __uint_as_float(r[1]);
-            if (c + 16 < 64) ptx::tmem_ld_32x32b_x16(taddr + c + 16, r);
-            continue;
-        }
-#pragma unroll
-        for (int j = 0; j < 16; j += 4)
-            *reinterpret_cast<uint4*>(stg + lane * STG16_LD + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-        if (c + 16 < 64) {
-            ptx::tmem_ld_32x32b_x16(taddr + c + 16, r);
-            if (DB) epi_prefetch16<EXT>(epi, nxt, row_base, row_l, n_base + c + 16 + c0, M);
-        }
-        __syncwarp();
-        if (dbg == 2) {
-            float4 a = *reinterpret_cast<const float4*>(stg + row_l * STG16_LD + c0);
-            float4 b = *reinterpret_cast<const float4*>(stg + (row_l + 16) * STG16_LD + c0 + 4);
-            if (a.x == 1.2345e-30f && b.y == 3.21e-30f) sbias[lane] = a.y;
-            __syncwarp();
-            continue;
-        }
-        const int n0 = n_base + c + c0;
-        float bias8[8];
-        if (epi.bias) {
-            *reinterpret_cast<float4*>(bias8) = *reinterpret_cast<const float4*>(sbias + c + c0);
-            *reinterpret_cast<float4*>(bias8 + 4) = *reinterpret_cast<const float4*>(sbias + c + c0 + 4);
-        }
-        float cs8[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) cs8[j] = 0.f;
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int rl = i * 16 + row_l;
-            const int64_t row = row_base + rl;
-            float v[8];
-            *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(stg + rl * STG16_LD + c0);
-            *reinterpret_cast<float4*>(v + 4) = *reinterpret_cast<const float4*>(stg + rl * STG16_LD + c0 + 4);
-            if (row < M) {
-                epilogue_vec8<ACT, DACT, EXT>(epi_l, row, n0, v, bias8, cur, i);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) cs8[j] += v[j];
-            }
-        }
-        if (epi.colsum_out) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float t = cs8[j];
-                t += __shfl_xor_sync(0xffffffffu, t, 1);
-                t += __shfl_xor_sync(0xffffffffu, t, 2);
-                t += __shfl_xor_sync(0xffffffffu, t, 4);
-                t += __shfl_xor_sync(0xffffffffu, t, 8);
-                if ((lane & 15) == 0) atomicAdd(scol + col_in_tile + c + c0 + j, t);
-            }
-        }
-        __syncwarp();
-        if (DB) cur = nxt;
-        else if (c + 16 < 64) epi_prefetch16<EXT>(epi, cur, row_base, row_l, n_base + c + 16 + c0, M);
-    }
-}
-
-template <int BN, int V>
-__global__ void __launch_bounds__(TileCfg3<BN>::THREADS, 1)
-gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const EpiParams epi,
-                const int M, const int N, const int K) {
-    pdl_trigger();
-    using Cfg = TileCfg3<BN>;
-    constexpr int STAGES = Cfg::STAGES;
-    constexpr int EPI_W = Cfg::EPI_W;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-    float* stg_all = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
-    float* scol = stg_all + EPI_W * STG16_WARP_FLOATS;
-    if (threadIdx.x < 256) scol[threadIdx.x] = 0.f;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::STG);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tfull_bar = empty_bar + STAGES;
-    uint64_t* tempty_bar = tfull_bar + 2;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_tiles = N / BN;
-    const int m_tiles = (M + BM - 1) / BM;
-    const int total = n_tiles * m_tiles;
-    const int KB = K / BK;
-    if (threadIdx.x == 0) {
-        ptx::prefetch_tmap(&tmA);
-        ptx::prefetch_tmap(&tmB);
-        for (int i = 0; i < STAGES; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], EPI_W); }
-        ptx::fence_mbar_init();
-    }
-    if (warp == 1) ptx::tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
-    ptx::tc_fence_before();
-    __syncthreads();
-    ptx::tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
-    pdl_wait();
-    if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-                const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-                for (int kb = 0; kb < KB; ++kb) {
-                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                    ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-                    ptx::tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
-                    ptx::tma_load_2d(sa + A_STAGE_BYTES, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN);
-            int stage = 0; uint32_t phase = 0;
-            int it = 0;
-            for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-                const int as = it & 1;
-                const uint32_t aphase = (it >> 1) & 1;
-                ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
-                ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * BN;
-                for (int kb = 0; kb < KB; ++kb) {
-                    ptx::mbar_wait(&full_bar[stage], phase);
-                    ptx::tc_fence_after();
-                    const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                    const uint64_t adesc = ptx::umma_desc_kmajor_sw128(sa);
-                    const uint64_t bdesc = ptx::umma_desc_kmajor_sw128(sa + A_STAGE_BYTES);
-#pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k)
-                        ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                    ptx::umma_commit(&empty_bar[stage]);
-                    if (kb == KB - 1) ptx::umma_commit(&tfull_bar[as]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                }
-            }
-        }
-    } else {
-        using EV = EpiVariant<V>;
-        const int quad = warp & 3;
-        const int slab = (warp - 2) >> 2;                     // 64-column slab of the tile
-        float* stg = stg_all + (warp - 2) * STG16_WARP_FLOATS;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-            const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-            const int as = it & 1;
-            const uint32_t aphase = (it >> 1) & 1;
-            const int64_t row_base = (int64_t)m_blk * BM + quad * 32;
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN + slab * 64;
-            epilogue_slab64<EV::ACT, EV::DACT, EV::EXT>(epi, stg, scol, slab * 64, taddr, row_base, n_blk * BN + slab * 64, M, lane,
-                                                        [&]() {
-                                                            ptx::mbar_wait(&tfull_bar[as], aphase);
-                                                            ptx::tc_fence_after();
-                                                        });
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (epi.colsum_out) {
-                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_W) : "memory");
-                const int te = threadIdx.x - 64;
-                if (te < BN) { atomicAdd(epi.colsum_out + n_blk * BN + te, scol[te]); scol[te] = 0.f; }
-                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_W) : "memory");
-            }
-            if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
-        }
-    }
-    ptx::tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        __syncwarp();
-        ptx::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
-    }
-}
 
 
 // ---------------------------------------------------------------------------------------- row-layout epilogue (v5)
@@ -998,384 +773,6 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 
-// ---------------------------------------------------------------------------------------- CTA pair + row-layout epilogue
-// gemm_tc5_kernel: the cta_group::2 mainloop of gemm_tc2_kernel (each CTA loads its 128 rows of A and HALF of the W
-// tile; one tcgen05.mma spans both SMs) with the row-layout epilogue of gemm_tc4_kernel.  Per-FLOP L2->SM operand
-// traffic drops 1.5x, which is what the epilogue's own L2 traffic competes with on the N = 2304 / 3072 shapes.
-template <int BN, int V> struct TileCfg5 {
-    static constexpr int EPI_W = 4 * (BN / 64);
-    static constexpr int THREADS = 64 + 32 * EPI_W;
-    static constexpr int EPI_BYTES = EPI_W * EpiBufs<V>::WARP_BYTES + 1024;
-    static constexpr int B_STAGE_BYTES = (BN / 2) * BK * 2;
-    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    static constexpr int STAGES_RAW = (232448 - EPI_BYTES - 1024 - 256) / STAGE_BYTES;
-    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-    static constexpr bool OK = STAGES >= 3;
-    static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-    static constexpr int SMEM_BYTES = (STAGES > 0 ? STAGES : 1) * STAGE_BYTES + EPI_BYTES + 1024 + 256;
-};
-template <int BN, int V>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TileCfg5<BN, V>::THREADS, 1)
-gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmP, const EpiParams epi,
-                const int M, const int N, const int K) {
-    pdl_trigger();
-    using Cfg = TileCfg5<BN, V>;
-    using EB = EpiBufs<V>;
-    using EV = EpiVariant<V>;
-    constexpr int STAGES = Cfg::STAGES;
-    constexpr int EPI_W = Cfg::EPI_W;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES;
-    float* scol = reinterpret_cast<float*>(epi_smem + EPI_W * EB::WARP_BYTES);   // [slab buffers][bias][scol]
-    if (threadIdx.x < 256) scol[threadIdx.x] = 0.f;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + Cfg::EPI_BYTES);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tfull_bar = empty_bar + STAGES;
-    uint64_t* tempty_bar = tfull_bar + 2;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = ptx::cluster_ctarank();
-    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-    const int n_tiles = N / BN;
-    const int m_tiles = (M + 2 * BM - 1) / (2 * BM);
-    const int total = n_tiles * m_tiles;
-    const int KB = K / BK;
-    if (threadIdx.x == 0) {
-        ptx::prefetch_tmap(&tmA);
-        ptx::prefetch_tmap(&tmB);
-        for (int i = 0; i < STAGES; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], 2 * EPI_W); }
-        ptx::fence_mbar_init();
-    }
-    if (warp == 1) ptx::tmem_alloc_2cta<Cfg::TMEM_COLS>(tmem_ptr);
-    ptx::tc_fence_before();
-    __syncthreads();
-    ptx::cluster_sync();
-    ptx::tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
-    pdl_wait();
-    if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int tile = pair; tile < total; tile += npairs) {
-                const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-                for (int kb = 0; kb < KB; ++kb) {
-                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                    if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-                    ptx::tma_load_2d_2sm(sa, &tmA, &full_bar[stage], kb * BK, m_blk * 2 * BM + (int)rank * BM);
-                    ptx::tma_load_2d_2sm(sa + A_STAGE_BYTES, &tmB, &full_bar[stage], kb * BK, n_blk * BN + (int)rank * (BN / 2));
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
-            constexpr uint32_t idesc = ptx::umma_idesc_bf16(2 * BM, BN);
-            int stage = 0; uint32_t phase = 0;
-            int it = 0;
-            for (int tile = pair; tile < total; tile += npairs, ++it) {
-                const int as = it & 1;
-                const uint32_t aphase = (it >> 1) & 1;
-                ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
-                ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * BN;
-                for (int kb = 0; kb < KB; ++kb) {
-                    ptx::mbar_wait(&full_bar[stage], phase);
-                    ptx::tc_fence_after();
-                    const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                    const uint64_t adesc = ptx::umma_desc_kmajor_sw128(sa);
-                    const uint64_t bdesc = ptx::umma_desc_kmajor_sw128(sa + A_STAGE_BYTES);
-#pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k)
-                        ptx::umma_bf16_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                    ptx::umma_commit_2cta(&empty_bar[stage], 3);
-                    if (kb == KB - 1) ptx::umma_commit_2cta(&tfull_bar[as], 3);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                }
-            }
-        }
-    } else {
-        constexpr int EXT = EV::EXT;
-        const int ew = warp - 2;
-        const int quad = warp & 3;
-        const int slab = ew >> 2;
-        constexpr bool TMA_ST = (EXT == 0);                   // plain / activation variants: the slab leaves through TMA
-        const uint32_t buf0 = ptx::smem_u32(epi_smem + ew * (EB::NBUF * 4096));   // out (in place over dact_src / res1); 1 KB aligned
-        const uint32_t buf1 = buf0 + 4096;                    // out_pre, or res2
-        float* sbias = reinterpret_cast<float*>(epi_smem + EPI_W * (EB::NBUF * 4096) + ew * 256);
-        if (TMA_ST && lane == 0) { ptx::prefetch_tmap(&tmO); if (want_pre_k(epi, EB::PRE)) ptx::prefetch_tmap(&tmP); }
-        const bf16* g0 = (EXT & 1) ? (const bf16*)epi.dact_src : (const bf16*)epi.res1;
-        const bf16* g1 = (const bf16*)epi.res2;
-        const bool want_pre = EB::PRE && epi.out_pre != nullptr;
-        const int dbg = g_dbg_skip_epilogue;   // bench_tools only: 4 = no flush, 5 = no slab writes either, 6 = STG flush instead of TMA
-        auto fetch = [&](int tile) {
-            const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-            const int64_t rb = (int64_t)m_blk * 2 * BM + (int64_t)rank * BM + quad * 32;
-            const int nb = n_blk * BN + slab * 64;
-            if (EXT & 3) slab_fetch(buf0, g0, epi.ldo, rb, nb, M, lane);
-            if (EXT & 4) slab_fetch(buf1, g1, epi.ldo, rb, nb, M, lane);
-        };
-        if (EXT != 0 && pair < total) fetch(pair);
-        int it = 0;
-        for (int tile = pair; tile < total; tile += npairs, ++it) {
-            const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-            const int as = it & 1;
-            const uint32_t aphase = (it >> 1) & 1;
-            const int64_t row_base = (int64_t)m_blk * 2 * BM + (int64_t)rank * BM + quad * 32;
-            const int n_base = n_blk * BN + slab * 64;
-            const int64_t row = row_base + lane;
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN + slab * 64;
-            if (epi.bias) {
-                sbias[lane] = __bfloat162float(((const bf16*)epi.bias)[n_base + lane]);
-                sbias[lane + 32] = __bfloat162float(((const bf16*)epi.bias)[n_base + lane + 32]);
-            }
-            float rs = 1.f;
-            if (epi.row_scale && row < M) rs = epi.row_scale[(int)row % epi.row_mod];
-            ptx::mbar_wait(&tfull_bar[as], aphase);
-            ptx::tc_fence_after();
-            uint32_t ra[16], rb16[16];
-            ptx::tmem_ld_32x32b_x16(taddr, ra);
-            cp_async_commit_wait();
-            if (TMA_ST && lane == 0) ptx::bulk_wait_read0();   // the previous tile's TMA store has finished reading the slab
-            __syncwarp();
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                uint32_t (&cur)[16] = (q & 1) ? rb16 : ra;
-                uint32_t (&nxt)[16] = (q & 1) ? ra : rb16;
-                ptx::tmem_wait_ld();
-                if (q < 3) ptx::tmem_ld_32x32b_x16(taddr + (q + 1) * 16, nxt);
-                if (q == 3) {                                  // accumulator drained: hand the TMEM buffer back early
-                    ptx::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive_cluster(&tempty_bar[as], 0);   // the leader's MMA warp waits for both CTAs
-                }
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    const int ch = 2 * q + hh;
-                    const uint32_t off = slab_off(lane, ch);
-                    uint4 xd = make_uint4(0, 0, 0, 0), x1 = xd, x2 = xd, pre_pk = xd;
-                    if (EXT & 1) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(xd.x), "=r"(xd.y), "=r"(xd.z), "=r"(xd.w) : "r"(buf0 + off));
-                    if ((EXT & 3) == 2) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x1.x), "=r"(x1.y), "=r"(x1.z), "=r"(x1.w) : "r"(buf0 + off));
-                    if (EXT & 4) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x2.x), "=r"(x2.y), "=r"(x2.z), "=r"(x2.w) : "r"(buf1 + off));
-                    float v[8], bias8[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(cur[hh * 8 + j]);
-                    if (epi.bias) {
-                        *reinterpret_cast<float4*>(bias8) = *reinterpret_cast<const float4*>(sbias + ch * 8);
-                        *reinterpret_cast<float4*>(bias8 + 4) = *reinterpret_cast<const float4*>(sbias + ch * 8 + 4);
-                    }
-                    const uint4 o = epi_math8<EV::ACT, EV::DACT, EXT>(epi, rs, v, bias8, xd, x1, x2, pre_pk, want_pre);
-                    if (dbg == 5 && o.x != 0x12345678u) continue;
-                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(buf0 + off), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
-                    if (want_pre)
-                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(buf1 + off), "r"(pre_pk.x), "r"(pre_pk.y), "r"(pre_pk.z), "r"(pre_pk.w) : "memory");
-                }
-            }
-            if (dbg == 4 || dbg == 5) { __syncwarp(); continue; }
-            if (TMA_ST && !epi.colsum_out && dbg != 6) {
-                ptx::fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) {
-                    ptx::tma_store_2d(&tmO, buf0, n_base, (int)row_base);
-                    if (want_pre) ptx::tma_store_2d(&tmP, buf1, n_base, (int)row_base);
-                    ptx::bulk_commit();
-                }
-                continue;
-            }
-            __syncwarp();
-            // flush: 4 full rows per instruction
-            float cs8[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) cs8[j] = 0.f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = i * 4 + (lane >> 3), ch = lane & 7;
-                const int64_t grow = row_base + r;
-                if (grow < M) {
-                    const uint32_t off = slab_off(r, ch);
-                    uint4 o;
-                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w) : "r"(buf0 + off));
-                    const int64_t goff = grow * epi.ldo + n_base + ch * 8;
-                    *reinterpret_cast<uint4*>((bf16*)epi.out + goff) = o;
-                    if (want_pre) {
-                        uint4 pp;
-                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(pp.x), "=r"(pp.y), "=r"(pp.z), "=r"(pp.w) : "r"(buf1 + off));
-                        *reinterpret_cast<uint4*>((bf16*)epi.out_pre + goff) = pp;
-                    }
-                    if (epi.colsum_out) {
-                        float t[8];
-                        unpack8(o, t);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) cs8[j] += t[j];
-                    }
-                }
-            }
-            if (epi.colsum_out) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float t = cs8[j];
-                    t += __shfl_xor_sync(0xffffffffu, t, 8);
-                    t += __shfl_xor_sync(0xffffffffu, t, 16);
-                    if (lane < 8) atomicAdd(scol + slab * 64 + lane * 8 + j, t);
-                }
-            }
-            __syncwarp();
-            if (EXT != 0 && tile + npairs < total) fetch(tile + npairs);
-            if (epi.colsum_out) {
-                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_W) : "memory");
-                const int te = threadIdx.x - 64;
-                if (te < BN) { atomicAdd(epi.colsum_out + n_blk * BN + te, scol[te]); scol[te] = 0.f; }
-                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_W) : "memory");
-            }
-        }
-    }
-    if (warp >= 2 && lane == 0) ptx::bulk_wait0();   // smem must stay valid until the TMA stores have read it
-    ptx::tc_fence_before();
-    __syncthreads();
-    ptx::cluster_sync();     // no CTA may exit (or free TMEM) while its peer can still signal / read it
-    if (warp == 1) {
-        __syncwarp();
-        ptx::tmem_dealloc_2cta<Cfg::TMEM_COLS>(tmem_base);
-    }
-}
-
-
-// ---------------------------------------------------------------------------------------- 2-CTA GEMM
-// Same pipeline with tcgen05.mma.cta_group::2: a CTA pair computes a 256 x BN tile.  Each CTA TMA-loads its
-// own 128 rows of A and only HALF of the W tile (BN/2 rows); the pair's tensor cores read both halves, so the
-// L2->SM operand traffic per FLOP drops by ~1.5x versus the 1-CTA kernel (which is L2-bandwidth bound, see
-// profiles/).  The leader CTA (cluster rank 0) issues the MMAs; full barriers live in the leader, empty /
-// accumulator-full barriers are signalled in both CTAs by a multicast tcgen05.commit.
-template <int BN> struct TileCfg2 {
-    static constexpr int B_STAGE_BYTES = (BN / 2) * BK * 2;
-    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    static constexpr int STAGES_RAW = (232448 - STG_BYTES - 1024 - 256) / STAGE_BYTES;
-    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-    static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 + 256;
-};
-
-template <int BN, int V>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const EpiParams epi,
-                const int M, const int N, const int K) {
-    pdl_trigger();   // the next kernel may start its prologue; it blocks in its own pdl_wait() until this grid is done
-    using Cfg = TileCfg2<BN>;
-    constexpr int STAGES = Cfg::STAGES;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a __shared__ pointer
-    float* stg_all = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
-    float* scol = stg_all + EPI_WARPS * STG_WARP_FLOATS;
-    if (threadIdx.x < 256) scol[threadIdx.x] = 0.f;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + STG_BYTES);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tfull_bar = empty_bar + STAGES;
-    uint64_t* tempty_bar = tfull_bar + 2;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = ptx::cluster_ctarank();
-    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-    const int n_tiles = N / BN;
-    const int m_tiles = (M + 2 * BM - 1) / (2 * BM);
-    const int total = n_tiles * m_tiles;
-    const int KB = K / BK;
-
-    if (threadIdx.x == 0) {
-        ptx::prefetch_tmap(&tmA);
-        ptx::prefetch_tmap(&tmB);
-        for (int i = 0; i < STAGES; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], 2 * EPI_WARPS); }
-        ptx::fence_mbar_init();
-    }
-    if (warp == 1) ptx::tmem_alloc_2cta<Cfg::TMEM_COLS>(tmem_ptr);
-    ptx::tc_fence_before();
-    __syncthreads();
-    ptx::cluster_sync();
-    ptx::tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
-    pdl_wait();
-
-    if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int tile = pair; tile < total; tile += npairs) {
-                const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-                for (int kb = 0; kb < KB; ++kb) {
-                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                    if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-                    ptx::tma_load_2d_2sm(sa, &tmA, &full_bar[stage], kb * BK, m_blk * 2 * BM + (int)rank * BM);
-                    ptx::tma_load_2d_2sm(sa + A_STAGE_BYTES, &tmB, &full_bar[stage], kb * BK, n_blk * BN + (int)rank * (BN / 2));
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
-            constexpr uint32_t idesc = ptx::umma_idesc_bf16(2 * BM, BN);
-            int stage = 0; uint32_t phase = 0;
-            int it = 0;
-            for (int tile = pair; tile < total; tile += npairs, ++it) {
-                const int as = it & 1;
-                const uint32_t aphase = (it >> 1) & 1;
-                ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
-                ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * BN;
-                for (int kb = 0; kb < KB; ++kb) {
-                    ptx::mbar_wait(&full_bar[stage], phase);
-                    ptx::tc_fence_after();
-                    const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                    const uint64_t adesc = ptx::umma_desc_kmajor_sw128(sa);
-                    const uint64_t bdesc = ptx::umma_desc_kmajor_sw128(sa + A_STAGE_BYTES);
-#pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k)
-                        ptx::umma_bf16_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                    ptx::umma_commit_2cta(&empty_bar[stage], 3);
-                    if (kb == KB - 1) ptx::umma_commit_2cta(&tfull_bar[as], 3);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                }
-            }
-        }
-    } else {
-        const int quad = warp & 3;
-        const int half = (warp - 2) >> 2;
-        float* stg = stg_all + (warp - 2) * STG_WARP_FLOATS;
-        int it = 0;
-        for (int tile = pair; tile < total; tile += npairs, ++it) {
-            const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-            const int as = it & 1;
-            const uint32_t aphase = (it >> 1) & 1;
-            const int64_t row_base = (int64_t)m_blk * 2 * BM + (int64_t)rank * BM + quad * 32;
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN + half * (BN / 2);
-            epilogue_warp<BN / 2, V>(epi, stg, scol, half * (BN / 2), taddr, row_base, n_blk * BN + half * (BN / 2), M, lane, [&]() {
-                ptx::mbar_wait(&tfull_bar[as], aphase);
-                ptx::tc_fence_after();
-            });
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (epi.colsum_out) {      // one global atomic per column per tile (the 8 epilogue warps meet on named barrier 1)
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                const int te = threadIdx.x - 64;
-                if (te < BN) { atomicAdd(epi.colsum_out + n_blk * BN + te, scol[te]); scol[te] = 0.f; }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-            }
-            if (lane == 0) ptx::mbar_arrive_cluster(&tempty_bar[as], 0);   // the leader's MMA warp waits for both CTAs
-        }
-    }
-    ptx::tc_fence_before();
-    __syncthreads();
-    ptx::cluster_sync();     // no CTA may exit (or free TMEM) while its peer can still signal / read it
-    if (warp == 1) {
-        __syncwarp();
-        ptx::tmem_dealloc_2cta<Cfg::TMEM_COLS>(tmem_base);
-    }
-}
-
-
 // ---------------------------------------------------------------------------------------- fused adapter
 // Adapter bottleneck (vit_clip.py:51-69) as ONE kernel per direction:
 //   forward : out = res1 + res2 + alpha * rs * (gelu(a W1^T + b1) W2^T + b2)      (h, g' = rs*gelu(h) kept for backward)
@@ -1552,7 +949,6 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // faster on gemm_tc_kernel: its stores trickle out chunk by chunk instead of one burst per tile), 1 = gemm_tc_kernel,
 // 3 = gemm_tc3_kernel, 4 = gemm_tc4_kernel wherever its shared-memory budget allows
 static int g_epi_kernel = 0;
-static int g_pair_epi = 0;          // 1: gemm_tc5_kernel (CTA pairs + row-layout epilogue) where it tiles
 static int g_direct = 1;           // 0: never use the DIRECT (register-store) epilogue, 1: auto (K >= 512), 2: always
 static inline bool use_tc4(int v) { return (g_epi_kernel == 4 || (g_epi_kernel == 0 && v != 1)) && v != 7; }
 // DIRECT epilogue: 32-byte sector stores from registers; for every variant without fused column sums once the mainloop
@@ -1626,37 +1022,20 @@ int make_tmap_bf16(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols
     return AIMB_OK;
 }
 
-static int num_sms() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
-}
+static int num_sms() { return device_sm_count(); }
 
 template <int BN, int V>
 static int launch_tc_v(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p, int M, int N, int K, cudaStream_t s) {
     using Cfg = TileCfg<BN>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(gemm_tc_kernel<BN, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
-            return AIMB_ERR_CUDA;
-        attr_set = true;
-    }
+    // generic kernel (runtime-switched epilogue, variant 7): the fallback for every combination the row-layout kernel's
+    // buffers do not fit, and debug mode 1
+    AIMB_SET_SMEM_ATTR(Cfg::SMEM_BYTES, gemm_tc_kernel<BN, 7>);
     int total = (N / BN) * ((M + BM - 1) / BM);
     int grid = total < num_sms() ? total : num_sms();
     if (use_tc4_direct(V, K, p)) {
         if constexpr (V != 7 && TileCfg4<BN, V, true>::OK) {
             using Cfg4 = TileCfg4<BN, V, true>;
-            static bool attr4d = false;
-            if (!attr4d) {
-                if (cudaFuncSetAttribute(gemm_tc4_kernel<BN, V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg4::SMEM_BYTES) != cudaSuccess)
-                    return AIMB_ERR_CUDA;
-                attr4d = true;
-            }
+            AIMB_SET_SMEM_ATTR(Cfg4::SMEM_BYTES, gemm_tc4_kernel<BN, V, true>);
             launch_k((gemm_tc4_kernel<BN, V, true>), dim3(grid), dim3(Cfg4::THREADS), Cfg4::SMEM_BYTES, s, ta, tb, ta, ta, p, M, N, K);
             AIMB_CHECK_LAUNCH();
             return AIMB_OK;
@@ -1665,12 +1044,7 @@ static int launch_tc_v(const CUtensorMap& ta, const CUtensorMap& tb, const EpiPa
     if constexpr (V != 7 && TileCfg4<BN, V, false>::OK) {
         if (use_tc4(V)) {
             using Cfg4 = TileCfg4<BN, V, false>;
-            static bool attr4 = false;
-            if (!attr4) {
-                if (cudaFuncSetAttribute(gemm_tc4_kernel<BN, V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg4::SMEM_BYTES) != cudaSuccess)
-                    return AIMB_ERR_CUDA;
-                attr4 = true;
-            }
+            AIMB_SET_SMEM_ATTR(Cfg4::SMEM_BYTES, gemm_tc4_kernel<BN, V, false>);
             CUtensorMap to = ta, tp = ta;                       // placeholders when the variant does not store through TMA
             if (EpiVariant<V>::EXT == 0) {
                 if (make_tmap_bf16(&to, p.out, M, N, p.ldo, 32)) return AIMB_ERR_DRIVER;
@@ -1681,19 +1055,7 @@ static int launch_tc_v(const CUtensorMap& ta, const CUtensorMap& tb, const EpiPa
             return AIMB_OK;
         }
     }
-    if (g_epi_kernel == 3 || g_epi_kernel == 4) {
-        using Cfg3 = TileCfg3<BN>;
-        static bool attr3 = false;
-        if (!attr3) {
-            if (cudaFuncSetAttribute(gemm_tc3_kernel<BN, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg3::SMEM_BYTES) != cudaSuccess)
-                return AIMB_ERR_CUDA;
-            attr3 = true;
-        }
-        launch_k((gemm_tc3_kernel<BN, V>), dim3(grid), dim3(Cfg3::THREADS), Cfg3::SMEM_BYTES, s, ta, tb, p, M, N, K);
-        AIMB_CHECK_LAUNCH();
-        return AIMB_OK;
-    }
-    launch_k((gemm_tc_kernel<BN, V>), dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, s, ta, tb, p, M, N, K);
+    launch_k((gemm_tc_kernel<BN, 7>), dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, s, ta, tb, p, M, N, K);
     AIMB_CHECK_LAUNCH();
     return AIMB_OK;
 }
@@ -1711,97 +1073,6 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const EpiPara
     }
 }
 
-template <int BN, int V>
-static int launch_tc2_v(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p, int M, int N, int K, cudaStream_t s) {
-    using Cfg = TileCfg2<BN>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(gemm_tc2_kernel<BN, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
-            return AIMB_ERR_CUDA;
-        attr_set = true;
-    }
-    int total = (N / BN) * ((M + 2 * BM - 1) / (2 * BM));
-    int pairs = num_sms() / 2;
-    if (total < pairs) pairs = total;
-    launch_k((gemm_tc2_kernel<BN, V>), dim3(2 * pairs), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, s, ta, tb, p, M, N, K);
-    AIMB_CHECK_LAUNCH();
-    return AIMB_OK;
-}
-template <int BN>
-static int launch_tc2(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p, int M, int N, int K, cudaStream_t s) {
-    switch (pick_variant(p)) {
-        case 0: return launch_tc2_v<BN, 0>(ta, tb, p, M, N, K, s);
-        case 1: return launch_tc2_v<BN, 1>(ta, tb, p, M, N, K, s);
-        case 2: return launch_tc2_v<BN, 2>(ta, tb, p, M, N, K, s);
-        case 3: return launch_tc2_v<BN, 3>(ta, tb, p, M, N, K, s);
-        case 4: return launch_tc2_v<BN, 4>(ta, tb, p, M, N, K, s);
-        case 5: return launch_tc2_v<BN, 5>(ta, tb, p, M, N, K, s);
-        case 6: return launch_tc2_v<BN, 6>(ta, tb, p, M, N, K, s);
-        default: return launch_tc2_v<BN, 7>(ta, tb, p, M, N, K, s);
-    }
-}
-
-// 2-CTA tile choice: minimise waves x per-tile cost over the 74 CTA pairs.
-
-template <int BN, int V>
-static int launch_tc5_v(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p, int M, int N, int K, cudaStream_t s) {
-    if constexpr (V != 7 && TileCfg5<BN, V>::OK) {
-        using Cfg = TileCfg5<BN, V>;
-        static bool attr_set = false;
-        if (!attr_set) {
-            if (cudaFuncSetAttribute(gemm_tc5_kernel<BN, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
-                return AIMB_ERR_CUDA;
-            attr_set = true;
-        }
-        CUtensorMap to = ta, tp = ta;
-        if (EpiVariant<V>::EXT == 0) {
-            if (make_tmap_bf16(&to, p.out, M, N, p.ldo, 32)) return AIMB_ERR_DRIVER;
-            if (p.out_pre && make_tmap_bf16(&tp, p.out_pre, M, N, p.ldo, 32)) return AIMB_ERR_DRIVER;
-        }
-        int total = (N / BN) * ((M + 2 * BM - 1) / (2 * BM));
-        int pairs = num_sms() / 2;
-        if (total < pairs) pairs = total;
-        launch_k((gemm_tc5_kernel<BN, V>), dim3(2 * pairs), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, s, ta, tb, to, tp, p, M, N, K);
-        AIMB_CHECK_LAUNCH();
-        return AIMB_OK;
-    } else {
-        return AIMB_ERR_UNSUPPORTED;
-    }
-}
-template <int BN>
-static int launch_tc5(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p, int M, int N, int K, cudaStream_t s) {
-    switch (pick_variant(p)) {
-        case 0: return launch_tc5_v<BN, 0>(ta, tb, p, M, N, K, s);
-        case 1: return launch_tc5_v<BN, 1>(ta, tb, p, M, N, K, s);
-        case 2: return launch_tc5_v<BN, 2>(ta, tb, p, M, N, K, s);
-        case 3: return launch_tc5_v<BN, 3>(ta, tb, p, M, N, K, s);
-        case 4: return launch_tc5_v<BN, 4>(ta, tb, p, M, N, K, s);
-        case 5: return launch_tc5_v<BN, 5>(ta, tb, p, M, N, K, s);
-        case 6: return launch_tc5_v<BN, 6>(ta, tb, p, M, N, K, s);
-    }
-    return AIMB_ERR_UNSUPPORTED;
-}
-
-static int pick_bn2(int64_t M, int N) {
-    const int cand[3] = {256, 192, 0};
-    int best = 0; double best_cost = 1e30;
-    int64_t mt = (M + 2 * BM - 1) / (2 * BM);
-    int pairs = num_sms() / 2;
-    for (int i = 0; i < 3; ++i) {
-        int bn = cand[i];
-        if (bn == 0 || N % bn) continue;
-        int64_t tiles = mt * (N / bn);
-        int64_t waves = (tiles + pairs - 1) / pairs;
-        double cost = (double)waves * ((double)bn + 16.0);
-        if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
-    }
-    return best;
-}
-
-// Pick the N tile that minimises  waves x (mainloop + fixed per-tile cost)  over the persistent grid.
-// Per-tile time ~ KB*bn (MMA-bound mainloop) + ~1536 (pipeline fill / epilogue tail), fitted to the sweep in
-// profiles/ (bench_tools/gemm_sweep.py): N=2304/3072 prefer 256, N=768 prefers 192.
-// which (tile width, epilogue variant) pairs leave >= 3 pipeline stages next to the slab buffers of gemm_tc4_kernel
 template <int V> static bool tc4_ok_v(int bn, bool direct) {
     switch (bn) {
         case 256: return direct ? TileCfg4<256, V, true>::OK : TileCfg4<256, V, false>::OK;
@@ -1846,37 +1117,6 @@ int gemm_tc_launch(const void* A, int64_t lda, const void* W, int64_t ldw, const
     if (K % BK || N % 64 || (lda % 8) || (ldw % 8) || ((uintptr_t)A & 15) || ((uintptr_t)W & 15)) return AIMB_ERR_ARG;
     if (p.ldo % 8 || ((uintptr_t)p.out & 15)) return AIMB_ERR_ARG;
     if (M >= (1ll << 31)) return AIMB_ERR_ARG;
-    if (cta_mode == 2 && N % 64 == 0 && M > BM) {       // CTA-pair kernel (cta_group::2), opt-in: see DESIGN.md
-        int bn2 = (force_bn == 256 || force_bn == 192) ? force_bn : pick_bn2(M, N);
-        if (bn2 && N % bn2 == 0) {
-            CUtensorMap ta2, tb2;
-            int rc2 = make_tmap_bf16(&ta2, A, M, K, lda, BM);
-            if (rc2) return rc2;
-            rc2 = make_tmap_bf16(&tb2, W, N, K, ldw, bn2 / 2);
-            if (rc2) return rc2;
-            switch (bn2) {
-                case 256: return launch_tc2<256>(ta2, tb2, p, (int)M, N, K, s);
-                case 192: return launch_tc2<192>(ta2, tb2, p, (int)M, N, K, s);
-            }
-        }
-    }
-    if (g_pair_epi && M > BM) {                         // CTA pairs + row-layout epilogue where the variant's buffers fit
-        const int bn5 = (force_bn == 256 || force_bn == 192 || force_bn == 128) ? force_bn : (N % 256 == 0 ? 256 : (N % 192 == 0 ? 192 : 0));
-        if (bn5 && N % bn5 == 0) {
-            CUtensorMap ta5, tb5;
-            int rc5 = make_tmap_bf16(&ta5, A, M, K, lda, BM);
-            if (rc5) return rc5;
-            rc5 = make_tmap_bf16(&tb5, W, N, K, ldw, bn5 / 2);
-            if (rc5) return rc5;
-            rc5 = AIMB_ERR_UNSUPPORTED;
-            switch (bn5) {
-                case 256: rc5 = launch_tc5<256>(ta5, tb5, p, (int)M, N, K, s); break;
-                case 192: rc5 = launch_tc5<192>(ta5, tb5, p, (int)M, N, K, s); break;
-                case 128: rc5 = launch_tc5<128>(ta5, tb5, p, (int)M, N, K, s); break;
-            }
-            if (rc5 != AIMB_ERR_UNSUPPORTED) return rc5;
-        }
-    }
     const int var = pick_variant(p);
     const bool direct = use_tc4_direct(var, K, p);
     int bn = force_bn > 0 ? force_bn : pick_bn(M, N, K, (direct || use_tc4(var)) ? var : -1, direct);
@@ -2010,12 +1250,7 @@ static int launch_wgrad(const CUtensorMap& tp, const CUtensorMap& tq, float* out
     constexpr int STG = 2 * BOX + (NS / 64) * BOX;
     constexpr int STAGES = (200 * 1024) / STG > 6 ? 6 : (200 * 1024) / STG;
     constexpr int SMEM = STAGES * STG + 4 * 32 * 33 * 4 + 1024 + 256;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(wgrad_tc_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess)
-            return AIMB_ERR_CUDA;
-        attr_set = true;
-    }
+    AIMB_SET_SMEM_ATTR(SMEM, wgrad_tc_kernel<NS>);
     int KB = (R + 63) / 64;
     int mtiles = CB / 128;
     int splits = num_sms() / mtiles;
@@ -2058,13 +1293,7 @@ template <int R, int BN2, int V1, int V2>
 static int launch_adapter_v(const CUtensorMap& ta, const CUtensorMap& tb1, const CUtensorMap& tb2, const EpiParams& e1,
                             const EpiParams& e2, int M, int D, cudaStream_t s) {
     using Cfg = AdapterCfg<R, BN2>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(adapter_tc_kernel<R, BN2, V1, V2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) !=
-            cudaSuccess)
-            return AIMB_ERR_CUDA;
-        attr_set = true;
-    }
+    AIMB_SET_SMEM_ATTR(Cfg::SMEM_BYTES, adapter_tc_kernel<R, BN2, V1, V2>);
     launch_k((adapter_tc_kernel<R, BN2, V1, V2>), dim3((M + BM - 1) / BM), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, s, ta, tb1, tb2, e1,
              e2, M, D);
     AIMB_CHECK_LAUNCH();
@@ -2109,12 +1338,19 @@ static int g_force_bn = 0;
 static int g_cta_mode = 0;   // 0/1: 1-CTA kernel (default), 2: CTA-pair (cta_group::2) kernel where it tiles
 extern "C" void aimb_debug_force_bn(int bn) { g_force_bn = bn; }
 extern "C" void aimb_debug_cta_mode(int mode) {
-    g_cta_mode = mode == 2 ? 2 : 1;      // 2: CTA-pair kernel (cta_group::2); everything else: 1-CTA mainloop with
-    aimb::g_epi_kernel = (mode == 2 || mode == 5) ? (mode == 5 ? 0 : 1) : mode;   // 0 auto, 1 gemm_tc_kernel, 3 gemm_tc3_kernel, 4 gemm_tc4_kernel
-    aimb::g_pair_epi = mode == 5;        // 5: gemm_tc5_kernel (CTA pairs + row-layout epilogue), falling back to auto
+    // 0: auto (gemm_tc4_kernel wherever its buffers fit), 1: force the generic gemm_tc_kernel, 4: force gemm_tc4_kernel.
+    // (modes 2 / 3 / 5 selected kernel generations that were measured and removed in round 2: profiles/r1_gemm_*.txt)
+    g_cta_mode = 1;
+    aimb::g_epi_kernel = (mode == 1 || mode == 4) ? mode : 0;
 }
 extern "C" void aimb_debug_direct_epilogue(int v) { aimb::g_direct = v; }
-extern "C" void aimb_debug_skip_epilogue(int v) { cudaMemcpyToSymbol(g_dbg_skip_epilogue, &v, sizeof(int)); }
+extern "C" void aimb_debug_skip_epilogue(int v) {
+#ifdef AIMB_DEBUG_EPILOGUE
+    cudaMemcpyToSymbol(g_dbg_skip_epilogue, &v, sizeof(int));
+#else
+    (void)v;       // compiled out of release builds
+#endif
+}
 
 extern "C" int aimb_gemm_nt(const void* A, int64_t lda, const void* W, int64_t ldw, const aimb_epilogue_t* epi, int64_t M,
                             int32_t N, int32_t K, int32_t dtype, int32_t impl, void* stream) {
@@ -2124,7 +1360,7 @@ extern "C" int aimb_gemm_nt(const void* A, int64_t lda, const void* W, int64_t l
     if (M == 0) return AIMB_OK;
     EpiParams p = make_epi(epi, N);
     cudaStream_t s = (cudaStream_t)stream;
-    if (p.colsum_out && cudaMemsetAsync(p.colsum_out, 0, (size_t)N * 4, s) != cudaSuccess) return AIMB_ERR_CUDA;
+    if (p.colsum_out && !p.colsum_accumulate && cudaMemsetAsync(p.colsum_out, 0, (size_t)N * 4, s) != cudaSuccess) return AIMB_ERR_CUDA;
     // tcgen05 kernel for every shape it tiles (all ViT-B/16 and ViT-L/14 GEMMs); shapes it cannot tile
     // (N or K not a multiple of 64 — toy widths only) run on the SIMT kernel, still on the GPU.
     // (also M < 128: the per-frame [B*T, D] GEMMs of the fork block — a TMA box may not exceed the tensor)
@@ -2164,7 +1400,7 @@ extern "C" int aimb_adapter_fused(const void* A, int64_t lda, const void* W1, co
     if (M == 0) return AIMB_OK;
     EpiParams e1 = make_epi(epi1, R), e2 = make_epi(epi2, D);
     cudaStream_t s = (cudaStream_t)stream;
-    if (e1.colsum_out && cudaMemsetAsync(e1.colsum_out, 0, (size_t)R * 4, s) != cudaSuccess) return AIMB_ERR_CUDA;
+    if (e1.colsum_out && !e1.colsum_accumulate && cudaMemsetAsync(e1.colsum_out, 0, (size_t)R * 4, s) != cudaSuccess) return AIMB_ERR_CUDA;
     if (e2.colsum_out) return AIMB_ERR_UNSUPPORTED;
     return adapter_tc_launch(A, lda, W1, W2, e1, e2, M, D, R, s);
 }

@@ -66,6 +66,7 @@ class Engine:
         self._cur_mode = "eval"
         self.saved: Optional[dict] = None
         self.attn_impl = lib.IMPL_AUTO
+        self.grads_prezeroed = False
         self.gemm_impl = lib.IMPL_AUTO
         # T_Adapter has no skip and is the only consumer of the temporal out_proj (vitclip_aim.py:203-204), so
         # D_fc1(out_proj(o)) = o (W1 Wo)^T + (W1 bo + b1): the temporal out_proj GEMM and its dgrad need not be launched.
@@ -142,7 +143,7 @@ class Engine:
         ev.record(torch.cuda.current_stream(self.device))
         self._side2.wait_event(ev)
         with torch.cuda.stream(self._side2):
-            lib.colsum(dx, colsum_out, row_scale=colsum_row_scale, alpha=colsum_alpha)
+            self._colsum(dx, colsum_out, row_scale=colsum_row_scale, alpha=colsum_alpha)
         self._side2_busy = True
         return dx
 
@@ -160,7 +161,17 @@ class Engine:
         self.saved = None
 
     def gemm(self, a, w, out, **kw):
+        if self.grads_prezeroed and kw.get("colsum_out") is not None:
+            kw["colsum_accumulate"] = True
         return lib.gemm_nt(a, w, out, impl=self.gemm_impl, **kw)
+
+    # gradient outputs: when the caller has zeroed the whole flat gradient buffer once, the ~200 per-call memsets of the
+    # weight-gradient / column-sum kernels (graph memset nodes between the kernels) are not issued
+    def _wgrad(self, dy, x, dw, alpha=1.0):
+        return lib.gemm_wgrad(dy, x, dw, alpha=alpha, accumulate=self.grads_prezeroed)
+
+    def _colsum(self, x, out, row_scale=None, alpha=1.0):
+        return lib.colsum(x, out, row_scale=row_scale, alpha=alpha, accumulate=self.grads_prezeroed)
 
     # ------------------------------------------------------------------ forward
     def forward(self, x: torch.Tensor, W: Dict[str, torch.Tensor], d: Dims, training: bool,
@@ -428,7 +439,8 @@ class Engine:
 
     # ------------------------------------------------------------------ backward
     def backward(self, dfeat: torch.Tensor, W: Dict[str, torch.Tensor], WT: Dict[str, torch.Tensor],
-                 grads: Dict[str, torch.Tensor], on_block_done: Optional[Callable[[int], None]] = None):
+                 grads: Dict[str, torch.Tensor], on_block_done: Optional[Callable[[int], None]] = None,
+                 grads_prezeroed: bool = False):
         """dfeat fp32 [B, D, T].  WT: transposed weights ([K,N] contiguous) for the dgrad GEMMs.
         grads: name -> fp32 tensor (views of the flat gradient buffer), overwritten.
         on_block_done(i) is called after block i's gradients are complete (i = L for ln_post, -1 for
@@ -438,6 +450,7 @@ class Engine:
             raise lib.AimbError("Engine.backward() without a pending training forward")
         d: Dims = sv["d"]
         self._cur_mode = "train"
+        self.grads_prezeroed = bool(grads_prezeroed)
         M, D, n = d.M, d.D, d.n
         dx = self.buf("dx", (M, D))
         tm, tr = sv["tail"]
@@ -476,26 +489,26 @@ class Engine:
         side = self.wgrad_side and not (self.fuse_adapters and lib.adapter_fused_supported(dy, r, D))
         if side:
             with torch.cuda.stream(self._side_begin()):
-                lib.gemm_wgrad(dy, g, grads[k2w], alpha=alpha)
+                self._wgrad(dy, g, grads[k2w], alpha=alpha)
         else:
-            lib.gemm_wgrad(dy, g, grads[k2w], alpha=alpha)
+            self._wgrad(dy, g, grads[k2w], alpha=alpha)
         if not db2_fused:
-            lib.colsum(dy, grads[k2b], row_scale=rs, alpha=alpha)
+            self._colsum(dy, grads[k2b], row_scale=rs, alpha=alpha)
         # d_h = rs * alpha * (dy W2) * gelu'(h) ; db1 = column sums of d_h, taken in the same epilogue
         d_h = self.buf("d_h", (M, r))
         epi1 = dict(dact_src=h, dact=lib.ACT_GELU, alpha=alpha, row_scale=rs, colsum_out=grads[k1b])
         epi2 = dict(res1=d_a_res)
         if self.fuse_adapters and self.gemm_impl == lib.IMPL_AUTO and lib.adapter_fused_supported(dy, r, D):
             lib.adapter_fused(dy, WT[k2w], WT[k1w], d_h, d_a_out, epi1, epi2)
-            lib.gemm_wgrad(d_h, a, grads[k1w])
+            self._wgrad(d_h, a, grads[k1w])
             return d_a_out
         self.gemm(dy, WT[k2w], d_h, **epi1)
         if side:
             with torch.cuda.stream(self._side_begin()):      # ordered after the d_h GEMM, concurrent with the d_a GEMM
-                lib.gemm_wgrad(d_h, a, grads[k1w])
+                self._wgrad(d_h, a, grads[k1w])
         self.gemm(d_h, WT[k1w], d_a_out, **epi2)
         if not side:
-            lib.gemm_wgrad(d_h, a, grads[k1w])
+            self._wgrad(d_h, a, grads[k1w])
         elif not lazy_join:
             self._join_side()
         return d_a_out
@@ -511,9 +524,9 @@ class Engine:
         side = self.wgrad_side
         if side:
             with torch.cuda.stream(self._side_begin()):
-                lib.gemm_wgrad(dy, g, grads[k2w])
+                self._wgrad(dy, g, grads[k2w])
         else:
-            lib.gemm_wgrad(dy, g, grads[k2w])
+            self._wgrad(dy, g, grads[k2w])
         d_h = self.buf("d_h", (M, r))
         self.gemm(dy, WT[k2w], d_h, dact_src=h, dact=lib.ACT_GELU, row_scale=rs, colsum_out=grads[k1b])
 

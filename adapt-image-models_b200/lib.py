@@ -31,7 +31,8 @@ class Epilogue(C.Structure):
     _fields_ = [("bias", C.c_void_p), ("row_scale", C.c_void_p), ("res1", C.c_void_p), ("res2", C.c_void_p),
                 ("dact_src", C.c_void_p), ("out", C.c_void_p), ("out_pre", C.c_void_p), ("alpha", C.c_float),
                 ("row_mod", C.c_int32), ("act", C.c_int32), ("dact", C.c_int32), ("bias_rowscaled", C.c_int32),
-                ("out_f32", C.c_int32), ("accumulate", C.c_int32), ("ldo", C.c_int64), ("colsum_out", C.c_void_p)]
+                ("out_f32", C.c_int32), ("accumulate", C.c_int32), ("ldo", C.c_int64), ("colsum_out", C.c_void_p),
+                ("colsum_accumulate", C.c_int32)]
 
 
 # name -> argtypes; every function returns int except where noted.  Must list EVERY symbol of aimb200.h.
@@ -200,7 +201,8 @@ def tail_bwd(dfeat, x, mean, rstd, gamma, dx, dgamma, dbeta, B, T, n):
 
 
 def make_epilogue(out, bias=None, row_scale=None, res1=None, res2=None, dact_src=None, out_pre=None, alpha=1.0, act=0,
-                  dact=0, bias_rowscaled=False, out_f32=False, accumulate=False, ldo=0, colsum_out=None) -> Epilogue:
+                  dact=0, bias_rowscaled=False, out_f32=False, accumulate=False, ldo=0, colsum_out=None,
+                  colsum_accumulate=False) -> Epilogue:
     e = Epilogue()
     e.bias, e.row_scale, e.res1, e.res2 = _ptr(bias), _ptr(row_scale), _ptr(res1), _ptr(res2)
     e.dact_src, e.out, e.out_pre = _ptr(dact_src), _ptr(out), _ptr(out_pre)
@@ -210,6 +212,7 @@ def make_epilogue(out, bias=None, row_scale=None, res1=None, res2=None, dact_src
     e.bias_rowscaled, e.out_f32, e.accumulate = int(bias_rowscaled), int(out_f32), int(accumulate)
     e.ldo = ldo
     e.colsum_out = _ptr(colsum_out)
+    e.colsum_accumulate = int(colsum_accumulate)
     return e
 
 

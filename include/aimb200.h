@@ -51,8 +51,9 @@ extern "C" {
  *   if (row_scale && !bias_rowscaled) v *= row_scale[m % row_mod]   (DropPath per-token multiplier)
  *   v += res1[m,n] + res2[m,n]
  *   out[m,n] = v          (or out[m,n] += v when accumulate && out_f32)
- *   if (colsum_out) colsum_out[n] = sum_m v               (fp32; the bias gradient of the layer that consumes `out`,
- *                                                         produced while the tile is still in registers)
+ *   if (colsum_out) colsum_out[n] (+)= sum_m v            (fp32; the bias gradient of the layer that consumes `out`,
+ *                                                         produced while the tile is still in registers; `+=` when
+ *                                                         colsum_accumulate: the caller has zeroed the buffer)
  * NULL pointers disable the corresponding term. */
 typedef struct aimb_epilogue {
     const void* bias;       /* [N], dtype */
@@ -70,7 +71,8 @@ typedef struct aimb_epilogue {
     int32_t out_f32;
     int32_t accumulate;
     int64_t ldo; /* 0 -> N */
-    float* colsum_out; /* [N] fp32, overwritten */
+    float* colsum_out; /* [N] fp32, overwritten (or accumulated into, see colsum_accumulate) */
+    int32_t colsum_accumulate; /* 1: do not zero colsum_out first (one memset of the whole gradient buffer by the caller) */
 } aimb_epilogue_t;
 
 int aimb_version(void);

@@ -127,7 +127,7 @@ def test_gemm_simt_bf16(case):
     assert _gemm_case(lib, "bf16", 333, 192, 128, case, lib.IMPL_SIMT) < 1.5e-2
 
 
-@pytest.mark.parametrize("cta_mode", [0, 5, 4, 3, 2, 1])
+@pytest.mark.parametrize("cta_mode", [0, 4, 1])
 @pytest.mark.parametrize("bn", [64, 128, 192, 256])
 @pytest.mark.parametrize("M,N,K", [(128, 768, 64), (1576, 768, 768), (300, 768, 3072), (12608, 2304, 768), (129, 768, 128),
                                    (385, 768, 192)])
@@ -146,7 +146,7 @@ def test_gemm_tc_shapes(cta_mode, bn, M, N, K):
         lib.load().aimb_debug_cta_mode(0)
 
 
-@pytest.mark.parametrize("cta_mode", [0, 5, 4, 3, 2, 1])
+@pytest.mark.parametrize("cta_mode", [0, 4, 1])
 @pytest.mark.parametrize("case", EPI_CASES)
 def test_gemm_tc_epilogues(case, cta_mode):
     lib = _lib()

@@ -34,7 +34,7 @@ def _worker(rank, world, port, q):
         m.attach_grad_sync(sync)
 
         class FakeEngine:      # fills each block's gradient slice with (rank+1) and reports completion in backward order
-            def backward(self, dfeat, W, WT, grads, on_done):
+            def backward(self, dfeat, W, WT, grads, on_done, **kw):
                 L = m.layers
                 for n_, g in grads.items():
                     if n_.startswith("ln_post"):
