@@ -148,7 +148,7 @@ class ViT_CLIP(nn.Module):
         self.num_tadapter, self.adapter_scale = num_tadapter, float(adapter_scale)
         self.drop_path_rate = float(drop_path_rate)
         self.pretrained = pretrained
-        self.checkpoint = checkpoint   # accepted for config compatibility; activations are kept (fits 180 GB)
+        self.checkpoint = bool(checkpoint)   # per-block activation recompute in backward (vit_clip.py:318-319)
         self.conv1 = nn.Conv2d(3, width, kernel_size=patch_size, stride=patch_size, bias=False)
         scale = width ** -0.5
         self.class_embedding = nn.Parameter(scale * torch.randn(width))
@@ -391,7 +391,7 @@ class ViT_CLIP(nn.Module):
         if x.dtype == torch.float16:      # apex O1 / auto_fp16 callers (recognizers/base.py:141): exact in fp32 mode, and the
             x = x.to(self.compute_dtype)  # patch GEMM reads bf16 anyway in bf16 mode
         with torch.cuda.device(x.device):     # kernels and streams follow the tensors, not the caller's current device
-            return self._engine.forward(x.contiguous(), W, d, training, masks, WT)
+            return self._engine.forward(x.contiguous(), W, d, training, masks, WT, checkpoint=self.checkpoint)
 
     def _run_backward(self, dfeat: torch.Tensor):
         W, WT, d = self._step_ctx

@@ -67,6 +67,7 @@ class Engine:
         self.saved: Optional[dict] = None
         self.attn_impl = lib.IMPL_AUTO
         self.grads_prezeroed = False
+        self.ckpt = False
         self.gemm_impl = lib.IMPL_AUTO
         # T_Adapter has no skip and is the only consumer of the temporal out_proj (vitclip_aim.py:203-204), so
         # D_fc1(out_proj(o)) = o (W1 Wo)^T + (W1 bo + b1): the temporal out_proj GEMM and its dgrad need not be launched.
@@ -175,13 +176,17 @@ class Engine:
 
     # ------------------------------------------------------------------ forward
     def forward(self, x: torch.Tensor, W: Dict[str, torch.Tensor], d: Dims, training: bool,
-                drop_masks: Optional[List] = None, WT: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
+                drop_masks: Optional[List] = None, WT: Optional[Dict[str, torch.Tensor]] = None,
+                checkpoint: bool = False) -> torch.Tensor:
         """x [B,3,T,H,W] (fp32 / bf16 / uint8) -> feat fp32 [B, D, T].  W: weights in compute dtype.
         drop_masks[i] = (mask_t, mask_m): fp32 [n] DropPath multipliers (0 or 1/keep) or None."""
         M, D, r, n, BT = d.M, d.D, d.r, d.n, d.BT
         sv = {"d": d, "blocks": []} if training else None
         key = "train" if training else "eval"
         self._enter_mode(key, d)
+        # checkpoint=True (vit_clip.py:318-319, torch.utils.checkpoint per block): only the block INPUTS are kept; every
+        # block's saved activations live in ONE shared buffer set and are recomputed block by block in backward
+        self.ckpt = bool(checkpoint and training)
         # ---- stem
         cols = self.buf("cols", (BT * d.G * d.G, d.kpad))
         lib.im2col(x, cols, d.patch, W.get("input_mean"), W.get("input_std"))
@@ -283,7 +288,7 @@ class Engine:
     def _block_fwd(self, i, x, W, d, training, masks, sv):
         M, D, r, n = d.M, d.D, d.r, d.n
         pre = f"transformer.resblocks.{i}."
-        bk = ("train", i) if training else "eval"          # per-block buffers only when they must survive
+        bk = (("train", "ckpt") if self.ckpt else ("train", i)) if training else "eval"   # per-block buffers only when they must survive
         mask_t, mask_m = masks
         S = {} if training else None
         f32 = torch.float32
@@ -346,7 +351,7 @@ class Engine:
         x += (1 - lambda) a_o + drop_path(scale * S_Adapter(lambda a_c)); then the shared MLP half."""
         M, D, n, BT = d.M, d.D, d.n, d.BT
         pre = f"transformer.resblocks.{i}."
-        bk = ("train", i) if training else "eval"
+        bk = (("train", "ckpt") if self.ckpt else ("train", i)) if training else "eval"
         mask_s, mask_m = masks
         f32 = torch.float32
         Wqkv, bqkv = W[pre + "attn.in_proj_weight"], W[pre + "attn.in_proj_bias"]
@@ -460,10 +465,19 @@ class Engine:
             on_block_done(d.L)
         for i in reversed(range(d.L)):
             prev_mask_m = sv["blocks"][i - 1]["masks"][1] if i > 0 else None
+            S = sv["blocks"][i]
+            if self.ckpt:
+                # recompute this block's activations from its saved input (same DropPath masks -> identical values)
+                self._join_side()
+                self._join_side2()
+                tmp = {"blocks": []}
+                fwd = self._block_fwd_fork if d.block == "fork" else self._block_fwd
+                fwd(i, S["x"], W, d, True, S["masks"], tmp)
+                S = tmp["blocks"][0]
             if d.block == "fork":
-                dx = self._block_bwd_fork(i, dx, W, WT, grads, d, sv["blocks"][i])
+                dx = self._block_bwd_fork(i, dx, W, WT, grads, d, S)
             else:
-                dx = self._block_bwd(i, dx, W, WT, grads, d, sv["blocks"][i], prev_mask_m)
+                dx = self._block_bwd(i, dx, W, WT, grads, d, S, prev_mask_m)
             if on_block_done:
                 on_block_done(i)
         # ln_pre backward -> dz ; temporal_embedding grad = sum over (b, token)   (vit_clip.py:443-447)

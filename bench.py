@@ -268,8 +268,10 @@ def run_ours(args):
     import aimb200
     from aimb200 import lib
     lib.load()
-    C = CONFIGS[args.config]
-    mc = C["model"]
+    C = dict(CONFIGS[args.config])
+    if args.per_gpu > 0:
+        C["per_gpu"] = args.per_gpu
+    mc = dict(C["model"], checkpoint=bool(args.checkpoint))
     B, views, T = C["per_gpu"], C.get("views", 1), mc["num_frames"]
     tr = Trainer(dev, world, mc, dtype=args.dtype, train=C["train"], views=views)
     g = torch.Generator().manual_seed(2 + rank)
@@ -461,7 +463,7 @@ def run_ours(args):
                "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
                "config": {"workload": C["workload"], "name": args.config, "global_batch": world * B, "per_gpu": B,
-                          "parallelism": f"dp{world}", "block": "aim", "input": "uint8 clips, GPUNormalize fused into the patch load",
+                          "parallelism": f"dp{world}", "block": "aim", "activation_checkpointing": bool(args.checkpoint), "input": "uint8 clips, GPUNormalize fused into the patch load",
                           "cuda_graph": use_graph, "peak_hbm_gib": round(peak_mem, 1),
                           "l2": "flushed between steps (256 MiB memset, its time subtracted)"},
                "e2e": {"value": e2e, "unit": C["unit"], "h2d_bytes_per_step": host_x.numel() + host_y.numel() * 8,
@@ -500,6 +502,8 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--sustain-s", type=float, default=5.0, help="length of the extra sustained-clock loop (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--per-gpu", type=int, default=0, help="override the clips (videos) per GPU of the chosen config")
+    ap.add_argument("--checkpoint", action="store_true", help="checkpoint=True: per-block activation recompute (vit_clip.py:318-319)")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a captured CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -360,3 +360,27 @@ def test_distributed_data_parallel_wrapper_sees_ordinary_grads():
     finally:
         if own_pg:
             dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("block", ["aim", "fork"])
+def test_checkpoint_true_recomputes_and_matches(block):
+    """checkpoint=True (vit_clip.py:318-319: torch.utils.checkpoint per block): same logits and gradients as with stored
+    activations (the recompute is deterministic, DropPath masks are reused), with one shared set of per-block buffers."""
+    cfg = O.OracleCfg(**TINY, block=block)
+    x = O.fixture_clip(cfg, 2).cuda()
+    res = {}
+    for ck in (False, True):
+        m = aimb200.build_backbone(dict(type="ViT_CLIP", drop_path_rate=0.3, block=block, compute_dtype="bf16", checkpoint=ck, **TINY))
+        m.init_weights()
+        m.load_state_dict(O.fixture_state_dict(cfg))
+        m = m.cuda().train()
+        torch.manual_seed(5)
+        torch.cuda.reset_peak_memory_stats()
+        feat = m(x)
+        feat.square().mean().backward()
+        nb = sum(t.numel() * t.element_size() for t in m._engine._bufs.values())
+        res[ck] = (feat.detach().clone(), {k: p.grad.clone() for k, p in m.named_parameters() if p.requires_grad}, nb)
+    assert torch.equal(res[False][0], res[True][0])
+    for k in res[False][1]:
+        assert torch.allclose(res[False][1][k], res[True][1][k], rtol=1e-5, atol=1e-8), k    # fp32 atomics: order may differ
+    assert res[True][2] < 0.8 * res[False][2]          # 2 layers: one shared activation set instead of two
