@@ -46,7 +46,7 @@ CONFIGS = {
     "cfg3": dict(model=dict(VITB, num_frames=16, **ADAPT), train=True, per_gpu=8, tflop=1.719, unit="clips/s",
                  metric="AIM ViT-B/16 16x224 train clips/s",
                  workload="AIM ViT-B/16 16x224 training step (cfg3): 8 clips/GPU"),
-    "cfg5": dict(model=dict(VITL, num_frames=32, **ADAPT), train=True, per_gpu=int(os.environ.get("AIMB200_CFG5_CLIPS", "14")),
+    "cfg5": dict(model=dict(VITL, num_frames=32, **ADAPT), train=True, per_gpu=int(os.environ.get("AIMB200_CFG5_CLIPS", "20")),
                  tflop=15.94, unit="clips/s", metric="AIM ViT-L/14 32x224 train clips/s",
                  workload="AIM ViT-L/14 32x224 bf16 training step (cfg5), batch sized for 180 GB HBM"),
     "cfg4": dict(model=dict(VITL, num_frames=8, **ADAPT), train=False, per_gpu=8, views=3, tflop=5.60, unit="videos/s",
