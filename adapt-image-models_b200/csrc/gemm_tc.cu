@@ -814,7 +814,7 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint64_t* tfull_bar = a2_bar + 1;             // [2]
     uint64_t* tempty_bar = tfull_bar + 2;         // [2]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = ptx::warp_id_uniform(), lane = threadIdx.x & 31;
     const int m_blk = blockIdx.x;
     const int KB1 = D / BK, KB2 = R / BK, NCH = D / BN2;
 
@@ -832,31 +832,31 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
     pdl_wait();
 
     if (warp == 0) {
-        if (lane == 0) {
+        {
             int stage = 0; uint32_t phase = 0;
             for (int kb = 0; kb < KB1; ++kb) {
                 ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                ptx::mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + Cfg::B1_BYTES);
+                ptx::mbar_arrive_expect_tx_e(&full_bar[stage], A_STAGE_BYTES + Cfg::B1_BYTES);
                 uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-                ptx::tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
-                ptx::tma_load_2d(sa + A_STAGE_BYTES, &tmB1, &full_bar[stage], kb * BK, 0);
+                ptx::tma_load_2d_e(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+                ptx::tma_load_2d_e(sa + A_STAGE_BYTES, &tmB1, &full_bar[stage], kb * BK, 0);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
             for (int j = 0; j < NCH; ++j)
                 for (int kb = 0; kb < KB2; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                    ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::B2_BYTES);
+                    ptx::mbar_arrive_expect_tx_e(&full_bar[stage], Cfg::B2_BYTES);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-                    ptx::tma_load_2d(sa + A_STAGE_BYTES, &tmB2, &full_bar[stage], kb * BK, j * BN2);
+                    ptx::tma_load_2d_e(sa + A_STAGE_BYTES, &tmB2, &full_bar[stage], kb * BK, j * BN2);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             constexpr uint32_t idesc1 = ptx::umma_idesc_bf16(BM, R);
             constexpr uint32_t idesc2 = ptx::umma_idesc_bf16(BM, BN2);
             int stage = 0; uint32_t phase = 0;
@@ -868,9 +868,9 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const uint64_t bdesc = ptx::umma_desc_kmajor_sw128(sa + A_STAGE_BYTES);
 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k)
-                    ptx::umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc1, (kb | k) != 0 ? 1u : 0u);
-                ptx::umma_commit(&empty_bar[stage]);
-                if (kb == KB1 - 1) ptx::umma_commit(acc1_bar);
+                    ptx::umma_bf16_e(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc1, (kb | k) != 0 ? 1u : 0u);
+                ptx::umma_commit_e(&empty_bar[stage]);
+                if (kb == KB1 - 1) ptx::umma_commit_e(acc1_bar);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
             ptx::mbar_wait(a2_bar, 0);            // hidden tile is in smem (and acc1's TMEM columns are drained)
@@ -889,9 +889,9 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     const uint64_t bdesc = ptx::umma_desc_kmajor_sw128(sb);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k)
-                        ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc2, (kb | k) != 0 ? 1u : 0u);
-                    ptx::umma_commit(&empty_bar[stage]);
-                    if (kb == KB2 - 1) ptx::umma_commit(&tfull_bar[buf]);
+                        ptx::umma_bf16_e(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc2, (kb | k) != 0 ? 1u : 0u);
+                    ptx::umma_commit_e(&empty_bar[stage]);
+                    if (kb == KB2 - 1) ptx::umma_commit_e(&tfull_bar[buf]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
