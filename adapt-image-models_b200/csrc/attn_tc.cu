@@ -56,7 +56,7 @@ struct FwdBars {
 };
 
 __global__ void __launch_bounds__(FWD_THREADS, 1)
-attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, bf16* __restrict__ o, float* __restrict__ lse, const int n,
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tmO, float* __restrict__ lse, const int n,
                    const int heads, const int D, const int nprob, const int MT, const int NKP, const int NST, long long* __restrict__ tl) {
     pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
@@ -65,7 +65,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, bf16* __restrict__ o,
     const int STAGE_B = MT * QTILE_B + 2 * KB * BOXB;
     // bench_tools only: event timeline of CTA 0 (clock64 per unit and event), see bench_tools/attn_tc_timeline.py
     auto mark = [&](int u, int ev) { if (tl && blockIdx.x == 0 && (threadIdx.x & 31) == 0) tl[u * 16 + ev] = clock64(); };
-    FwdBars* bars = reinterpret_cast<FwdBars*>(smem + NST * STAGE_B);
+    uint8_t* sO = smem + NST * STAGE_B;                     // output staging: one [128 rows][64] box per softmax warpgroup
+    FwdBars* bars = reinterpret_cast<FwdBars*>(sO + 2 * QTILE_B);
     const int warp = ptx::warp_id_uniform(), lane = threadIdx.x & 31;
     const int nloc = (nprob - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // problems of this CTA
     const int U = nloc * MT;                                                             // units of this CTA
@@ -75,6 +76,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, bf16* __restrict__ o,
     const int RS = OSEP ? NKP : 256;
     if (threadIdx.x == 0) {
         ptx::prefetch_tmap(&tm);
+        ptx::prefetch_tmap(&tmO);
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&bars->qk_full[i], 1); ptx::mbar_init(&bars->v_full[i], 1);
             ptx::mbar_init(&bars->qk_empty[i], 1); ptx::mbar_init(&bars->v_empty[i], 1);
@@ -253,22 +255,41 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm, bf16* __restrict__ o,
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&bars->o_empty[g]);      // the output columns may be rewritten while we store
             if (wq == 0) mark(u, 4);
-            if (active && row < n) {
+            // the tile leaves through shared memory: a thread writes its 128-byte row as swizzled 16-byte chunks and one TMA
+            // store per unit writes the [128 rows][64] box; the tensor map clips the rows >= n.  (32-byte stores straight from
+            // the registers measured ~1000 clk per unit: every warp instruction touched 32 different lines.)
+            const bool storer = wq == 0 && lane == 0;
+            if (it > 0) {                                         // the previous unit's store has finished reading the box
+                if (storer) ptx::bulk_wait_read0();
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+            }
+            if (active) {
                 const float inv = __fdividef(1.f, sum);
-                uint32_t ob[32];
+                const int rr = wq * 32 + lane;
+                const uint32_t base = ptx::smem_u32(sO + g * QTILE_B) + rr * 128;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    ob[j] = pack_bf16(__uint_as_float(va[2 * j]) * inv, __uint_as_float(va[2 * j + 1]) * inv);
-                    ob[16 + j] = pack_bf16(__uint_as_float(vb[2 * j]) * inv, __uint_as_float(vb[2 * j + 1]) * inv);
+                for (int i = 0; i < 8; ++i) {
+                    const uint32_t (&src)[32] = i < 4 ? va : vb;
+                    const int j0 = (i & 3) * 8;
+                    const uint32_t w0 = pack_bf16(__uint_as_float(src[j0]) * inv, __uint_as_float(src[j0 + 1]) * inv);
+                    const uint32_t w1 = pack_bf16(__uint_as_float(src[j0 + 2]) * inv, __uint_as_float(src[j0 + 3]) * inv);
+                    const uint32_t w2 = pack_bf16(__uint_as_float(src[j0 + 4]) * inv, __uint_as_float(src[j0 + 5]) * inv);
+                    const uint32_t w3 = pack_bf16(__uint_as_float(src[j0 + 6]) * inv, __uint_as_float(src[j0 + 7]) * inv);
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(base + ((i ^ (rr & 7)) << 4)), "r"(w0), "r"(w1), "r"(w2),
+                                 "r"(w3) : "memory");
                 }
-                bf16* op = o + ((int64_t)f * n + row) * D + h * HD;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) st_global_v8(op + q * 16, ob + q * 8);
-                if (lse) lse[((int64_t)f * heads + h) * n + row] = mx * SCALE + __logf(sum);
+                if (lse && row < n) lse[((int64_t)f * heads + h) * n + row] = mx * SCALE + __logf(sum);
+            }
+            ptx::fence_proxy_async();
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+            if (storer) {
+                ptx::tma_store_3d(&tmO, ptx::smem_u32(sO + g * QTILE_B), h * HD, mt * 128, f);
+                ptx::bulk_commit();
             }
             if (wq == 0) mark(u, 5);
         }
     }
+    if (warp >= 4 && (warp & 3) == 0 && lane == 0) ptx::bulk_wait0();      // shared memory must outlive the last TMA stores
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -296,7 +317,7 @@ constexpr float LOG2E = 1.4426950408889634f;
 
 struct BwdBars {
     uint64_t in_full[2], in_empty[2], v_full[2], v_empty[2], dl_full[2];
-    uint64_t sdp_full, pds_full, dvk_full, acc_empty, dq_full, dq_empty;
+    uint64_t sdp_full[2], pds_full[2], dvk_full, acc_empty, dq_full, dq_empty;
     uint32_t tmem_ptr;
 };
 
@@ -348,7 +369,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             ptx::mbar_init(&bars->in_full[i], 1); ptx::mbar_init(&bars->in_empty[i], 2); ptx::mbar_init(&bars->dl_full[i], 2);
         }
         for (int i = 0; i < 2; ++i) { ptx::mbar_init(&bars->v_full[i], 1); ptx::mbar_init(&bars->v_empty[i], 1); }
-        ptx::mbar_init(&bars->sdp_full, 1); ptx::mbar_init(&bars->pds_full, 8);
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&bars->sdp_full[i], 1); ptx::mbar_init(&bars->pds_full[i], 4); }
         ptx::mbar_init(&bars->dvk_full, 1); ptx::mbar_init(&bars->acc_empty, 8);
         ptx::mbar_init(&bars->dq_full, 1); ptx::mbar_init(&bars->dq_empty, 8);
         ptx::fence_mbar_init();
@@ -389,7 +410,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         const uint32_t idesc_dq = ptx::umma_idesc_bf16(128, HD, 1, 1);      // dQ: A and B MN-major
         const uint32_t aK = ptx::smem_u32(sK), aQ = ptx::smem_u32(sQ), aG = ptx::smem_u32(sG), aV = ptx::smem_u32(sV),
                        aS = ptx::smem_u32(sS);
-        uint32_t s = 0, c = 0;                                              // step and key-block counters (barrier phases)
+        uint32_t s = 0, s1 = 0, c = 0;                                      // step / second-half-step / key-block counters (barrier phases)
         for (int k = 0; k < nloc; ++k) {
             const int st = stage_of(k);
             ptx::mbar_wait(&bars->in_full[st], phase_of(k));
@@ -398,42 +419,64 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
                 for (int h = 0; h < NH; ++h, ++s) {
                     const int Nh = min(128, NQP - h * 128);
                     const int KSh = Nh >> 4;
-                    const uint32_t idesc_s = ptx::umma_idesc_bf16(128, Nh);
+                    // the query chunks of a step are produced, consumed and fed back in two halves (one per math warpgroup):
+                    // the second half's S^T / dP^T MMAs run while the first half is already in the math warps, and the first
+                    // half's dV / dK MMAs run while the second half is still there
+                    const int cs = (KSh + 1) >> 1;                          // 16-query chunks of the first half
+                    const int NA = cs << 4, NB = Nh - NA;
                     ptx::tc_fence_after();
                     {   // S^T = K_kb Q_h^T, dP^T = V_kb dO_h^T
                         const uint64_t ka = ptx::umma_desc_kmajor_sw128(aK + st * MATB + kb * 16384);
                         const uint64_t qb = ptx::umma_desc_kmajor_sw128(aQ + st * MATB + h * 16384);
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) ptx::umma_bf16_e(tb, ka + 2 * kk, qb + 2 * kk, idesc_s, kk ? 1u : 0u);
-                        if (h == 0) { ptx::mbar_wait(&bars->v_full[kb], (uint32_t)k & 1u); ptx::tc_fence_after(); }
                         const uint64_t va = ptx::umma_desc_kmajor_sw128(aV + kb * 16384);
                         const uint64_t gb = ptx::umma_desc_kmajor_sw128(aG + st * MATB + h * 16384);
+                        const uint32_t idesc_a = ptx::umma_idesc_bf16(128, NA);
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) ptx::umma_bf16_e(tb + 128, va + 2 * kk, gb + 2 * kk, idesc_s, kk ? 1u : 0u);
-                        ptx::umma_commit_e(&bars->sdp_full);
+                        for (int kk = 0; kk < 4; ++kk) ptx::umma_bf16_e(tb, ka + 2 * kk, qb + 2 * kk, idesc_a, kk ? 1u : 0u);
+                        if (h == 0) { ptx::mbar_wait(&bars->v_full[kb], (uint32_t)k & 1u); ptx::tc_fence_after(); }
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) ptx::umma_bf16_e(tb + 128, va + 2 * kk, gb + 2 * kk, idesc_a, kk ? 1u : 0u);
+                        ptx::umma_commit_e(&bars->sdp_full[0]);
+                        if (NB > 0) {
+                            const uint32_t idesc_b = ptx::umma_idesc_bf16(128, NB);
+                            const uint64_t ro = (uint64_t)(NA * 8);                // NA query rows further: NA * 128 B, in 16-byte units
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) ptx::umma_bf16_e(tb + NA, ka + 2 * kk, qb + ro + 2 * kk, idesc_b, kk ? 1u : 0u);
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) ptx::umma_bf16_e(tb + 128 + NA, va + 2 * kk, gb + ro + 2 * kk, idesc_b, kk ? 1u : 0u);
+                            ptx::umma_commit_e(&bars->sdp_full[1]);
+                        }
                         if (h == NH - 1) ptx::umma_commit_e(&bars->v_empty[kb]);    // last use of this half of V
                         mark(s, 8);
                     }
-                    ptx::mbar_wait(&bars->pds_full, s & 1u);
-                    mark(s, 9);                 // P^T in TMEM, dS^T in shared memory
-                    if (h == 0 && c > 0) ptx::mbar_wait(&bars->acc_empty, (c - 1) & 1u);      // dV / dK columns drained
-                    if (kb == 0 && h == 0 && k > 0) ptx::mbar_wait(&bars->dq_empty, (uint32_t)(k - 1) & 1u);
-                    ptx::tc_fence_after();
                     const uint64_t g_mn = ptx::umma_desc_mnmajor_sw128(aG + st * MATB + h * 16384, 16384);
                     const uint64_t q_mn = ptx::umma_desc_mnmajor_sw128(aQ + st * MATB + h * 16384, 16384);
                     const uint64_t k_mn = ptx::umma_desc_mnmajor_sw128(aK + st * MATB + kb * 16384, 16384);
                     const uint64_t s_k = ptx::umma_desc_kmajor_sw128(aS);
                     const uint64_t s_mn = ptx::umma_desc_mnmajor_sw128(aS, 16384);
+                    auto dv_dk = [&](int j0, int j1) {
 #pragma unroll 4
-                    for (int j = 0; j < KSh; ++j) {      // dV_kb += P^T dO_h : 16 queries per MMA; P^T chunk j sits where its math warp put it
-                        const int csplit = (KSh + 1) >> 1;
-                        const uint32_t p_col = j < csplit ? 8 * j : 16 * csplit + 8 * (j - csplit);
-                        ptx::umma_bf16_ts_e(tb + 256, tb + p_col, g_mn + (uint64_t)(j * 128), idesc_acc, (h | j) ? 1u : 0u);
+                        for (int j = j0; j < j1; ++j) {     // dV_kb += P^T dO_h : 16 queries per MMA; P^T chunk j sits where its math warp put it
+                            const uint32_t p_col = j < cs ? 8 * j : 16 * cs + 8 * (j - cs);
+                            ptx::umma_bf16_ts_e(tb + 256, tb + p_col, g_mn + (uint64_t)(j * 128), idesc_acc, (h | j) ? 1u : 0u);
+                        }
+#pragma unroll 4
+                        for (int j = j0; j < j1; ++j)       // dK_kb += dS^T Q_h : A = dS^T boxes, K-major (64 queries per box)
+                            ptx::umma_bf16_e(tb + 320, s_k + (uint64_t)((j >> 2) * 1024 + (j & 3) * 2), q_mn + (uint64_t)(j * 128),
+                                             idesc_acc, (h | j) ? 1u : 0u);
+                    };
+                    ptx::mbar_wait(&bars->pds_full[0], s & 1u);             // first half: P^T in TMEM, dS^T in shared memory
+                    mark(s, 9);
+                    if (h == 0 && c > 0) ptx::mbar_wait(&bars->acc_empty, (c - 1) & 1u);      // dV / dK columns drained
+                    if (kb == 0 && h == 0 && k > 0) ptx::mbar_wait(&bars->dq_empty, (uint32_t)(k - 1) & 1u);
+                    ptx::tc_fence_after();
+                    dv_dk(0, cs);
+                    if (NB > 0) {
+                        ptx::mbar_wait(&bars->pds_full[1], s1 & 1u);
+                        ++s1;
+                        ptx::tc_fence_after();
+                        dv_dk(cs, KSh);
                     }
-#pragma unroll 4
-                    for (int j = 0; j < KSh; ++j)        // dK_kb += dS^T Q_h : A = dS^T boxes, K-major (64 queries per box)
-                        ptx::umma_bf16_e(tb + 320, s_k + (uint64_t)((j >> 2) * 1024 + (j & 3) * 2), q_mn + (uint64_t)(j * 128),
-                                         idesc_acc, (h | j) ? 1u : 0u);
 #pragma unroll 4
                     for (int j = 0; j < KSkb; ++j)       // dQ_h += dS K_kb : A = the same boxes, MN-major (16 keys per MMA)
                         ptx::umma_bf16_e(tb + 384 + h * 64, s_mn + (uint64_t)(j * 128), k_mn + (uint64_t)(j * 128), idesc_dq,
@@ -481,7 +524,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         const uint32_t sS_row = ptx::smem_u32(sS) + r * 128;
         const bool storer = threadIdx.x == 128;                           // issues (and drains) the TMA stores
         bool st_pending = false;                                          // a TMA store may still be reading the dS^T buffer
-        uint32_t s = 0, c = 0;
+        uint32_t s = 0, s1 = 0, c = 0;
         // results leave through the (then idle) dS^T buffer: a thread writes its row as swizzled 16-byte chunks and the two
         // [128 rows][64] boxes go out as TMA stores whose tensor map clips rows >= n (padded keys / queries are never
         // written).  (Plain st.global from 256 threads measured 3-4x slower here: the CTAs run in lockstep and their store
@@ -511,12 +554,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             const float* l2 = dl + (k & 1) * 512;
             ptx::mbar_wait(&bars->dl_full[k & 1], (uint32_t)(k >> 1) & 1u);
             for (int kb = 0; kb < KBL; ++kb) {
-                const bool kvalid = kb * 128 + r < n;
+                const uint32_t kmask = kb * 128 + r < n ? 0xffffffffu : 0u;
                 for (int h = 0; h < NH; ++h, ++s) {
                     const int Nh = min(128, NQP - h * 128);
                     const int NC = Nh >> 4;                               // 16-query chunks of this half
                     const int c0 = ch ? (NC + 1) >> 1 : 0, c1 = ch ? NC : (NC + 1) >> 1;
-                    ptx::mbar_wait(&bars->sdp_full, s & 1u);
+                    if (ch == 0) {
+                        ptx::mbar_wait(&bars->sdp_full[0], s & 1u);
+                    } else if (c0 < c1) {                              // the second half exists only when there are >= 2 chunks
+                        ptx::mbar_wait(&bars->sdp_full[1], s1 & 1u);
+                        ++s1;
+                    }
                     ptx::tc_fence_after();
                     if (warp == 4) mark(s, 0);
                     uint32_t sv[2][16], dv[2][16];
@@ -549,9 +597,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
                                 float p1 = ex2_ftz(fmaf(__uint_as_float(sc[2 * j + 1]), SCALE_LOG2, -lv[2 * j + 1]));
                                 float d0 = p0 * (__uint_as_float(dc[2 * j]) - dd[2 * j]);
                                 float d1 = p1 * (__uint_as_float(dc[2 * j + 1]) - dd[2 * j + 1]);
-                                if (!kvalid) { p0 = p1 = d0 = d1 = 0.f; }           // padded keys contribute nothing
-                                pkc[j] = pack_bf16(p0, p1);
-                                dsp[j] = pack_bf16(d0, d1);
+                                pkc[j] = pack_bf16(p0, p1) & kmask;                  // padded keys contribute nothing
+                                dsp[j] = pack_bf16(d0, d1) & kmask;
                             }
                             if (ci == 0) drain_store();     // the previous results' TMA store has finished reading the buffer
                             // dS^T -> shared memory: box (cc*16)/64 of 64 queries, row r, two 16-byte chunks (128B swizzle)
@@ -573,7 +620,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
                     ptx::fence_proxy_async();
                     ptx::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&bars->pds_full);
+                    if (lane == 0 && (ch == 0 || c0 < c1)) ptx::mbar_arrive(&bars->pds_full[ch]);
                     if (warp == 4) mark(s, 2);
                     if (h == NH - 1) {
                         // ---- dV_kb, dK_kb complete (and the MMAs that read the dS^T buffer with them)
@@ -746,14 +793,17 @@ int attn_spatial_fwd_tc(const void* qkv, void* o, float* lse, int frames, int n,
     const int NKP = (n + 15) & ~15;
     const int KB = (NKP + BOXR - 1) / BOXR;
     const int STAGE_B = MT * QTILE_B + 2 * KB * BOXB;
-    const int NST = (2 * STAGE_B + 2048 <= 227 * 1024) ? 2 : 1;
-    const int smem = NST * STAGE_B + 1024 + 256;
+    const int NST = (2 * STAGE_B + 2 * QTILE_B + 2048 <= 227 * 1024) ? 2 : 1;
+    const int smem = NST * STAGE_B + 2 * QTILE_B + 1024 + 256;
+    CUtensorMap to;
+    rc = make_tmap3(&to, o, frames, n, D, 128);
+    if (rc) return rc;
     AIMB_SET_SMEM_ATTR(227 * 1024, attn_fwd_tc_kernel);
     const int nprob = frames * heads;
     const int sms = sm_count();
     const int waves = (nprob + sms - 1) / sms;
     const int grid = (nprob + waves - 1) / waves;
-    launch_k(attn_fwd_tc_kernel, dim3(grid), dim3(FWD_THREADS), (size_t)smem, s, tm, (bf16*)o, lse, n, heads, D, nprob, MT, NKP, NST, g_attn_timeline);
+    launch_k(attn_fwd_tc_kernel, dim3(grid), dim3(FWD_THREADS), (size_t)smem, s, tm, to, lse, n, heads, D, nprob, MT, NKP, NST, g_attn_timeline);
     AIMB_CHECK_LAUNCH();
     return AIMB_OK;
 }
