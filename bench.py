@@ -219,7 +219,7 @@ class Trainer:
         self.world, self.views, self.train = world, views, train
         self.sync = None
         if train:
-            self.sync = aimb200.GradSync(bucket_blocks=int(os.environ.get("AIMB200_BUCKET_BLOCKS", "3"))) if world > 1 else None
+            self.sync = aimb200.GradSync(bucket_blocks=int(os.environ.get("AIMB200_BUCKET_BLOCKS", "6"))) if world > 1 else None
             if self.sync is not None:
                 self.backbone.attach_grad_sync(self.sync)
             decay = [p for n, p in self.backbone.named_parameters() if p.requires_grad and "Adapter" in n and n.endswith("weight")]
