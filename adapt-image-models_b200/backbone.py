@@ -418,7 +418,8 @@ class ViT_CLIP(nn.Module):
                 done_hi[0] = lo
 
         with torch.cuda.device(flat_grad.device) if flat_grad.is_cuda else contextlib.nullcontext():
-            self._engine.backward(dfeat.reshape(d.B, d.D, d.T).float(), W, WT, grads, on_done, grads_prezeroed=True)
+            self._engine.backward(dfeat.reshape(d.B, d.D, d.T).float(), W, WT, grads, on_done, grads_prezeroed=True,
+                                  bucket_ends_at=(lambda i: sync.want_bucket(i, L)) if sync is not None else None)
         if sync is not None:
             if done_hi[0] > 0:
                 sync.bucket_done(flat_grad, 0, done_hi[0])

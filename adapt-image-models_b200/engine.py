@@ -70,13 +70,17 @@ class Engine:
         self.ckpt = False
         self.gemm_impl = lib.IMPL_AUTO
         # T_Adapter has no skip and is the only consumer of the temporal out_proj (vitclip_aim.py:203-204), so
-        # D_fc1(out_proj(o)) = o (W1 Wo)^T + (W1 bo + b1): the temporal out_proj GEMM and its dgrad need not be launched.
-        # Built, parity-green (tests/test_backbone_gpu.py with AIMB200_FUSE_T_OUTPROJ=1) and measured: the 24 removed
-        # 12608 x 768 x 768 GEMMs (-0.48 ms) cost less than the 36 + 60 tiny per-step launches that form W1 Wo, its
-        # transpose and dW1 = (d_h^T o) Wo^T + db1 (x) bo (675 vs 709 clips/s) -> opt-in until those are one grouped launch
-        self.fuse_t_outproj = os.environ.get("AIMB200_FUSE_T_OUTPROJ", "0") == "1"
+        # D_fc1(out_proj(o)) = o (W1 Wo)^T + (W1 bo + b1): the temporal out_proj GEMM and its dgrad are never launched
+        # (-24 GEMMs of 12608 x 768 x 768 per step, -5 % of the step's FLOPs, a_t is never written).  The per-step products
+        # W1 Wo, their transposes and dW1 = (d_h^T o) Wo^T + db1 (x) bo are batched over all blocks (3 launches in forward,
+        # 4 per gradient bucket in backward); the first version issued them per block (96 tiny launches) and lost more
+        # than the removed GEMMs gave (675 vs 709 clips/s); batched: 731 -> 753 clips/s.
+        self.fuse_t_outproj = os.environ.get("AIMB200_FUSE_T_OUTPROJ", "1") == "1"
         self.t_fused = False
         self.fuse_adapters = os.environ.get("AIMB200_FUSE_ADAPTERS", "0") == "1"   # opt-in: measured on par at M = 12608
+        # MLP_Adapter shares its input with mlp.c_fc and its sum with mlp.c_proj (vitclip_aim.py:210-211): its two GEMMs ride
+        # on the frozen ones as N- / K-concatenated segments of ONE launch each, forward and backward (-4 launches per block)
+        self.pair_mlp = os.environ.get("AIMB200_PAIR_MLP", "1") == "1"
         # adapter weight-gradient kernels are off the critical path of backward: they run on a side stream (captured
         # into the step graph as parallel branches) and fill the SMs the small dgrad GEMMs / kernel tails leave idle
         self.wgrad_side = os.environ.get("AIMB200_WGRAD_STREAM", "1") == "1"
@@ -220,22 +224,67 @@ class Engine:
             self.saved = sv
         return feat
 
+    def _per_block(self, T: Dict[str, torch.Tensor], leaf: str, d: Dims) -> torch.Tensor:
+        """[L, *shape] strided view of one per-block trainable tensor (parameters / gradients of all blocks live in ONE flat
+        buffer with a uniform block stride: backbone.py::_flatten_trainable)."""
+        t0 = T[f"transformer.resblocks.0.{leaf}"]
+        if d.L == 1:
+            return t0.unsqueeze(0)
+        t1 = T[f"transformer.resblocks.1.{leaf}"]
+        step = (t1.data_ptr() - t0.data_ptr()) // t0.element_size()
+        return t0.as_strided((d.L,) + tuple(t0.shape), (step,) + tuple(t0.stride()))
+
+    def _t_frozen_stacks(self, W, WT, d):
+        """out_proj weights of all blocks stacked once (frozen): Wo [L, D_out, D_in], Wo^T, bo (compute dtype and fp32)."""
+        key = tuple(W[f"transformer.resblocks.{i}.attn.out_proj.weight"].data_ptr() for i in range(d.L))
+        if getattr(self, "_t_stack_key", None) != key:
+            pre = "transformer.resblocks.{}."
+            Wo = torch.stack([W[pre.format(i) + "attn.out_proj.weight"] for i in range(d.L)])
+            WoT = torch.stack([WT[pre.format(i) + "attn.out_proj.weight"] for i in range(d.L)])
+            bo = torch.stack([W[pre.format(i) + "attn.out_proj.bias"] for i in range(d.L)])
+            self._t_stack_key, self._t_stack = key, (Wo, WoT, bo, bo.float())
+        return self._t_stack
+
     def _prep_t_fused(self, W, WT, d, training):
-        """Per step (D_fc1 is trainable): W1o = W1 Wo [r, D], b1o = W1 bo + b1, and W1o^T for the dgrad."""
-        r, D = d.r, d.D
-        for i in range(d.L):
+        """Per step (D_fc1 is trainable), for ALL blocks in three batched launches: W1o = W1 Wo [r, D], b1o = W1 bo + b1,
+        and W1o^T for the dgrad.  These are weight x weight products (0.23 GFLOP per block), not part of the activation
+        path: one strided-batched library GEMM each instead of 36 tile-kernel launches."""
+        r, D, L = d.r, d.D, d.L
+        Wo, WoT, bo, _ = self._t_frozen_stacks(W, WT, d)
+        W1 = self._per_block(W, "T_Adapter.D_fc1.weight", d)                    # [L, r, D]
+        b1 = self._per_block(W, "T_Adapter.D_fc1.bias", d)                      # [L, r]
+        w1o = self.buf("t_w1o", (L, r, D))
+        torch.bmm(W1, Wo, out=w1o)                                              # sum_j W1[r, j] Wo[j, i]
+        b1o = self.buf("t_b1o", (L, 1, r))
+        torch.baddbmm(b1.unsqueeze(1), bo.unsqueeze(1), W1.transpose(1, 2), out=b1o)
+        if training:
+            w1oT = self.buf("t_w1oT", (L, D, r))                                # the N x K operand of d_o = d_h W1o
+            w1oT.copy_(w1o.transpose(1, 2))
+            self.buf("t_G", (L, r, D), torch.float32).zero_()                   # d_h^T o of every block, see _t_flush
+        for i in range(L):
             pre = f"transformer.resblocks.{i}."
-            w1, b1 = W[pre + "T_Adapter.D_fc1.weight"], W[pre + "T_Adapter.D_fc1.bias"]
-            woT, bo = WT[pre + "attn.out_proj.weight"], W[pre + "attn.out_proj.bias"]
-            w1o = self.buf("t_w1o", (r, D), key=i)
-            self.gemm(w1, woT, w1o)                                  # [r, D_in] = sum_j W1[r, j] Wo[j, i]
-            b1o = self.buf("t_b1o", (1, r), key=i)
-            self.gemm(bo.view(1, D), w1, b1o, bias=b1)               # W1 bo + b1
-            W[pre + "T_Adapter.w1o"], W[pre + "T_Adapter.b1o"] = w1o, b1o.view(r)
+            W[pre + "T_Adapter.w1o"], W[pre + "T_Adapter.b1o"] = w1o[i], b1o[i].view(r)
             if training:
-                w1oT = self.buf("t_w1oT", (D, r), key=i)
-                self.gemm(woT, w1, w1oT)                             # [D_in, r]: the N x K operand of d_o = d_h W1o
-                W[pre + "T_Adapter.w1oT"] = w1oT
+                W[pre + "T_Adapter.w1oT"] = w1oT[i]
+
+    def _t_flush(self, lo, hi, W, WT, grads, d):
+        """T_Adapter.D_fc1 weight gradients of blocks lo..hi-1 from the accumulated G = d_h^T o:
+        dW1 = G Wo^T + db1 (x) bo   (a = o Wo^T + bo was never materialised).  One batched launch chain per gradient
+        bucket, issued when the bucket's last block has finished its backward."""
+        if hi <= lo:
+            return
+        r, D, L = d.r, d.D, d.L
+        _, WoT, _, bo32 = self._t_frozen_stacks(W, WT, d)
+        self._join_side()                                                       # the wgrads that fill G run on the side stream
+        G = self.buf("t_G", (L, r, D), torch.float32)[lo:hi]
+        Gb = self.buf("t_Gb", (L, r, D))[lo:hi]
+        Gb.copy_(G)
+        Gw = self.buf("t_Gw", (L, r, D))[lo:hi]
+        torch.bmm(Gb, WoT[lo:hi], out=Gw)                                       # sum_j G[r, j] Wo[j', j]
+        dW1 = self._per_block(grads, "T_Adapter.D_fc1.weight", d)[lo:hi]
+        db1 = self._per_block(grads, "T_Adapter.D_fc1.bias", d)[lo:hi]
+        dW1.copy_(Gw)
+        dW1.baddbmm_(db1.unsqueeze(2), bo32[lo:hi].unsqueeze(1))
 
     def _adapter_fwd(self, name, pre, a, W, d, bk, training, rs, alpha, res1, res2, out):
         """out = res1 + res2 + alpha * rs * (fc2(gelu(fc1(a))))   (rs folded into the hidden, see backward)."""
@@ -262,25 +311,67 @@ class Engine:
         xn2 = self.buf("xn2", (M, D), key=bk)
         m3, r3 = self.buf("ln2_m", (M,), f32, bk), self.buf("ln2_r", (M,), f32, bk)
         lib.layernorm_fwd(x2, W[pre + "ln_2.weight"], W[pre + "ln_2.bias"], xn2, m3, r3)
-        tmp = self.buf("tmp", (M, D))
-        h_m, g_m = self._adapter_fwd("MLP_Adapter", pre, xn2, W, d, bk, training, mask_m, d.scale, x2, None, tmp)
         hf = self.buf("hf", (M, 4 * D), key=bk) if training else None
         gf = self.buf("gf", (M, 4 * D))
-        self.gemm(xn2, W[pre + "mlp.c_fc.weight"], gf, bias=W[pre + "mlp.c_fc.bias"], act=lib.ACT_QUICKGELU, out_pre=hf)
         xo = self.buf("x", (M, D), key=("train", i + 1) if training else ("eval", (i + 1) % 2))
+        if self._pair_mlp_ok(xn2, d):
+            # [hf | h_m] = xn2 [Wfc ; W1]^T in one launch; g_m = scale * mask_m * GELU(h_m) carries the whole branch factor
+            h_m = self.buf("MLP_Adapter_h", (M, d.r), key=bk) if training else None
+            g_m = self.buf("MLP_Adapter_g", (M, d.r), key=bk)
+            lib.gemm_dual_ncat(xn2, W[pre + "mlp.c_fc.weight"], W[pre + "MLP_Adapter.D_fc1.weight"], gf, g_m,
+                               dict(bias=W[pre + "mlp.c_fc.bias"], act=lib.ACT_QUICKGELU, out_pre=hf),
+                               dict(bias=W[pre + "MLP_Adapter.D_fc1.bias"], act=lib.ACT_GELU, out_pre=h_m, row_scale=mask_m,
+                                    alpha=d.scale))
+            # x_out = [gf | g_m] [Wp | W2]^T + bp + scale * mask_m * b2 + x2
+            lib.gemm_dual_kcat(gf, W[pre + "mlp.c_proj.weight"], g_m, W[pre + "MLP_Adapter.D_fc2.weight"], xo,
+                               bias2=W[pre + "MLP_Adapter.D_fc2.bias"], bias2_row_scale=mask_m, bias2_scale=d.scale,
+                               bias=W[pre + "mlp.c_proj.bias"], res1=x2)
+            return xo, dict(ln2=(m3, r3), xn2=xn2, h_m=h_m, g_m=g_m, hf=hf, paired=True)
+        tmp = self.buf("tmp", (M, D))
+        h_m, g_m = self._adapter_fwd("MLP_Adapter", pre, xn2, W, d, bk, training, mask_m, d.scale, x2, None, tmp)
+        self.gemm(xn2, W[pre + "mlp.c_fc.weight"], gf, bias=W[pre + "mlp.c_fc.bias"], act=lib.ACT_QUICKGELU, out_pre=hf)
         self.gemm(gf, W[pre + "mlp.c_proj.weight"], xo, bias=W[pre + "mlp.c_proj.bias"], res1=tmp)
-        return xo, dict(ln2=(m3, r3), xn2=xn2, h_m=h_m, g_m=g_m, hf=hf)
+        return xo, dict(ln2=(m3, r3), xn2=xn2, h_m=h_m, g_m=g_m, hf=hf, paired=False)
+
+    def _pair_mlp_ok(self, xn2, d):
+        return (self.pair_mlp and self.dtype == torch.bfloat16 and self.gemm_impl == lib.IMPL_AUTO and not self.fuse_adapters
+                and lib.dual_supported(xn2, 4 * d.D, d.r) and lib.dual_supported(xn2, d.D, 0, d.r))
 
     def _mlp_bwd(self, i, dx, W, WT, grads, d, S, mask_m, db2_fused, colsum_for=None):
         """backward of _mlp_fwd: returns dx2 = d(x2) (accumulated in place in `dx`)."""
         M, D = d.M, d.D
         pre = f"transformer.resblocks.{i}."
         d_hf = self.buf("d_big", (M, 4 * D))
-        self.gemm(dx, WT[pre + "mlp.c_proj.weight"], d_hf, dact_src=S["hf"], dact=lib.ACT_QUICKGELU)
         d_xn2 = self.buf("d_xn", (M, D))
-        self.gemm(d_hf, WT[pre + "mlp.c_fc.weight"], d_xn2)
-        self._adapter_bwd("MLP_Adapter", pre, dx, S["xn2"], S["h_m"], S["g_m"], W, WT, grads, d, mask_m, d.scale,
-                          d_xn2, d_xn2, db2_fused=db2_fused)
+        if S.get("paired"):
+            k1w, k1b = pre + "MLP_Adapter.D_fc1.weight", pre + "MLP_Adapter.D_fc1.bias"
+            k2w, k2b = pre + "MLP_Adapter.D_fc2.weight", pre + "MLP_Adapter.D_fc2.bias"
+            d_h = self.buf("d_h_m", (M, d.r))
+            self._join_side()          # the previous block's fc1 wgrad / db1 column sums still read d_h_m
+            # [d_hf | d_h] = dx [Wp^T ; W2^T]^T . [QuickGELU'(hf) | scale * mask_m * GELU'(h_m)]
+            lib.gemm_dual_ncat(dx, WT[pre + "mlp.c_proj.weight"], WT[k2w], d_hf, d_h,
+                               dict(dact_src=S["hf"], dact=lib.ACT_QUICKGELU),
+                               dict(dact_src=S["h_m"], dact=lib.ACT_GELU, alpha=d.scale, row_scale=mask_m))
+
+            def _wgrads():             # g_m already carries scale * mask_m
+                self._wgrad(dx, S["g_m"], grads[k2w])
+                self._colsum(d_h, grads[k1b])
+                self._wgrad(d_h, S["xn2"], grads[k1w])
+
+            if self.wgrad_side:
+                with torch.cuda.stream(self._side_begin()):
+                    _wgrads()
+            if not db2_fused:
+                self._colsum(dx, grads[k2b], row_scale=mask_m, alpha=d.scale)
+            lib.gemm_dual_kcat(d_hf, WT[pre + "mlp.c_fc.weight"], d_h, WT[k1w], d_xn2)      # d_xn2 = d_hf Wfc + d_h W1
+            if not self.wgrad_side:
+                _wgrads()
+            self._join_side()          # dW2 reads dx, which the LayerNorm backward below rewrites in place
+        else:
+            self.gemm(dx, WT[pre + "mlp.c_proj.weight"], d_hf, dact_src=S["hf"], dact=lib.ACT_QUICKGELU)
+            self.gemm(d_hf, WT[pre + "mlp.c_fc.weight"], d_xn2)
+            self._adapter_bwd("MLP_Adapter", pre, dx, S["xn2"], S["h_m"], S["g_m"], W, WT, grads, d, mask_m, d.scale,
+                              d_xn2, d_xn2, db2_fused=db2_fused)
         m3, r3 = S["ln2"]
         self._ln_bwd(d_xn2, S["x2"], m3, r3, W[pre + "ln_2.weight"], dx, dx, colsum_out=colsum_for)
         return dx
@@ -445,7 +536,7 @@ class Engine:
     # ------------------------------------------------------------------ backward
     def backward(self, dfeat: torch.Tensor, W: Dict[str, torch.Tensor], WT: Dict[str, torch.Tensor],
                  grads: Dict[str, torch.Tensor], on_block_done: Optional[Callable[[int], None]] = None,
-                 grads_prezeroed: bool = False):
+                 grads_prezeroed: bool = False, bucket_ends_at: Optional[Callable[[int], bool]] = None):
         """dfeat fp32 [B, D, T].  WT: transposed weights ([K,N] contiguous) for the dgrad GEMMs.
         grads: name -> fp32 tensor (views of the flat gradient buffer), overwritten.
         on_block_done(i) is called after block i's gradients are complete (i = L for ln_post, -1 for
@@ -463,9 +554,11 @@ class Engine:
                      grads["ln_post.bias"], d.B, d.T, n)
         if on_block_done:
             on_block_done(d.L)
+        t_hi = d.L                     # blocks [i, t_hi) still owe their T_Adapter.D_fc1 weight gradient (fused out_proj)
         for i in reversed(range(d.L)):
             prev_mask_m = sv["blocks"][i - 1]["masks"][1] if i > 0 else None
             S = sv["blocks"][i]
+            self._cur_block = i
             if self.ckpt:
                 # recompute this block's activations from its saved input (same DropPath masks -> identical values)
                 self._join_side()
@@ -478,6 +571,9 @@ class Engine:
                 dx = self._block_bwd_fork(i, dx, W, WT, grads, d, S)
             else:
                 dx = self._block_bwd(i, dx, W, WT, grads, d, S, prev_mask_m)
+            if self.t_fused and (i == 0 or (bucket_ends_at is not None and bucket_ends_at(i))):
+                self._t_flush(i, t_hi, W, WT, grads, d)
+                t_hi = i
             if on_block_done:
                 on_block_done(i)
         # ln_pre backward -> dz ; temporal_embedding grad = sum over (b, token)   (vit_clip.py:443-447)
@@ -544,22 +640,13 @@ class Engine:
         d_h = self.buf("d_h", (M, r))
         self.gemm(dy, WT[k2w], d_h, dact_src=h, dact=lib.ACT_GELU, row_scale=rs, colsum_out=grads[k1b])
 
-        def _w1_grad():
-            G = self.buf("t_G", (r, D), torch.float32)
-            lib.gemm_wgrad(d_h, o, G)                                           # d_h^T o, fp32
-            Gb = self.buf("t_Gb", (r, D))
-            Gb.copy_(G)
-            Gw = self.buf("t_Gw", (r, D))
-            self.gemm(Gb, W[pre + "attn.out_proj.weight"], Gw)                          # (d_h^T o) Wo^T on the tensor cores
-            grads[k1w].copy_(Gw)
-            grads[k1w].addr_(grads[k1b], W[pre + "attn.out_proj.bias"].float())        # + db1 (x) bo
-
+        G = self.buf("t_G", (d.L, r, D), torch.float32)[self._cur_block]
         if side:
             with torch.cuda.stream(self._side_begin()):       # ordered after the d_h GEMM (and its fused db1 column sums)
-                _w1_grad()
+                lib.gemm_wgrad(d_h, o, G, accumulate=True)                      # d_h^T o, fp32 (zeroed in _prep_t_fused)
         self.gemm(d_h, W[pre + "T_Adapter.w1oT"], d_o_out)
         if not side:
-            _w1_grad()
+            lib.gemm_wgrad(d_h, o, G, accumulate=True)
 
     def _block_bwd(self, i, dx, W, WT, grads, d, S, prev_mask_m=None):
         M, D, n = d.M, d.D, d.n

@@ -51,6 +51,8 @@ SIGNATURES = {
     "aimb_gemm_nt": [_P, _L, _P, _L, C.POINTER(Epilogue), _L, _I, _I, _I, _I, _P],
     "aimb_gemm_strided": [_P, _L, _L, _P, _L, _L, C.POINTER(Epilogue), _L, _I, _I, _I, _P],
     "aimb_adapter_fused": [_P, _L, _P, _P, C.POINTER(Epilogue), C.POINTER(Epilogue), _L, _I, _I, _I, _P],
+    "aimb_gemm_dual": [_I, _P, _L, _P, _L, _P, _L, _P, _L, C.POINTER(Epilogue), C.POINTER(Epilogue), _P, _P, _I, _F, _L, _I, _I,
+                       _I, _I, _I, _P],
     "aimb_gemm_wgrad": [_P, _L, _P, _L, _P, _L, _I, _I, _F, _I, _I, _I, _P],
     "aimb_colsum": [_P, _L, _P, _I, _F, _P, _L, _I, _I, _I, _P],
     "aimb_transpose": [_P, _P, _I, _I, _I, _P],
@@ -244,6 +246,44 @@ def adapter_fused(a, w1, w2, hidden_out, out, epi1: dict, epi2: dict):
     _count()
     _chk(load().aimb_adapter_fused(_ptr(a), a.stride(0), _ptr(w1), _ptr(w2), C.byref(e1), C.byref(e2), M, D, R, dt_code(a),
                                    _stream()), f"adapter_fused[{M}x{D}x{R}]")
+    return out
+
+
+def dual_supported(a, n1: int, n2: int, k2: int = 0) -> bool:
+    """shapes the paired tcgen05 GEMM (aimb_gemm_dual) tiles; anything else takes the separate gemm_nt calls"""
+    M, K = a.shape
+    if a.dtype != torch.bfloat16 or M < 128 or K % 64 or a.stride(1) != 1 or a.stride(0) % 8:
+        return False
+    if k2:      # KCAT: one [M, n1] output over K + k2
+        return k2 % 64 == 0 and (n1 % 192 == 0 or n1 % 256 == 0) and n1 % 16 == 0
+    return n1 % 256 == 0 and n2 in (192, 256)
+
+
+def gemm_dual_ncat(a, w1, w2, out1, out2, epi1: dict, epi2: dict):
+    """[out1 | out2] = [epi1(a @ w1^T) | epi2(a @ w2^T)] in one launch (same left operand)."""
+    M, K = a.shape
+    N1, N2 = w1.shape[0], w2.shape[0]
+    assert w1.shape[1] == K and w2.shape[1] == K and out1.shape == (M, N1) and out2.shape == (M, N2)
+    e1 = make_epilogue(out1, ldo=out1.stride(0), **epi1)
+    e2 = make_epilogue(out2, ldo=out2.stride(0), **epi2)
+    _count()
+    _chk(load().aimb_gemm_dual(0, _ptr(a), a.stride(0), _ptr(w1), w1.stride(0), None, 0, _ptr(w2), w2.stride(0), C.byref(e1),
+                               C.byref(e2), None, None, 0, 1.0, M, N1, N2, K, 0, dt_code(a), _stream()),
+         f"gemm_dual_ncat[{M}x({N1}+{N2})x{K}]")
+
+
+def gemm_dual_kcat(a1, w1, a2, w2, out, bias2=None, bias2_row_scale=None, bias2_scale=1.0, **epi):
+    """out = epilogue(a1 @ w1^T + a2 @ w2^T + bias2 * bias2_scale * bias2_row_scale[m % len]) in one launch."""
+    M, K1 = a1.shape
+    K2 = a2.shape[1]
+    N = w1.shape[0]
+    assert w1.shape == (N, K1) and w2.shape == (N, K2) and a2.shape[0] == M and out.shape == (M, N)
+    e = make_epilogue(out, ldo=out.stride(0), **epi)
+    rs = bias2_row_scale
+    _count()
+    _chk(load().aimb_gemm_dual(1, _ptr(a1), a1.stride(0), _ptr(w1), w1.stride(0), _ptr(a2), a2.stride(0), _ptr(w2), w2.stride(0),
+                               C.byref(e), None, _ptr(bias2), _ptr(rs), rs.numel() if rs is not None else 0, bias2_scale, M, N, 0,
+                               K1, K2, dt_code(a1), _stream()), f"gemm_dual_kcat[{M}x{N}x({K1}+{K2})]")
     return out
 
 

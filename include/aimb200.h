@@ -141,6 +141,22 @@ int aimb_gemm_wgrad(const void* dY, int64_t ldy, const void* X, int64_t ldx, flo
  * caller then issues the two aimb_gemm_nt calls this kernel fuses). */
 int aimb_adapter_fused(const void* A, int64_t lda, const void* W1, const void* W2, const aimb_epilogue_t* epi1,
                        const aimb_epilogue_t* epi2, int64_t M, int32_t D, int32_t R, int32_t dtype, void* stream);
+/* Two nn.Linear of one block in ONE tcgen05 launch (bf16 only).  The MLP adapter reads the same ln_2(x) as mlp.c_fc and
+ * adds into the same sum as mlp.c_proj (vitclip_aim.py:210-211 == vit_clip.py:285-286), so its two small GEMMs ride on the
+ * frozen ones, forward and backward:
+ *   AIMB_DUAL_NCAT  [C1 | C2] = [epi1(A1 W1^T) | epi2(A1 W2^T)]    A1 [M,K1], W1 [N1,K1], W2 [N2,K1]; A2 / K2 ignored;
+ *                   each epilogue has its own outputs, leading dimension, activation (c_fc | D_fc1;  d_hf | d_h)
+ *   AIMB_DUAL_KCAT  C = epi1(A1 W1^T + A2 W2^T  [+ bias2[n] * bias2_scale * bias2_row_scale[m % bias2_row_mod]])
+ *                   A1 [M,K1], W1 [N1,K1], A2 [M,K2], W2 [N1,K2]; epi2 / N2 ignored (c_proj + D_fc2;  c_fc^T + D_fc1^T)
+ * No colsum_out / out_f32.  Returns AIMB_ERR_UNSUPPORTED for shapes outside N1 % 256 == 0, N2 in {192, 256} (NCAT) or
+ * N1 % 192 == 0 / N1 % 256 == 0 (KCAT), K % 64 == 0, M >= 128, 32-byte aligned outputs with ldo % 16 == 0: the caller then
+ * issues the separate aimb_gemm_nt calls. */
+#define AIMB_DUAL_NCAT 0
+#define AIMB_DUAL_KCAT 1
+int aimb_gemm_dual(int32_t mode, const void* A1, int64_t lda1, const void* W1, int64_t ldw1, const void* A2, int64_t lda2,
+                   const void* W2, int64_t ldw2, const aimb_epilogue_t* epi1, const aimb_epilogue_t* epi2, const void* bias2,
+                   const float* bias2_row_scale, int32_t bias2_row_mod, float bias2_scale, int64_t M, int32_t N1, int32_t N2,
+                   int32_t K1, int32_t K2, int32_t dtype, void* stream);
 /* Bias gradient: out[c] (+)= alpha * sum_r x[r, c] * (row_scale ? row_scale[r % row_mod] : 1)  (fp32 out). */
 int aimb_colsum(const void* x, int64_t ld, const float* row_scale, int32_t row_mod, float alpha, float* out,
                 int64_t R, int32_t C, int32_t accumulate, int32_t dtype, void* stream);

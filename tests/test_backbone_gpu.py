@@ -101,6 +101,40 @@ def test_vitb16_8x224_logits_vs_golden_and_oracle(mode, block):
     assert O.normalised_max_err(lo, ref) < 5e-6
 
 
+@pytest.mark.parametrize("env", [dict(AIMB200_FUSE_T_OUTPROJ="1"), dict(AIMB200_FUSE_T_OUTPROJ="0"), dict(AIMB200_PAIR_MLP="0"),
+                                 dict(AIMB200_FUSE_T_OUTPROJ="1", AIMB200_WGRAD_STREAM="0")])
+def test_vitb16_launch_fusions_vs_golden(env, monkeypatch):
+    """Every launch-count variant of the block (temporal out_proj folded into T_Adapter.D_fc1 with batched per-step weight
+    products; MLP-adapter GEMMs riding on c_fc / c_proj as N- / K-concatenated segments; side streams on / off) gives the
+    reference's logits and all 147 gradients within the bf16 gates."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    gold = np.load(os.path.join(G, "vitb16_8x224_aim.npz"))
+    cfg = O.OracleCfg(block="aim")
+    m = _build(cfg, "bf16")
+    x = O.fixture_clip(cfg, 1)
+    hw, hb = O.fixture_head(cfg, 400)
+    lg, loss, grads = _cuda_logits_and_grads(m, cfg, x, hw, hb, torch.tensor(gold["labels"]))
+    eng = m._engine
+    if "AIMB200_FUSE_T_OUTPROJ" in env:
+        assert eng.t_fused == (env["AIMB200_FUSE_T_OUTPROJ"] == "1")
+    assert eng.pair_mlp == (env.get("AIMB200_PAIR_MLP", "1") == "1")
+    ref = torch.tensor(gold["logits_f64"])
+    assert O.normalised_max_err(lg, ref) < 2e-2 and int(lg.argmax()) == int(ref.argmax())
+    names = [str(s) for s in gold["grad_names"]]
+    for i, k in enumerate(names):
+        g = grads[k].double().reshape(-1)
+        e = abs(float(g.norm()) - gold["grad_norm"][i]) / max(gold["grad_norm"][i], 1e-30)
+        assert e < 6e-2, (k, e)
+    for k in gold.files:
+        if k.startswith("grad/"):
+            assert O.normalised_max_err(grads[k[5:]], torch.tensor(gold[k])) < 6e-2, k
+    m.eval()
+    with torch.no_grad():
+        lg2 = O.head_logits(m(x.cuda()), hw.cuda(), hb.cuda()).cpu()
+    assert O.normalised_max_err(lg2, lg) < 5e-3
+
+
 def test_bf16_top1_identical_batch4():
     cfg = O.OracleCfg(block="aim")
     m = _build(cfg, "bf16").eval()

@@ -191,6 +191,87 @@ def test_gemm_tc_matches_simt_bitwise_inputs():
     assert _err(o1, o2.double()) < 8e-3
 
 
+@pytest.mark.parametrize("M,D,R", [(12608, 768, 192), (1576, 768, 192), (300, 1024, 256), (128, 768, 192), (4111, 1024, 256)])
+@pytest.mark.parametrize("direction", ["fwd", "bwd"])
+def test_gemm_dual_ncat(M, D, R, direction):
+    """Paired GEMM, N-concatenation: [c_fc | MLP_Adapter.D_fc1] forward (QuickGELU | GELU * alpha * DropPath, both
+    pre-activations saved) and [d_hf | d_h] backward, against fp64 math of the two separate layers."""
+    lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(M + R)
+    bf = torch.bfloat16
+    a = torch.randn(M, D, device="cuda", generator=g).to(bf)
+    w1 = (torch.randn(4 * D, D, device="cuda", generator=g) / math.sqrt(D)).to(bf)
+    w2 = (torch.randn(R, D, device="cuda", generator=g) / math.sqrt(D)).to(bf)
+    b1 = torch.randn(4 * D, device="cuda", generator=g).to(bf)
+    b2 = torch.randn(R, device="cuda", generator=g).to(bf)
+    rs = (torch.rand(7, device="cuda", generator=g) > 0.3).float() / 0.7
+    rsm = rs.double()[torch.arange(M, device="cuda") % 7][:, None]
+    o1, p1 = torch.empty(M, 4 * D, device="cuda", dtype=bf), torch.empty(M, 4 * D, device="cuda", dtype=bf)
+    o2, p2 = torch.empty(M, R, device="cuda", dtype=bf), torch.empty(M, R, device="cuda", dtype=bf)
+    assert lib.dual_supported(a, 4 * D, R)
+    acc1, acc2 = a.double() @ w1.double().T, a.double() @ w2.double().T
+    qg = lambda u: u * torch.sigmoid(1.702 * u)
+    if direction == "fwd":
+        lib.gemm_dual_ncat(a, w1, w2, o1, o2, dict(bias=b1, act=lib.ACT_QUICKGELU, out_pre=p1),
+                           dict(bias=b2, act=lib.ACT_GELU, out_pre=p2, row_scale=rs, alpha=0.5))
+        torch.cuda.synchronize()
+        h1, h2 = acc1 + b1.double(), acc2 + b2.double()
+        assert _err(p1, h1) < 8e-3 and _err(p2, h2) < 8e-3
+        assert _err(o1, qg(h1.to(bf).double())) < 8e-3
+        assert _err(o2, F.gelu(h2.to(bf).double()) * 0.5 * rsm) < 8e-3
+        # inference: no saved pre-activations
+        o1b, o2b = torch.empty_like(o1), torch.empty_like(o2)
+        lib.gemm_dual_ncat(a, w1, w2, o1b, o2b, dict(bias=b1, act=lib.ACT_QUICKGELU), dict(bias=b2, act=lib.ACT_GELU))
+        torch.cuda.synchronize()
+        assert _err(o1b, qg(h1)) < 8e-3 and _err(o2b, F.gelu(h2)) < 8e-3
+    else:
+        s1 = torch.randn(M, 4 * D, device="cuda", generator=g).to(bf)
+        s2 = torch.randn(M, R, device="cuda", generator=g).to(bf)
+        lib.gemm_dual_ncat(a, w1, w2, o1, o2, dict(dact_src=s1, dact=lib.ACT_QUICKGELU),
+                           dict(dact_src=s2, dact=lib.ACT_GELU, row_scale=rs, alpha=0.5))
+        torch.cuda.synchronize()
+        u1 = s1.double().requires_grad_(True)
+        qg(u1).sum().backward()
+        u2 = s2.double().requires_grad_(True)
+        F.gelu(u2).sum().backward()
+        assert _err(o1, acc1 * u1.grad) < 8e-3
+        assert _err(o2, acc2 * u2.grad * 0.5 * rsm) < 8e-3
+
+
+@pytest.mark.parametrize("M,N,K1,K2", [(12608, 768, 3072, 192), (1576, 768, 3072, 192), (300, 1024, 4096, 256), (128, 768, 192, 64),
+                                       (4111, 1024, 1024, 256), (12608, 768, 768, 192)])
+@pytest.mark.parametrize("case", ["plain", "bias_res_bias2", "bias_res_bias2_rowscale"])
+def test_gemm_dual_kcat(M, N, K1, K2, case):
+    """Paired GEMM, K-concatenation: one accumulator over two operand pairs (c_proj + MLP_Adapter.D_fc2 forward with the
+    adapter's DropPath-scaled bias; c_fc^T + D_fc1^T backward)."""
+    lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(M + K2)
+    bf = torch.bfloat16
+    a1 = torch.randn(M, K1, device="cuda", generator=g).to(bf)
+    a2 = torch.randn(M, K2, device="cuda", generator=g).to(bf)
+    w1 = (torch.randn(N, K1, device="cuda", generator=g) / math.sqrt(K1)).to(bf)
+    w2 = (torch.randn(N, K2, device="cuda", generator=g) / math.sqrt(K2)).to(bf)
+    bias = torch.randn(N, device="cuda", generator=g).to(bf)
+    bias2 = torch.randn(N, device="cuda", generator=g).to(bf)
+    r1 = torch.randn(M, N, device="cuda", generator=g).to(bf)
+    rs = (torch.rand(7, device="cuda", generator=g) > 0.3).float() / 0.7
+    rsm = rs.double()[torch.arange(M, device="cuda") % 7][:, None]
+    out = torch.empty(M, N, device="cuda", dtype=bf)
+    assert lib.dual_supported(a1, N, 0, K2)
+    acc = a1.double() @ w1.double().T + a2.double() @ w2.double().T
+    if case == "plain":
+        lib.gemm_dual_kcat(a1, w1, a2, w2, out)
+        ref = acc
+    elif case == "bias_res_bias2":
+        lib.gemm_dual_kcat(a1, w1, a2, w2, out, bias2=bias2, bias2_scale=0.5, bias=bias, res1=r1)
+        ref = acc + bias.double() + 0.5 * bias2.double() + r1.double()
+    else:
+        lib.gemm_dual_kcat(a1, w1, a2, w2, out, bias2=bias2, bias2_row_scale=rs, bias2_scale=0.5, bias=bias, res1=r1)
+        ref = acc + bias.double() + 0.5 * rsm * bias2.double() + r1.double()
+    torch.cuda.synchronize()
+    assert _err(out, ref) < 8e-3
+
+
 @pytest.mark.parametrize("M,D,R", [(12608, 768, 192), (1576, 768, 192), (300, 1024, 256), (136, 256, 64), (128, 768, 192)])
 def test_adapter_fused_forward_and_backward(M, D, R):
     """One-kernel adapter (GEMM1 -> smem hidden -> GEMM2) against fp64 math and against the two-GEMM path."""
