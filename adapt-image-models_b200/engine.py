@@ -77,6 +77,11 @@ class Engine:
         # than the removed GEMMs gave (675 vs 709 clips/s); batched: 731 -> 753 clips/s.
         self.fuse_t_outproj = os.environ.get("AIMB200_FUSE_T_OUTPROJ", "1") == "1"
         self.t_fused = False
+        # S_Adapter (skip connection, vitclip_aim.py:208): x2 = x1 + a + fc2(gelu(fc1(a))), a = out_proj(o_s).  With the same
+        # product, h = o_s (W1 Wo)^T + b1o and x2 = x1 + [o_s | g] [Wo | W2]^T + bo + b2: out_proj and D_fc2 share ONE
+        # K-concatenated launch and a is never materialised; backward: d_o = [dx2 | d_h] [Wo^T | W1o^T]^T the same way.
+        self.fuse_s_outproj = os.environ.get("AIMB200_FUSE_S_OUTPROJ", "1") == "1"
+        self.s_fused = False
         self.fuse_adapters = os.environ.get("AIMB200_FUSE_ADAPTERS", "0") == "1"   # opt-in: measured on par at M = 12608
         # MLP_Adapter shares its input with mlp.c_fc and its sum with mlp.c_proj (vitclip_aim.py:210-211): its two GEMMs ride
         # on the frozen ones as N- / K-concatenated segments of ONE launch each, forward and backward (-4 launches per block)
@@ -206,8 +211,13 @@ class Engine:
             sv["z"], sv["ln_pre"] = z, (mean0, rstd0)
         self.t_fused = (self.fuse_t_outproj and d.block == "aim" and d.num_tadapter == 1 and WT is not None
                         and self.dtype == torch.bfloat16)
+        self.s_fused = (self.fuse_s_outproj and d.block == "aim" and WT is not None and self.dtype == torch.bfloat16
+                        and self.gemm_impl == lib.IMPL_AUTO and not self.fuse_adapters
+                        and lib.dual_supported(xcur, D, 0, r))
         if self.t_fused:
-            self._prep_t_fused(W, WT, d, training)
+            self._prep_fused("T_Adapter", W, WT, d, training)
+        if self.s_fused:
+            self._prep_fused("S_Adapter", W, WT, d, training)
         for i in range(d.L):
             masks = drop_masks[i] if (drop_masks is not None) else (None, None)
             if d.block == "fork":
@@ -245,30 +255,30 @@ class Engine:
             self._t_stack_key, self._t_stack = key, (Wo, WoT, bo, bo.float())
         return self._t_stack
 
-    def _prep_t_fused(self, W, WT, d, training):
+    def _prep_fused(self, ad, W, WT, d, training):
         """Per step (D_fc1 is trainable), for ALL blocks in three batched launches: W1o = W1 Wo [r, D], b1o = W1 bo + b1,
         and W1o^T for the dgrad.  These are weight x weight products (0.23 GFLOP per block), not part of the activation
         path: one strided-batched library GEMM each instead of 36 tile-kernel launches."""
         r, D, L = d.r, d.D, d.L
         Wo, WoT, bo, _ = self._t_frozen_stacks(W, WT, d)
-        W1 = self._per_block(W, "T_Adapter.D_fc1.weight", d)                    # [L, r, D]
-        b1 = self._per_block(W, "T_Adapter.D_fc1.bias", d)                      # [L, r]
-        w1o = self.buf("t_w1o", (L, r, D))
+        W1 = self._per_block(W, ad + ".D_fc1.weight", d)                        # [L, r, D]
+        b1 = self._per_block(W, ad + ".D_fc1.bias", d)                          # [L, r]
+        w1o = self.buf(ad + "_w1o", (L, r, D))
         torch.bmm(W1, Wo, out=w1o)                                              # sum_j W1[r, j] Wo[j, i]
-        b1o = self.buf("t_b1o", (L, 1, r))
+        b1o = self.buf(ad + "_b1o", (L, 1, r))
         torch.baddbmm(b1.unsqueeze(1), bo.unsqueeze(1), W1.transpose(1, 2), out=b1o)
         if training:
-            w1oT = self.buf("t_w1oT", (L, D, r))                                # the N x K operand of d_o = d_h W1o
+            w1oT = self.buf(ad + "_w1oT", (L, D, r))                            # the N x K operand of d_o = d_h W1o
             w1oT.copy_(w1o.transpose(1, 2))
-            self.buf("t_G", (L, r, D), torch.float32).zero_()                   # d_h^T o of every block, see _t_flush
+            self.buf(ad + "_G", (L, r, D), torch.float32).zero_()               # d_h^T o of every block, see _flush_fused
         for i in range(L):
             pre = f"transformer.resblocks.{i}."
-            W[pre + "T_Adapter.w1o"], W[pre + "T_Adapter.b1o"] = w1o[i], b1o[i].view(r)
+            W[pre + ad + ".w1o"], W[pre + ad + ".b1o"] = w1o[i], b1o[i].view(r)
             if training:
-                W[pre + "T_Adapter.w1oT"] = w1oT[i]
+                W[pre + ad + ".w1oT"] = w1oT[i]
 
-    def _t_flush(self, lo, hi, W, WT, grads, d):
-        """T_Adapter.D_fc1 weight gradients of blocks lo..hi-1 from the accumulated G = d_h^T o:
+    def _flush_fused(self, ad, lo, hi, W, WT, grads, d):
+        """<ad>.D_fc1 weight gradients of blocks lo..hi-1 from the accumulated G = d_h^T o:
         dW1 = G Wo^T + db1 (x) bo   (a = o Wo^T + bo was never materialised).  One batched launch chain per gradient
         bucket, issued when the bucket's last block has finished its backward."""
         if hi <= lo:
@@ -276,13 +286,13 @@ class Engine:
         r, D, L = d.r, d.D, d.L
         _, WoT, _, bo32 = self._t_frozen_stacks(W, WT, d)
         self._join_side()                                                       # the wgrads that fill G run on the side stream
-        G = self.buf("t_G", (L, r, D), torch.float32)[lo:hi]
-        Gb = self.buf("t_Gb", (L, r, D))[lo:hi]
+        G = self.buf(ad + "_G", (L, r, D), torch.float32)[lo:hi]
+        Gb = self.buf(ad + "_Gb", (L, r, D))[lo:hi]
         Gb.copy_(G)
-        Gw = self.buf("t_Gw", (L, r, D))[lo:hi]
+        Gw = self.buf(ad + "_Gw", (L, r, D))[lo:hi]
         torch.bmm(Gb, WoT[lo:hi], out=Gw)                                       # sum_j G[r, j] Wo[j', j]
-        dW1 = self._per_block(grads, "T_Adapter.D_fc1.weight", d)[lo:hi]
-        db1 = self._per_block(grads, "T_Adapter.D_fc1.bias", d)[lo:hi]
+        dW1 = self._per_block(grads, ad + ".D_fc1.weight", d)[lo:hi]
+        db1 = self._per_block(grads, ad + ".D_fc1.bias", d)[lo:hi]
         dW1.copy_(Gw)
         dW1.baddbmm_(db1.unsqueeze(2), bo32[lo:hi].unsqueeze(1))
 
@@ -423,10 +433,18 @@ class Engine:
         o_s = self.buf("o_s", (M, D), key=bk)
         lse = self.buf("lse_s", (d.BT, d.heads, n), f32, bk) if training else None
         lib.attn_spatial_fwd(qkv_s, o_s, lse, d.BT, n, d.heads, impl=self.attn_impl)
-        a_s = self.buf("a_s", (M, D), key=bk)
-        self.gemm(o_s, Wo, a_s, bias=bo)
         x2 = self.buf("x2", (M, D), key=bk)
-        h_s, g_s = self._adapter_fwd("S_Adapter", pre, a_s, W, d, bk, training, None, 1.0, x1, a_s, x2)
+        if self.s_fused:
+            a_s = None
+            h_s = self.buf("S_Adapter_h", (M, r), key=bk) if training else None
+            g_s = self.buf("S_Adapter_g", (M, r), key=bk)
+            self.gemm(o_s, W[pre + "S_Adapter.w1o"], g_s, bias=W[pre + "S_Adapter.b1o"], act=lib.ACT_GELU, out_pre=h_s)
+            lib.gemm_dual_kcat(o_s, Wo, g_s, W[pre + "S_Adapter.D_fc2.weight"], x2, bias2=W[pre + "S_Adapter.D_fc2.bias"],
+                               bias=bo, res1=x1)                       # x2 = x1 + (o_s Wo^T + bo) + (g W2^T + b2)
+        else:
+            a_s = self.buf("a_s", (M, D), key=bk)
+            self.gemm(o_s, Wo, a_s, bias=bo)
+            h_s, g_s = self._adapter_fwd("S_Adapter", pre, a_s, W, d, bk, training, None, 1.0, x1, a_s, x2)
         xo, mlp_saved = self._mlp_fwd(i, x2, W, d, training, mask_m, bk)
         if training:
             S.update(x=x, ln1t=(m1, r1), qkv_t=qkv_t, o_t=o_t, a_t=a_t, h_t=h_t, g_t=g_t, x1=x1, ln1s=(m2, r2),
@@ -571,8 +589,11 @@ class Engine:
                 dx = self._block_bwd_fork(i, dx, W, WT, grads, d, S)
             else:
                 dx = self._block_bwd(i, dx, W, WT, grads, d, S, prev_mask_m)
-            if self.t_fused and (i == 0 or (bucket_ends_at is not None and bucket_ends_at(i))):
-                self._t_flush(i, t_hi, W, WT, grads, d)
+            if (self.t_fused or self.s_fused) and (i == 0 or (bucket_ends_at is not None and bucket_ends_at(i))):
+                if self.t_fused:
+                    self._flush_fused("T_Adapter", i, t_hi, W, WT, grads, d)
+                if self.s_fused:
+                    self._flush_fused("S_Adapter", i, t_hi, W, WT, grads, d)
                 t_hi = i
             if on_block_done:
                 on_block_done(i)
@@ -640,11 +661,36 @@ class Engine:
         d_h = self.buf("d_h", (M, r))
         self.gemm(dy, WT[k2w], d_h, dact_src=h, dact=lib.ACT_GELU, row_scale=rs, colsum_out=grads[k1b])
 
-        G = self.buf("t_G", (d.L, r, D), torch.float32)[self._cur_block]
+        G = self.buf("T_Adapter_G", (d.L, r, D), torch.float32)[self._cur_block]
         if side:
             with torch.cuda.stream(self._side_begin()):       # ordered after the d_h GEMM (and its fused db1 column sums)
-                lib.gemm_wgrad(d_h, o, G, accumulate=True)                      # d_h^T o, fp32 (zeroed in _prep_t_fused)
+                lib.gemm_wgrad(d_h, o, G, accumulate=True)                      # d_h^T o, fp32 (zeroed in _prep_fused)
         self.gemm(d_h, W[pre + "T_Adapter.w1oT"], d_o_out)
+        if not side:
+            lib.gemm_wgrad(d_h, o, G, accumulate=True)
+
+    def _s_fused_bwd(self, pre, dy, S, W, WT, grads, d, d_o_out):
+        """Backward of x2 = x1 + [o | g] [Wo | W2]^T + bo + b2, g = gelu(o W1o^T + b1o), dy = d(x2):
+        d_h = (dy W2) . gelu'(h) (+ db1 column sums);  d_o = [dy | d_h] [Wo^T | W1o^T]^T in one K-concatenated launch;
+        dW2 = dy^T g and G = d_h^T o on the side stream (dW1 = G Wo^T + db1 (x) bo in _flush_fused).  db2 = colsum(dy) was
+        fused into the LayerNorm backward that produced dy.  The caller joins the side stream before dy is rewritten."""
+        M, r, D = dy.shape[0], d.r, d.D
+        k1b, k2w = pre + "S_Adapter.D_fc1.bias", pre + "S_Adapter.D_fc2.weight"
+        h, g, o = S["h_s"], S["g_s"], S["o_s"]
+        self._join_side()              # the previous adapter's weight gradients still read the shared d_h scratch
+        side = self.wgrad_side
+        if side:
+            with torch.cuda.stream(self._side_begin()):
+                self._wgrad(dy, g, grads[k2w])
+        else:
+            self._wgrad(dy, g, grads[k2w])
+        d_h = self.buf("d_h", (M, r))
+        self.gemm(dy, WT[k2w], d_h, dact_src=h, dact=lib.ACT_GELU, colsum_out=grads[k1b])
+        G = self.buf("S_Adapter_G", (d.L, r, D), torch.float32)[self._cur_block]
+        if side:
+            with torch.cuda.stream(self._side_begin()):
+                lib.gemm_wgrad(d_h, o, G, accumulate=True)
+        lib.gemm_dual_kcat(dy, WT[pre + "attn.out_proj.weight"], d_h, W[pre + "S_Adapter.w1oT"], d_o_out)
         if not side:
             lib.gemm_wgrad(d_h, o, G, accumulate=True)
 
@@ -658,11 +704,14 @@ class Engine:
         dx2 = self._mlp_bwd(i, dx, W, WT, grads, d, S, mask_m, db2_fused=(i < d.L - 1),
                             colsum_for=grads[pre + "S_Adapter.D_fc2.bias"])
         # ---------------- spatial: x2 = x1 + a_s + S_Adapter_noskip(a_s)
-        d_as = self.buf("d_a", (M, D))
-        self._adapter_bwd("S_Adapter", pre, dx2, S["a_s"], S["h_s"], S["g_s"], W, WT, grads, d, None, 1.0, d_as, dx2,
-                          db2_fused=True, lazy_join=True)
         d_os = self.buf("d_o", (M, D))
-        self.gemm(d_as, WT[pre + "attn.out_proj.weight"], d_os)
+        if self.s_fused:
+            self._s_fused_bwd(pre, dx2, S, W, WT, grads, d, d_os)
+        else:
+            d_as = self.buf("d_a", (M, D))
+            self._adapter_bwd("S_Adapter", pre, dx2, S["a_s"], S["h_s"], S["g_s"], W, WT, grads, d, None, 1.0, d_as, dx2,
+                              db2_fused=True, lazy_join=True)
+            self.gemm(d_as, WT[pre + "attn.out_proj.weight"], d_os)
         d_qkv = self.buf("d_qkv", (M, 3 * D))
         lib.attn_spatial_bwd(S["qkv_s"], S["o_s"], d_os, S["lse"], d_qkv, d.BT, n, d.heads, impl=self.attn_impl)
         d_xn1 = self.buf("d_xn", (M, D))

@@ -101,8 +101,9 @@ def test_vitb16_8x224_logits_vs_golden_and_oracle(mode, block):
     assert O.normalised_max_err(lo, ref) < 5e-6
 
 
-@pytest.mark.parametrize("env", [dict(AIMB200_FUSE_T_OUTPROJ="1"), dict(AIMB200_FUSE_T_OUTPROJ="0"), dict(AIMB200_PAIR_MLP="0"),
-                                 dict(AIMB200_FUSE_T_OUTPROJ="1", AIMB200_WGRAD_STREAM="0")])
+@pytest.mark.parametrize("env", [dict(), dict(AIMB200_FUSE_T_OUTPROJ="0"), dict(AIMB200_PAIR_MLP="0"), dict(AIMB200_FUSE_S_OUTPROJ="0"),
+                                 dict(AIMB200_FUSE_T_OUTPROJ="0", AIMB200_FUSE_S_OUTPROJ="0", AIMB200_PAIR_MLP="0"),
+                                 dict(AIMB200_WGRAD_STREAM="0")])
 def test_vitb16_launch_fusions_vs_golden(env, monkeypatch):
     """Every launch-count variant of the block (temporal out_proj folded into T_Adapter.D_fc1 with batched per-step weight
     products; MLP-adapter GEMMs riding on c_fc / c_proj as N- / K-concatenated segments; side streams on / off) gives the
@@ -116,8 +117,8 @@ def test_vitb16_launch_fusions_vs_golden(env, monkeypatch):
     hw, hb = O.fixture_head(cfg, 400)
     lg, loss, grads = _cuda_logits_and_grads(m, cfg, x, hw, hb, torch.tensor(gold["labels"]))
     eng = m._engine
-    if "AIMB200_FUSE_T_OUTPROJ" in env:
-        assert eng.t_fused == (env["AIMB200_FUSE_T_OUTPROJ"] == "1")
+    assert eng.t_fused == (env.get("AIMB200_FUSE_T_OUTPROJ", "1") == "1")
+    assert eng.s_fused == (env.get("AIMB200_FUSE_S_OUTPROJ", "1") == "1")
     assert eng.pair_mlp == (env.get("AIMB200_PAIR_MLP", "1") == "1")
     ref = torch.tensor(gold["logits_f64"])
     assert O.normalised_max_err(lg, ref) < 2e-2 and int(lg.argmax()) == int(ref.argmax())
