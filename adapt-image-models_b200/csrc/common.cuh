@@ -142,6 +142,9 @@ struct EpiParams {
     int64_t ldo;          // leading dim of out/out_pre/res1/res2/dact_src (elements)
     float* colsum_out;    // [N] fp32: column sums of the stored values (atomically accumulated; zeroed by the host side)
     int32_t colsum_accumulate;   // host side only: skip that zeroing
+    const float* ln_mean;        // folded LayerNorm (see aimb200.h): acc = ln_rstd[m] * (acc - ln_mean[m] * ln_wsum[n])
+    const float* ln_rstd;
+    const float* ln_wsum;
 };
 
 inline EpiParams make_epi(const aimb_epilogue_t* e, int64_t ld_default) {
@@ -153,6 +156,8 @@ inline EpiParams make_epi(const aimb_epilogue_t* e, int64_t ld_default) {
     p.ldo = e->ldo > 0 ? e->ldo : ld_default;
     p.colsum_out = e->colsum_out;
     p.colsum_accumulate = e->colsum_accumulate;
+    const bool ln = e->ln_mean && e->ln_rstd && e->ln_wsum;
+    p.ln_mean = ln ? e->ln_mean : nullptr; p.ln_rstd = ln ? e->ln_rstd : nullptr; p.ln_wsum = ln ? e->ln_wsum : nullptr;
     return p;
 }
 

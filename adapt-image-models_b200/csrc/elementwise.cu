@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(128) layernorm_fwd_kernel(const T* __restrict_
     r.load(x + row * D, D, lane);
     float mean, rstd;
     ln_row<T>(r, D, lane, eps, mean, rstd);
-    ln_apply_store<T>(r, gamma, beta, y + row * D, D, lane, mean, rstd);
+    if (y) ln_apply_store<T>(r, gamma, beta, y + row * D, D, lane, mean, rstd);     // y == nullptr: statistics only
     if (lane == 0) {
         if (mean_o) mean_o[row] = mean;
         if (rstd_o) rstd_o[row] = rstd;
@@ -580,7 +580,7 @@ using namespace aimb;
 
 extern "C" int aimb_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd,
                                   int64_t rows, int32_t D, float eps, int32_t dtype, void* stream) {
-    if (!x || !gamma || !beta || !y || rows < 0 || !vec_ok(D, dtype)) return AIMB_ERR_ARG;
+    if (!x || !gamma || !beta || (!y && !(mean && rstd)) || rows < 0 || !vec_ok(D, dtype)) return AIMB_ERR_ARG;
     if (rows == 0) return AIMB_OK;
     cudaStream_t s = (cudaStream_t)stream;
     unsigned grid = (unsigned)((rows + 3) / 4);

@@ -10,6 +10,7 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& e, int64_t m, in
     float rs = 1.f;
     if (e.row_scale) rs = e.row_scale[m % e.row_mod];
     float v = acc;
+    if (e.ln_mean) v = (v - e.ln_mean[m] * e.ln_wsum[n]) * e.ln_rstd[m];
     if (e.bias) v += ldf<T>((const T*)e.bias + n) * (e.bias_rowscaled ? rs : 1.f);
     int64_t off = m * e.ldo + n;
     if (e.out_pre) { stf<T>((T*)e.out_pre + off, v); v = roundT<T>(v); }

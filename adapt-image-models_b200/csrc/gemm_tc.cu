@@ -127,6 +127,11 @@ __device__ __forceinline__ void epilogue_vec8(const EpiParams& e, int64_t m, int
     if (e.row_scale) rs = e.row_scale[m % e.row_mod];
     const int64_t off = m * e.ldo + n0;
     float t[8];
+    if (e.ln_mean) {       // folded LayerNorm (generic kernel only; the row-layout kernel has its own variant 8)
+        const float mu = e.ln_mean[m], rsd = e.ln_rstd[m];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (v[j] - mu * e.ln_wsum[n0 + j]) * rsd;
+    }
     if (e.bias) {
         const float bs = e.bias_rowscaled ? rs : 1.f;
 #pragma unroll
@@ -267,10 +272,12 @@ template <> struct EpiVariant<4> { static constexpr int ACT = AIMB_ACT_NONE, DAC
 template <> struct EpiVariant<5> { static constexpr int ACT = AIMB_ACT_NONE, DACT = AIMB_ACT_QUICKGELU, EXT = 1; };
 template <> struct EpiVariant<6> { static constexpr int ACT = AIMB_ACT_NONE, DACT = AIMB_ACT_GELU, EXT = 1; };
 template <> struct EpiVariant<7> { static constexpr int ACT = -1, DACT = -1, EXT = 7; };
+template <> struct EpiVariant<8> { static constexpr int ACT = AIMB_ACT_NONE, DACT = AIMB_ACT_NONE, EXT = 0; };   // 0 + folded LayerNorm (QKV)
 
 static int pick_variant(const EpiParams& e) {
     const int ext = (e.dact_src ? 1 : 0) | (e.res1 ? 2 : 0) | (e.res2 ? 4 : 0);
     const int act = e.act, dact = e.dact_src ? e.dact : AIMB_ACT_NONE;
+    if (e.ln_mean) return (ext == 0 && act == AIMB_ACT_NONE && !e.out_pre) ? 8 : 7;
     if (ext == 0 && act == AIMB_ACT_NONE) return 0;
     if (ext == 0 && act == AIMB_ACT_QUICKGELU) return 1;
     if (ext == 0 && act == AIMB_ACT_GELU) return 2;
@@ -440,7 +447,8 @@ template <int V, bool DIRECT = false> struct EpiBufs {
     static constexpr bool PRE = (V == 1 || V == 2);
     static constexpr int NEXT = ((EXT & 1) ? 1 : 0) + ((EXT & 2) ? 1 : 0) + ((EXT & 4) ? 1 : 0);
     static constexpr int NBUF = DIRECT ? NEXT : (NEXT > 0 ? NEXT : 1) + (PRE ? 1 : 0);   // slab path: out aliases the first operand buffer
-    static constexpr int WARP_BYTES = NBUF * 4096 + 256;                     // + 64 fp32 bias values
+    static constexpr int BIAS_BYTES = (V == 8) ? 512 : 256;                  // 64 fp32 bias values (+ 64 LayerNorm weight sums)
+    static constexpr int WARP_BYTES = NBUF * 4096 + BIAS_BYTES;
 };
 template <int BN, int V, bool DIRECT = false> struct TileCfg4 {
     static constexpr int EPI_W = 4 * (BN / 64);
@@ -617,7 +625,7 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         constexpr bool TMA_ST = (EXT == 0) && !DIRECT;                   // plain / activation variants: the slab leaves through TMA
         const uint32_t buf0 = ptx::smem_u32(epi_smem + ew * (EB::NBUF * 4096));   // out (in place over dact_src / res1); 1 KB aligned
         const uint32_t buf1 = buf0 + 4096;                    // out_pre, or res2
-        float* sbias = reinterpret_cast<float*>(epi_smem + EPI_W * (EB::NBUF * 4096) + ew * 256);
+        float* sbias = reinterpret_cast<float*>(epi_smem + EPI_W * (EB::NBUF * 4096) + ew * EB::BIAS_BYTES);
         if (TMA_ST && lane == 0) { ptx::prefetch_tmap(&tmO); if (want_pre_k(epi, EB::PRE)) ptx::prefetch_tmap(&tmP); }
         const bf16* g0 = (EXT & 1) ? (const bf16*)epi.dact_src : (const bf16*)epi.res1;
         const bf16* g1 = (const bf16*)epi.res2;
@@ -646,6 +654,12 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
             float rs = 1.f;
             if (epi.row_scale && row < M) rs = epi.row_scale[(int)row % epi.row_mod];
+            float ln_mu = 0.f, ln_rs = 1.f;
+            if (V == 8) {          // folded LayerNorm: lane = row, so each lane needs just its own row's statistics
+                sbias[64 + lane] = epi.ln_wsum[n_base + lane];
+                sbias[96 + lane] = epi.ln_wsum[n_base + lane + 32];
+                if (row < M) { ln_mu = epi.ln_mean[row]; ln_rs = epi.ln_rstd[row]; }
+            }
             ptx::mbar_wait(&tfull_bar[as], aphase);
             ptx::tc_fence_after();
             uint32_t ra[16], rb16[16];
@@ -679,6 +693,13 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     if (epi.bias) {
                         *reinterpret_cast<float4*>(bias8) = *reinterpret_cast<const float4*>(sbias + ch * 8);
                         *reinterpret_cast<float4*>(bias8 + 4) = *reinterpret_cast<const float4*>(sbias + ch * 8 + 4);
+                    }
+                    if (V == 8) {
+                        float s8[8];
+                        *reinterpret_cast<float4*>(s8) = *reinterpret_cast<const float4*>(sbias + 64 + ch * 8);
+                        *reinterpret_cast<float4*>(s8 + 4) = *reinterpret_cast<const float4*>(sbias + 64 + ch * 8 + 4);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = fmaf(-ln_mu, s8[j], v[j]) * ln_rs;
                     }
                     const uint4 o = epi_math8<EV::ACT, EV::DACT, EXT>(epi, rs, v, bias8, xd, x1, x2, pre_pk, want_pre);
                     if (dbg == 5 && o.x != 0x12345678u) continue;
@@ -1322,6 +1343,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const EpiPara
         case 4: return launch_tc_v<BN, 4>(ta, tb, p, M, N, K, s);
         case 5: return launch_tc_v<BN, 5>(ta, tb, p, M, N, K, s);
         case 6: return launch_tc_v<BN, 6>(ta, tb, p, M, N, K, s);
+        case 8: return launch_tc_v<BN, 8>(ta, tb, p, M, N, K, s);
         default: return launch_tc_v<BN, 7>(ta, tb, p, M, N, K, s);
     }
 }
@@ -1344,6 +1366,7 @@ static bool tc4_ok(int bn, int v, bool direct) {
         case 4: return tc4_ok_v<4>(bn, direct);
         case 5: return tc4_ok_v<5>(bn, direct);
         case 6: return tc4_ok_v<6>(bn, direct);
+        case 8: return tc4_ok_v<8>(bn, direct);
     }
     return false;
 }
@@ -1355,7 +1378,7 @@ static int pick_bn(int64_t M, int N, int K, int variant = -1, bool direct = fals
     for (int i = 0; i < 4; ++i) {
         int bn = cand[i];
         if (N % bn) continue;
-        if (variant >= 0 && variant < 7 && !tc4_ok(bn, variant, direct)) continue;
+        if (variant >= 0 && variant != 7 && !tc4_ok(bn, variant, direct)) continue;
         int64_t tiles = mt * (N / bn);
         int64_t waves = (tiles + num_sms() - 1) / num_sms();
         double per_tile = kb * (double)(bn < 128 ? 128 : bn) + 1536.0;   // below N=128 the A-operand traffic dominates
@@ -1405,7 +1428,7 @@ static int launch_dual_v(const CUtensorMap& ta, const CUtensorMap& tb, const CUt
 }
 
 static bool dual_epi_ok(const EpiParams& p) {
-    return !p.colsum_out && !p.out_f32 && p.out && (p.ldo % 16 == 0) && !((uintptr_t)p.out & 31) &&
+    return !p.colsum_out && !p.out_f32 && !p.ln_mean && p.out && (p.ldo % 16 == 0) && !((uintptr_t)p.out & 31) &&
            !(p.out_pre && ((uintptr_t)p.out_pre & 31)) && !(p.dact_src && ((uintptr_t)p.dact_src & 15)) &&
            !(p.res1 && ((uintptr_t)p.res1 & 15));
 }

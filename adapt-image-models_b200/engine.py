@@ -82,6 +82,11 @@ class Engine:
         # K-concatenated launch and a is never materialised; backward: d_o = [dx2 | d_h] [Wo^T | W1o^T]^T the same way.
         self.fuse_s_outproj = os.environ.get("AIMB200_FUSE_S_OUTPROJ", "1") == "1"
         self.s_fused = False
+        # ln_1 is frozen, so LN(x) Wqkv^T + b = rstd * (x (Wqkv * gamma)^T - mean * rowsum(Wqkv * gamma)) + (b + Wqkv beta):
+        # the QKV GEMM reads the un-normalised residual stream and applies the row statistics in its epilogue; the
+        # normalised activations are never written (a statistics-only pass replaces the LayerNorm kernel)
+        self.ln_fold = os.environ.get("AIMB200_LN_FOLD", "1") == "1"
+        self._ln_fold_cache: Dict[int, tuple] = {}
         self.fuse_adapters = os.environ.get("AIMB200_FUSE_ADAPTERS", "0") == "1"   # opt-in: measured on par at M = 12608
         # MLP_Adapter shares its input with mlp.c_fc and its sum with mlp.c_proj (vitclip_aim.py:210-211): its two GEMMs ride
         # on the frozen ones as N- / K-concatenated segments of ONE launch each, forward and backward (-4 launches per block)
@@ -168,6 +173,8 @@ class Engine:
         self._bufs.clear()
         self._buf_mode.clear()
         self._mode_sig.clear()
+        self._ln_fold_cache.clear()
+        self._t_stack_key = None
         self.saved = None
 
     def gemm(self, a, w, out, **kw):
@@ -296,6 +303,32 @@ class Engine:
         dW1.copy_(Gw)
         dW1.baddbmm_(db1.unsqueeze(2), bo32[lo:hi].unsqueeze(1))
 
+    def _ln_folded(self, i, W):
+        """(W * gamma in the compute dtype, fp32 row sums of exactly those values, b + W beta) of block i's in_proj / ln_1;
+        cached while the frozen source tensors are the same objects (the backbone replaces them when a parameter changes)."""
+        pre = f"transformer.resblocks.{i}."
+        src = (W[pre + "attn.in_proj_weight"], W[pre + "attn.in_proj_bias"], W[pre + "ln_1.weight"], W[pre + "ln_1.bias"])
+        ent = self._ln_fold_cache.get(i)
+        if ent is None or any(a is not b for a, b in zip(ent[0], src)):
+            w, b, g, be = (t.float() for t in src)
+            wf = (w * g[None, :]).to(self.dtype).contiguous()
+            ent = (src, wf, wf.float().sum(1).contiguous(), (b + w @ be).to(self.dtype).contiguous())
+            self._ln_fold_cache[i] = ent
+        return ent[1], ent[2], ent[3]
+
+    def _qkv_ln(self, i, x, W, out, mean, rstd, fold, xn_key=None):
+        """out = ln_1(x) Wqkv^T + b (vit_clip.py:132-138 after :71-77); returns ln_1(x) when it was materialised."""
+        pre = f"transformer.resblocks.{i}."
+        if fold:
+            lib.layernorm_fwd(x, W[pre + "ln_1.weight"], W[pre + "ln_1.bias"], None, mean, rstd)      # statistics only
+            wf, ws, cf = self._ln_folded(i, W)
+            self.gemm(x, wf, out, bias=cf, ln_mean=mean, ln_rstd=rstd, ln_wsum=ws)
+            return None
+        xn = self.buf("xn", x.shape, key=xn_key)
+        lib.layernorm_fwd(x, W[pre + "ln_1.weight"], W[pre + "ln_1.bias"], xn, mean, rstd)
+        self.gemm(xn, W[pre + "attn.in_proj_weight"], out, bias=W[pre + "attn.in_proj_bias"])
+        return xn
+
     def _adapter_fwd(self, name, pre, a, W, d, bk, training, rs, alpha, res1, res2, out):
         """out = res1 + res2 + alpha * rs * (fc2(gelu(fc1(a))))   (rs folded into the hidden, see backward)."""
         M, r = a.shape[0], d.r
@@ -397,18 +430,19 @@ class Engine:
         Wo, bo = W[pre + "attn.out_proj.weight"], W[pre + "attn.out_proj.bias"]
         ln1w, ln1b = W[pre + "ln_1.weight"], W[pre + "ln_1.bias"]
         # ---------------- temporal adaptation (vitclip_aim.py:199-206)
-        xn = self.buf("xn", (M, D), key=bk if (training and d.num_tadapter == 2) else None)
+        fold = self.ln_fold and self.dtype == torch.bfloat16 and self.gemm_impl == lib.IMPL_AUTO and M >= 128 and D % 64 == 0
         m1, r1 = self.buf("ln1t_m", (M,), f32, bk), self.buf("ln1t_r", (M,), f32, bk)
-        lib.layernorm_fwd(x, ln1w, ln1b, xn, m1, r1)
-        qkv_in = xn
+        qkv_t = self.buf("qkv_t", (M, 3 * D), key=bk)
         if d.num_tadapter == 2:
+            xn = self.buf("xn", (M, D), key=bk if training else None)
+            lib.layernorm_fwd(x, ln1w, ln1b, xn, m1, r1)
             xin = self.buf("xn_in", (M, D), key=bk)
             hi, gi = self._adapter_fwd("T_Adapter_in", pre, xn, W, d, bk, training, None, 1.0, xn, None, xin)
-            qkv_in = xin
             if training:
                 S["tin"] = (xn, hi, gi)
-        qkv_t = self.buf("qkv_t", (M, 3 * D), key=bk)
-        self.gemm(qkv_in, Wqkv, qkv_t, bias=bqkv)
+            self.gemm(xin, Wqkv, qkv_t, bias=bqkv)
+        else:
+            self._qkv_ln(i, x, W, qkv_t, m1, r1, fold)
         o_t = self.buf("o_t", (M, D), key=bk)
         lib.attn_temporal_fwd(qkv_t, o_t, d.B, d.T, n, d.heads)
         x1 = self.buf("x1", (M, D), key=bk)
@@ -425,11 +459,9 @@ class Engine:
             self.gemm(o_t, Wo, a_t, bias=bo)
             h_t, g_t = self._adapter_fwd("T_Adapter", pre, a_t, W, d, bk, training, mask_t, 1.0, x, None, x1)
         # ---------------- spatial adaptation (:208)
-        xn_s = self.buf("xn", (M, D))
         m2, r2 = self.buf("ln1s_m", (M,), f32, bk), self.buf("ln1s_r", (M,), f32, bk)
-        lib.layernorm_fwd(x1, ln1w, ln1b, xn_s, m2, r2)
         qkv_s = self.buf("qkv_s", (M, 3 * D), key=bk)
-        self.gemm(xn_s, Wqkv, qkv_s, bias=bqkv)
+        self._qkv_ln(i, x1, W, qkv_s, m2, r2, fold)
         o_s = self.buf("o_s", (M, D), key=bk)
         lse = self.buf("lse_s", (d.BT, d.heads, n), f32, bk) if training else None
         lib.attn_spatial_fwd(qkv_s, o_s, lse, d.BT, n, d.heads, impl=self.attn_impl)

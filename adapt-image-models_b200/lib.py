@@ -32,7 +32,7 @@ class Epilogue(C.Structure):
                 ("dact_src", C.c_void_p), ("out", C.c_void_p), ("out_pre", C.c_void_p), ("alpha", C.c_float),
                 ("row_mod", C.c_int32), ("act", C.c_int32), ("dact", C.c_int32), ("bias_rowscaled", C.c_int32),
                 ("out_f32", C.c_int32), ("accumulate", C.c_int32), ("ldo", C.c_int64), ("colsum_out", C.c_void_p),
-                ("colsum_accumulate", C.c_int32)]
+                ("colsum_accumulate", C.c_int32), ("ln_mean", C.c_void_p), ("ln_rstd", C.c_void_p), ("ln_wsum", C.c_void_p)]
 
 
 # name -> argtypes; every function returns int except where noted.  Must list EVERY symbol of aimb200.h.
@@ -146,7 +146,8 @@ def _count():
 def layernorm_fwd(x, gamma, beta, y, mean=None, rstd=None, eps=1e-5):
     rows, D = x.numel() // x.shape[-1], x.shape[-1]
     _count()
-    _chk(load().aimb_layernorm_fwd(_ptr(_c(x)), _ptr(gamma), _ptr(beta), _ptr(_c(y)), _ptr(mean), _ptr(rstd), rows, D,
+    _chk(load().aimb_layernorm_fwd(_ptr(_c(x)), _ptr(gamma), _ptr(beta), _ptr(_c(y)) if y is not None else None, _ptr(mean),
+                                   _ptr(rstd), rows, D,
                                    eps, dt_code(x), _stream()), "layernorm_fwd")
     return y
 
@@ -204,7 +205,7 @@ def tail_bwd(dfeat, x, mean, rstd, gamma, dx, dgamma, dbeta, B, T, n):
 
 def make_epilogue(out, bias=None, row_scale=None, res1=None, res2=None, dact_src=None, out_pre=None, alpha=1.0, act=0,
                   dact=0, bias_rowscaled=False, out_f32=False, accumulate=False, ldo=0, colsum_out=None,
-                  colsum_accumulate=False) -> Epilogue:
+                  colsum_accumulate=False, ln_mean=None, ln_rstd=None, ln_wsum=None) -> Epilogue:
     e = Epilogue()
     e.bias, e.row_scale, e.res1, e.res2 = _ptr(bias), _ptr(row_scale), _ptr(res1), _ptr(res2)
     e.dact_src, e.out, e.out_pre = _ptr(dact_src), _ptr(out), _ptr(out_pre)
@@ -215,6 +216,9 @@ def make_epilogue(out, bias=None, row_scale=None, res1=None, res2=None, dact_src
     e.ldo = ldo
     e.colsum_out = _ptr(colsum_out)
     e.colsum_accumulate = int(colsum_accumulate)
+    if ln_mean is not None:      # LayerNorm folded into this GEMM: fp32 row statistics of A + row sums of the scaled weight
+        assert ln_rstd is not None and ln_wsum is not None and ln_wsum.dtype == torch.float32 and ln_mean.dtype == torch.float32
+    e.ln_mean, e.ln_rstd, e.ln_wsum = _ptr(ln_mean), _ptr(ln_rstd), _ptr(ln_wsum)
     return e
 
 

@@ -73,6 +73,13 @@ typedef struct aimb_epilogue {
     int64_t ldo; /* 0 -> N */
     float* colsum_out; /* [N] fp32, overwritten (or accumulated into, see colsum_accumulate) */
     int32_t colsum_accumulate; /* 1: do not zero colsum_out first (one memset of the whole gradient buffer by the caller) */
+    /* LayerNorm folded into the GEMM that consumes it (vit_clip.py:71-77 feeding :132-138; the LayerNorms on this path are
+     * frozen): with A = the UN-normalised rows x, W' = W * gamma (per input column), ln_wsum[n] = sum_k W'[n,k] and
+     * bias[n] = b[n] + sum_k beta[k] W[n,k], the accumulator becomes  acc = ln_rstd[m] * (acc - ln_mean[m] * ln_wsum[n])
+     * before the steps above: LN(x) W^T + b without ever writing LN(x).  All three NULL (default) or all three set. */
+    const float* ln_mean;  /* [M] fp32 row means of A */
+    const float* ln_rstd;  /* [M] fp32 1/sqrt(var + eps) */
+    const float* ln_wsum;  /* [N] fp32 row sums of the gamma-scaled weight, taken from the values the GEMM reads */
 } aimb_epilogue_t;
 
 int aimb_version(void);
@@ -97,6 +104,7 @@ int aimb_temb_grad(const void* dz, float* out, int32_t B, int32_t T, int32_t n, 
                    void* stream);
 
 /* ---- LayerNorm: vit_clip.py:71-77 (fp32 statistics, eps 1e-5) ------------------------------ */
+/* y may be NULL: statistics only (mean / rstd for a GEMM with the LayerNorm folded in, and for the LayerNorm backward). */
 int aimb_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd,
                        int64_t rows, int32_t D, float eps, int32_t dtype, void* stream);
 /* dx = dres + LN'(dy) ; dres may be NULL; dx may alias dres or dy. */

@@ -103,7 +103,7 @@ def test_vitb16_8x224_logits_vs_golden_and_oracle(mode, block):
 
 @pytest.mark.parametrize("env", [dict(), dict(AIMB200_FUSE_T_OUTPROJ="0"), dict(AIMB200_PAIR_MLP="0"), dict(AIMB200_FUSE_S_OUTPROJ="0"),
                                  dict(AIMB200_FUSE_T_OUTPROJ="0", AIMB200_FUSE_S_OUTPROJ="0", AIMB200_PAIR_MLP="0"),
-                                 dict(AIMB200_WGRAD_STREAM="0")])
+                                 dict(AIMB200_WGRAD_STREAM="0"), dict(AIMB200_LN_FOLD="0")])
 def test_vitb16_launch_fusions_vs_golden(env, monkeypatch):
     """Every launch-count variant of the block (temporal out_proj folded into T_Adapter.D_fc1 with batched per-step weight
     products; MLP-adapter GEMMs riding on c_fc / c_proj as N- / K-concatenated segments; side streams on / off) gives the

@@ -62,7 +62,20 @@ def test_layernorm_fwd_bwd(dt, rows, D):
     assert _err(cs, refc) < (1e-4 if dt == "f32" else 5e-3)
 
 
-EPI_CASES = ["plain", "bias", "bias_qgelu_pre", "bias_gelu_rowscale", "res2", "dact", "bias_rowscaled_alpha"]
+def test_layernorm_stats_only():
+    lib = _lib()
+    x = (torch.randn(1576, 768, device="cuda") * 3 + 1.5).bfloat16()
+    g, b = torch.ones(768, device="cuda").bfloat16(), torch.zeros(768, device="cuda").bfloat16()
+    mean, rstd = torch.empty(1576, device="cuda"), torch.empty(1576, device="cuda")
+    lib.layernorm_fwd(x, g, b, None, mean, rstd)
+    torch.cuda.synchronize()
+    assert _err(mean, x.double().mean(1)) < 1e-5
+    assert _err(rstd, 1.0 / torch.sqrt(x.double().var(1, unbiased=False) + 1e-5)) < 1e-5
+    with pytest.raises(lib.AimbError):
+        lib.layernorm_fwd(x, g, b, None, None, None)
+
+
+EPI_CASES = ["plain", "bias", "bias_qgelu_pre", "bias_gelu_rowscale", "res2", "dact", "bias_rowscaled_alpha", "ln_fold"]
 
 
 def _gemm_case(lib, dt, M, N, K, case, impl, seed=0):
@@ -107,6 +120,12 @@ def _gemm_case(lib, dt, M, N, K, case, impl, seed=0):
     elif case == "bias_rowscaled_alpha":
         kw = dict(bias=bias, row_scale=rs, bias_rowscaled=True, alpha=0.5, res1=r1)
         ref = (acc + bias.double() * rsm) * 0.5 + r1.double()
+    elif case == "ln_fold":     # LayerNorm folded into the GEMM: A = un-normalised rows, W already scaled by gamma
+        mu = a.double().mean(1)
+        rstd = 1.0 / torch.sqrt(a.double().var(1, unbiased=False) + 1e-5)
+        wsum = w.double().sum(1)
+        kw = dict(bias=bias, ln_mean=mu.float().contiguous(), ln_rstd=rstd.float().contiguous(), ln_wsum=wsum.float().contiguous())
+        ref = ((a.double() - mu[:, None]) * rstd[:, None]) @ w.double().T + bias.double()
     lib.gemm_nt(a, w, out, impl=impl, **kw)
     torch.cuda.synchronize()
     e = _err(out, ref)
