@@ -250,6 +250,13 @@ class ViT_CLIP(nn.Module):
         return super()._apply(fn, *a, **k)
 
     # ------------------------------------------------------------------ weights in compute dtype
+    def _ekey(self, name: str) -> str:
+        """state_dict name -> the key the engine uses (identity here; ViT_ImageNet maps its timm-style names)."""
+        return name
+
+    def _engine_params(self) -> Dict[str, nn.Parameter]:
+        return {self._ekey(n): p for n, p in self.named_parameters()}
+
     def _dims(self, B: int) -> Dims:
         p, res = self.patch_size, self.input_resolution
         K = 3 * p * p
@@ -298,7 +305,7 @@ class ViT_CLIP(nn.Module):
     def _weights(self, training: bool):
         """Return (W, WT): every weight in the compute dtype; WT = transposes for the dgrad GEMMs."""
         cd = self.compute_dtype
-        params = dict(self.named_parameters())
+        params = self._engine_params()
         self._flatten_trainable(params)
         W: Dict[str, torch.Tensor] = {}
         WT: Dict[str, torch.Tensor] = {}
@@ -317,8 +324,10 @@ class ViT_CLIP(nn.Module):
                     w2 = torch.zeros(src.shape[0], kpad, dtype=cd, device=src.device)
                     w2[:, :K] = src.reshape(src.shape[0], K).to(cd)
                     ent = (ver, w2, None)
-                elif name == "temporal_embedding":
+                elif name in ("temporal_embedding", "positional_embedding"):       # [1, T, D] / [1, n, D] (timm) -> rows
                     ent = (ver, src.to(cd).reshape(-1, src.shape[-1]).contiguous(), None)
+                elif name == "class_embedding":
+                    ent = (ver, src.to(cd).reshape(-1).contiguous(), None)
                 else:
                     w = src.to(cd).contiguous()
                     wt = None
@@ -397,7 +406,7 @@ class ViT_CLIP(nn.Module):
         W, WT, d = self._step_ctx
         names = self.trainable_names()
         flat_grad = torch.zeros_like(self._flat)      # ONE memset: the gradient kernels accumulate into it
-        params = dict(self.named_parameters())
+        params = self._engine_params()
         grads = {}
         for n in names:
             o, k = self._offsets[n]
@@ -427,7 +436,7 @@ class ViT_CLIP(nn.Module):
         self._step_ctx = None
         out = []
         for p_name, p in self.named_parameters():
-            out.append(grads.get(p_name) if p.requires_grad else None)
+            out.append(grads.get(self._ekey(p_name)) if p.requires_grad else None)
         return out
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -471,3 +480,189 @@ class AIM(ViT_CLIP):
         super().__init__(input_resolution, num_frames, patch_size, width, layers, heads, drop_path_rate,
                          num_tadapter=num_tadapter, adapter_scale=adapter_scale, pretrained=pretrained, block="aim",
                          compute_dtype=compute_dtype)
+
+
+class _TimmAttention(nn.Module):
+    """Parameter container of vit_imagenet.py:54-86 (qkv / proj linears)."""
+
+    def __init__(self, dim, qkv_bias=True):
+        super().__init__()
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.proj = nn.Linear(dim, dim)
+
+
+class _TimmMlp(nn.Module):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, hidden)
+        self.act = nn.GELU()
+        self.fc2 = nn.Linear(hidden, dim)
+
+
+class _TimmBlock(nn.Module):
+    """Parameter tree of vit_imagenet.py:88-108 (the math lives in engine.py: same AIM block, exact-GELU MLP)."""
+
+    def __init__(self, dim, num_tadapter=1, qkv_bias=True, mlp_ratio=4.0, eps=1e-6):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=eps)
+        self.attn = _TimmAttention(dim, qkv_bias)
+        self.MLP_Adapter = Adapter(dim, skip_connect=False)
+        self.S_Adapter = Adapter(dim)
+        self.T_Adapter = Adapter(dim, skip_connect=False)
+        if num_tadapter == 2:
+            self.T_Adapter_in = Adapter(dim)
+        self.norm2 = nn.LayerNorm(dim, eps=eps)
+        self.mlp = _TimmMlp(dim, int(dim * mlp_ratio))
+
+
+class _PatchEmbed(nn.Module):
+    def __init__(self, patch_size, in_chans, embed_dim, bias=True):
+        super().__init__()
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size, bias=bias)
+
+
+_TIMM_TO_ENGINE = (("patch_embed.proj.", "conv1."), ("cls_token", "class_embedding"), ("pos_embed", "positional_embedding"),
+                   (".norm1.", ".ln_1."), (".norm2.", ".ln_2."), (".attn.qkv.weight", ".attn.in_proj_weight"),
+                   (".attn.qkv.bias", ".attn.in_proj_bias"), (".attn.proj.", ".attn.out_proj."), (".mlp.fc1.", ".mlp.c_fc."),
+                   (".mlp.fc2.", ".mlp.c_proj."))
+
+
+@BACKBONES.register_module()
+class ViT_ImageNet(ViT_CLIP):
+    """Drop-in for ``mmaction/models/backbones/vit_imagenet.py::ViT_ImageNet`` (SURVEY.md section 8 f4): the AIM block on a timm
+    ViT-B/16 — same constructor arguments, ``state_dict`` keys / shapes (``patch_embed.proj``, ``cls_token``, ``pos_embed``,
+    ``blocks.{i}.norm1 / attn.qkv / attn.proj / mlp.fc1 / mlp.fc2 / *_Adapter``, ``ln_post``), ``init_weights()`` and
+    ``forward([B,3,T,H,W]) -> [B, D, T, 1, 1]``.  Differences from the CLIP variant, all handled inside the same engine and
+    kernels: patch embedding with bias, no ``ln_pre``, LayerNorm eps 1e-6, exact GELU in the MLP, and DropPath drawn per
+    FRAME (the block works on ``[(b t), n, d]`` tensors, so timm's DropPath masks dim 0 = frames, vit_imagenet.py:110-126).
+
+    Training scope: the hand-written backward produces the AIM trainable set (adapters, ``temporal_embedding``, ``ln_post``).
+    The reference class itself freezes nothing (full fine-tuning through autograd); that weight-gradient path is not built,
+    so ``freeze_backbone=True`` (the default, the AIM recipe) freezes the pre-trained tensors in ``init_weights()`` and a
+    grad-enabled forward with any other trainable parameter raises ``AimbError`` instead of returning wrong gradients."""
+
+    def __init__(self, img_size=224, num_frames=8, patch_size=16, in_chans=3, embed_dim=768, depth=12, adapter_scale=0.5,
+                 num_tadapter=1, num_heads=12, mlp_ratio=4., patch_embedding_bias=True, qkv_bias=True, qk_scale=None,
+                 drop_rate=0., attn_drop_rate=0., drop_path_rate=0.1, norm_layer=None, pretrained=None,
+                 freeze_backbone: bool = True, compute_dtype: Optional[str] = None):
+        nn.Module.__init__(self)
+        if in_chans != 3 or mlp_ratio != 4.0:
+            raise NotImplementedError("ViT_ImageNet: in_chans=3 and mlp_ratio=4 are what the kernels implement")
+        if drop_rate or attn_drop_rate:
+            raise NotImplementedError("ViT_ImageNet: drop_rate / attn_drop_rate > 0 are not used by any in-tree config and not built")
+        if embed_dim % num_heads or embed_dim // num_heads != 64:
+            raise ValueError("head_dim must be 64")
+        if qk_scale is not None and abs(qk_scale - 0.125) > 1e-12:
+            raise NotImplementedError("qk_scale other than head_dim ** -0.5 is not built")
+        if num_tadapter not in (1, 2):
+            raise ValueError("num_tadapter must be 1 or 2")
+        eps = 1e-6                                    # the reference default: partial(nn.LayerNorm, eps=1e-6)
+        if norm_layer is not None:
+            eps = float(getattr(norm_layer(8), "eps", 1e-6))
+        compute_dtype = os.environ.get("AIMB200_DTYPE", compute_dtype or "bf16")
+        if compute_dtype not in ("bf16", "fp32"):
+            raise ValueError("compute_dtype must be 'bf16' or 'fp32'")
+        self.block = "aim"
+        self.compute_dtype = torch.bfloat16 if compute_dtype == "bf16" else torch.float32
+        self.input_resolution, self.patch_size, self.num_frames = img_size, patch_size, num_frames
+        self.width, self.layers, self.heads = embed_dim, depth, num_heads
+        self.num_features = self.embed_dim = embed_dim
+        self.depth = depth
+        self.num_tadapter, self.adapter_scale = num_tadapter, float(adapter_scale)
+        self.drop_path_rate = float(drop_path_rate)
+        self.pretrained = pretrained
+        self.checkpoint = False
+        self.freeze_backbone = bool(freeze_backbone)
+        self.ln_eps = eps
+        self.patch_embed = _PatchEmbed(patch_size, in_chans, embed_dim, bias=patch_embedding_bias)
+        n_patches = (img_size // patch_size) ** 2
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.pos_embed = nn.Parameter(torch.zeros(1, n_patches + 1, embed_dim))
+        self.temporal_embedding = nn.Parameter(torch.zeros(1, num_frames, embed_dim))
+        self.blocks = nn.ModuleList([_TimmBlock(embed_dim, num_tadapter, qkv_bias, mlp_ratio, eps) for _ in range(depth)])
+        self.ln_post = nn.LayerNorm(embed_dim, eps=eps)
+        nn.init.trunc_normal_(self.pos_embed, std=.02)
+        nn.init.trunc_normal_(self.cls_token, std=.02)
+        self._engine = None
+        self._frozen_cache = {}
+        self._train_names = None
+        self._flat = None
+        self._flat_ptrs = None
+        self._grad_sync = None
+        self._input_norm = None
+        self._step_ctx = None
+        self._gen = 0
+        self._norm_dev = None
+        self._zero_qkv_bias = None
+
+    def _ekey(self, name: str) -> str:
+        if name.startswith("blocks."):
+            name = "transformer.resblocks." + name[len("blocks."):]
+        for a, b in _TIMM_TO_ENGINE:
+            name = name.replace(a, b)
+        return name
+
+    def _dims(self, B: int) -> Dims:
+        d = super()._dims(B)
+        return Dims(**{**d.__dict__, "eps": self.ln_eps, "mlp_act": lib.ACT_GELU, "ln_pre": False})
+
+    def _weights(self, training: bool):
+        W, WT = super()._weights(training)
+        if "transformer.resblocks.0.attn.in_proj_bias" not in W:          # qkv_bias=False: the kernels take a zero bias
+            if self._zero_qkv_bias is None or self._zero_qkv_bias.device != self._flat.device:
+                self._zero_qkv_bias = torch.zeros(3 * self.width, dtype=self.compute_dtype, device=self._flat.device)
+            for i in range(self.layers):
+                W[f"transformer.resblocks.{i}.attn.in_proj_bias"] = self._zero_qkv_bias
+        return W, WT
+
+    def _drop_masks(self, d: Dims, device):
+        """timm DropPath on [(b t), n, d] tensors: one Bernoulli draw per FRAME (vit_imagenet.py:110-126), expanded to one
+        multiplier per activation row (row = frame * n + token) for the epilogues' row_scale[m % len]."""
+        if not self.training or self.drop_path_rate <= 0.0:
+            return None
+        rates = torch.linspace(0, self.drop_path_rate, self.layers)
+        keep = (1.0 - rates).to(device).view(-1, 1, 1)
+        m = ((torch.rand(self.layers, 2, d.BT, device=device) < keep).float() / keep).repeat_interleave(d.n, dim=2)
+        return [(None, None) if float(rates[i]) == 0.0 else (m[i, 0].contiguous(), m[i, 1].contiguous())
+                for i in range(self.layers)]
+
+    def init_weights(self, pretrained=None):
+        """vit_imagenet.py:182-229: trunc-normal(.02) linears, LN 1/0, optional timm checkpoint (``norm.*`` -> ``ln_post.*``),
+        zero ``D_fc2`` of every adapter; then the AIM freeze rule unless ``freeze_backbone=False``."""
+        def _init(m):
+            if isinstance(m, nn.Linear):
+                nn.init.trunc_normal_(m.weight, std=.02)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+            elif isinstance(m, nn.LayerNorm):
+                nn.init.constant_(m.bias, 0)
+                nn.init.constant_(m.weight, 1.0)
+
+        if pretrained:
+            self.pretrained = pretrained
+        if isinstance(self.pretrained, str):
+            self.apply(_init)
+            if not os.path.isfile(self.pretrained):
+                raise RuntimeError(f"pretrained={self.pretrained!r}: pass the path of a timm ViT state_dict file "
+                                   "(the reference reads checkpoints/jx_vit_base_p16_224-80ecf9dd.pth, vit_imagenet.py:199)")
+            sd = torch.load(self.pretrained, map_location="cpu")
+            sd = sd.get("state_dict", sd)
+            if "norm.weight" in sd:
+                sd["ln_post.weight"], sd["ln_post.bias"] = sd["norm.weight"], sd["norm.bias"]
+            self.load_state_dict(sd, strict=False)
+        elif self.pretrained is None:
+            self.apply(_init)
+        else:
+            raise TypeError('pretrained must be a str or None')
+        for n, m in self.blocks.named_modules():
+            if 'Adapter' in n and n.endswith('D_fc2') and isinstance(m, nn.Linear):
+                nn.init.constant_(m.weight, 0)
+                nn.init.constant_(m.bias, 0)
+        if self.freeze_backbone:
+            for name, param in self.named_parameters():
+                param.requires_grad = _is_trainable_name(name)
+        self.invalidate_cache()
+
+    @torch.jit.ignore
+    def no_weight_decay(self):
+        return {'pos_embed', 'temporal_embedding'}

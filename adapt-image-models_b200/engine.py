@@ -41,6 +41,10 @@ class Dims:
     num_tadapter: int
     scale: float
     block: str = "aim"
+    # ViT_ImageNet variant of the same block (vit_imagenet.py:88-126, 232-260): timm LayerNorm eps, exact-GELU MLP, no ln_pre
+    eps: float = 1e-5
+    mlp_act: int = lib.ACT_QUICKGELU
+    ln_pre: bool = True
 
     @property
     def BT(self):
@@ -203,19 +207,27 @@ class Engine:
         # checkpoint=True (vit_clip.py:318-319, torch.utils.checkpoint per block): only the block INPUTS are kept; every
         # block's saved activations live in ONE shared buffer set and are recomputed block by block in backward
         self.ckpt = bool(checkpoint and training)
+        self._eps = d.eps
         # ---- stem
         cols = self.buf("cols", (BT * d.G * d.G, d.kpad))
         lib.im2col(x, cols, d.patch, W.get("input_mean"), W.get("input_std"))
         tok = self.buf("tok", (BT * d.G * d.G, D))
-        self.gemm(cols, W["conv1.weight"], tok)
-        z = self.buf("z", (M, D), key=key) if training else None
+        self.gemm(cols, W["conv1.weight"], tok, bias=W.get("conv1.bias"))       # patch_embed.proj has a bias in ViT_ImageNet
         xcur = self.buf("x", (M, D), key=(key, 0))
         mean0 = self.buf("ln_pre_mean", (M,), torch.float32, key)
         rstd0 = self.buf("ln_pre_rstd", (M,), torch.float32, key)
-        lib.stem_assemble_ln(tok, W["class_embedding"], W["positional_embedding"], W["temporal_embedding"],
-                             W["ln_pre.weight"], W["ln_pre.bias"], z, xcur, mean0, rstd0, d.B, d.T, n)
-        if training:
-            sv["z"], sv["ln_pre"] = z, (mean0, rstd0)
+        if d.ln_pre:
+            z = self.buf("z", (M, D), key=key) if training else None
+            lib.stem_assemble_ln(tok, W["class_embedding"], W["positional_embedding"], W["temporal_embedding"],
+                                 W["ln_pre.weight"], W["ln_pre.bias"], z, xcur, mean0, rstd0, d.B, d.T, n, eps=d.eps)
+            if training:
+                sv["z"], sv["ln_pre"] = z, (mean0, rstd0)
+        else:
+            # no ln_pre (vit_imagenet.py:244-251): the assembled sum IS the block input; the kernel's LayerNorm output goes
+            # to a scratch buffer (one pass per step, not worth a second kernel variant)
+            lib.stem_assemble_ln(tok, W["class_embedding"], W["positional_embedding"], W["temporal_embedding"],
+                                 W["ln_post.weight"], W["ln_post.bias"], xcur, self.buf("stem_scratch", (M, D)), mean0, rstd0,
+                                 d.B, d.T, n, eps=d.eps)
         self.t_fused = (self.fuse_t_outproj and d.block == "aim" and d.num_tadapter == 1 and WT is not None
                         and self.dtype == torch.bfloat16)
         self.s_fused = (self.fuse_s_outproj and d.block == "aim" and WT is not None and self.dtype == torch.bfloat16
@@ -235,7 +247,7 @@ class Engine:
         feat = torch.empty(d.B, D, d.T, device=self.device, dtype=torch.float32)
         tm = self.buf("tail_mean", (BT,), torch.float32, key)
         tr = self.buf("tail_rstd", (BT,), torch.float32, key)
-        lib.tail_fwd(xcur, W["ln_post.weight"], W["ln_post.bias"], feat, tm, tr, d.B, d.T, n)
+        lib.tail_fwd(xcur, W["ln_post.weight"], W["ln_post.bias"], feat, tm, tr, d.B, d.T, n, eps=d.eps)
         if training:
             sv["x_last"], sv["tail"] = xcur, (tm, tr)
             self.saved = sv
@@ -320,12 +332,12 @@ class Engine:
         """out = ln_1(x) Wqkv^T + b (vit_clip.py:132-138 after :71-77); returns ln_1(x) when it was materialised."""
         pre = f"transformer.resblocks.{i}."
         if fold:
-            lib.layernorm_fwd(x, W[pre + "ln_1.weight"], W[pre + "ln_1.bias"], None, mean, rstd)      # statistics only
+            lib.layernorm_fwd(x, W[pre + "ln_1.weight"], W[pre + "ln_1.bias"], None, mean, rstd, eps=self._eps)      # statistics only
             wf, ws, cf = self._ln_folded(i, W)
             self.gemm(x, wf, out, bias=cf, ln_mean=mean, ln_rstd=rstd, ln_wsum=ws)
             return None
         xn = self.buf("xn", x.shape, key=xn_key)
-        lib.layernorm_fwd(x, W[pre + "ln_1.weight"], W[pre + "ln_1.bias"], xn, mean, rstd)
+        lib.layernorm_fwd(x, W[pre + "ln_1.weight"], W[pre + "ln_1.bias"], xn, mean, rstd, eps=self._eps)
         self.gemm(xn, W[pre + "attn.in_proj_weight"], out, bias=W[pre + "attn.in_proj_bias"])
         return xn
 
@@ -353,11 +365,11 @@ class Engine:
         f32 = torch.float32
         xn2 = self.buf("xn2", (M, D), key=bk)
         m3, r3 = self.buf("ln2_m", (M,), f32, bk), self.buf("ln2_r", (M,), f32, bk)
-        lib.layernorm_fwd(x2, W[pre + "ln_2.weight"], W[pre + "ln_2.bias"], xn2, m3, r3)
+        lib.layernorm_fwd(x2, W[pre + "ln_2.weight"], W[pre + "ln_2.bias"], xn2, m3, r3, eps=d.eps)
         hf = self.buf("hf", (M, 4 * D), key=bk) if training else None
         gf = self.buf("gf", (M, 4 * D))
         xo = self.buf("x", (M, D), key=("train", i + 1) if training else ("eval", (i + 1) % 2))
-        if self._pair_mlp_ok(xn2, d):
+        if d.mlp_act == lib.ACT_QUICKGELU and self._pair_mlp_ok(xn2, d):
             # [hf | h_m] = xn2 [Wfc ; W1]^T in one launch; g_m = scale * mask_m * GELU(h_m) carries the whole branch factor
             h_m = self.buf("MLP_Adapter_h", (M, d.r), key=bk) if training else None
             g_m = self.buf("MLP_Adapter_g", (M, d.r), key=bk)
@@ -372,7 +384,7 @@ class Engine:
             return xo, dict(ln2=(m3, r3), xn2=xn2, h_m=h_m, g_m=g_m, hf=hf, paired=True)
         tmp = self.buf("tmp", (M, D))
         h_m, g_m = self._adapter_fwd("MLP_Adapter", pre, xn2, W, d, bk, training, mask_m, d.scale, x2, None, tmp)
-        self.gemm(xn2, W[pre + "mlp.c_fc.weight"], gf, bias=W[pre + "mlp.c_fc.bias"], act=lib.ACT_QUICKGELU, out_pre=hf)
+        self.gemm(xn2, W[pre + "mlp.c_fc.weight"], gf, bias=W[pre + "mlp.c_fc.bias"], act=d.mlp_act, out_pre=hf)
         self.gemm(gf, W[pre + "mlp.c_proj.weight"], xo, bias=W[pre + "mlp.c_proj.bias"], res1=tmp)
         return xo, dict(ln2=(m3, r3), xn2=xn2, h_m=h_m, g_m=g_m, hf=hf, paired=False)
 
@@ -411,7 +423,7 @@ class Engine:
                 _wgrads()
             self._join_side()          # dW2 reads dx, which the LayerNorm backward below rewrites in place
         else:
-            self.gemm(dx, WT[pre + "mlp.c_proj.weight"], d_hf, dact_src=S["hf"], dact=lib.ACT_QUICKGELU)
+            self.gemm(dx, WT[pre + "mlp.c_proj.weight"], d_hf, dact_src=S["hf"], dact=d.mlp_act)
             self.gemm(d_hf, WT[pre + "mlp.c_fc.weight"], d_xn2)
             self._adapter_bwd("MLP_Adapter", pre, dx, S["xn2"], S["h_m"], S["g_m"], W, WT, grads, d, mask_m, d.scale,
                               d_xn2, d_xn2, db2_fused=db2_fused)
@@ -435,7 +447,7 @@ class Engine:
         qkv_t = self.buf("qkv_t", (M, 3 * D), key=bk)
         if d.num_tadapter == 2:
             xn = self.buf("xn", (M, D), key=bk if training else None)
-            lib.layernorm_fwd(x, ln1w, ln1b, xn, m1, r1)
+            lib.layernorm_fwd(x, ln1w, ln1b, xn, m1, r1, eps=d.eps)
             xin = self.buf("xn_in", (M, D), key=bk)
             hi, gi = self._adapter_fwd("T_Adapter_in", pre, xn, W, d, bk, training, None, 1.0, xn, None, xin)
             if training:
@@ -499,7 +511,7 @@ class Engine:
         Wo, bo = W[pre + "attn.out_proj.weight"], W[pre + "attn.out_proj.bias"]
         xn = self.buf("xn", (M, D))
         m1, r1 = self.buf("ln1s_m", (M,), f32, bk), self.buf("ln1s_r", (M,), f32, bk)
-        lib.layernorm_fwd(x, W[pre + "ln_1.weight"], W[pre + "ln_1.bias"], xn, m1, r1)
+        lib.layernorm_fwd(x, W[pre + "ln_1.weight"], W[pre + "ln_1.bias"], xn, m1, r1, eps=d.eps)
         # ---- temporal attention over the T cls tokens of each clip (:218-229); ln_1 is row-wise, so ln_1(cls) = cls rows of xn
         ct = xn.view(BT, n, D)[:, 0, :]                                    # [BT, D], row stride n*D (read in place)
         qkv_c = self.buf("qkv_c", (BT, 3 * D), key=bk)
@@ -630,9 +642,12 @@ class Engine:
             if on_block_done:
                 on_block_done(i)
         # ln_pre backward -> dz ; temporal_embedding grad = sum over (b, token)   (vit_clip.py:443-447)
-        m0, r0 = sv["ln_pre"]
-        dz = self.buf("dz", (M, D))
-        lib.layernorm_bwd(dx, sv["z"], m0, r0, W["ln_pre.weight"], None, dz)
+        if d.ln_pre:
+            m0, r0 = sv["ln_pre"]
+            dz = self.buf("dz", (M, D))
+            lib.layernorm_bwd(dx, sv["z"], m0, r0, W["ln_pre.weight"], None, dz)
+        else:
+            dz = dx
         lib.temb_grad(dz, grads["temporal_embedding"], d.B, d.T, n)
         if on_block_done:
             on_block_done(-1)

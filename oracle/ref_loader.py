@@ -77,10 +77,11 @@ def _install_stubs():
     mb._aimb200_stub = True
     mu = types.ModuleType("mmaction.utils")
     mu.get_root_logger = lambda *a, **k: logging.getLogger("mmaction")
-    for n in ("timm", "timm.models", "clip", "mmaction", "mmaction.models", "mmaction.models.backbones"):
+    for n in ("timm", "timm.models", "clip", "mmaction", "mmaction.models", "mmaction.models.backbones", "turtle"):   # vit_imagenet.py:2
         m = types.ModuleType(n)
         m.__path__ = []
         sys.modules[n] = m
+    sys.modules["turtle"].forward = None          # vit_imagenet.py:2 `from turtle import forward` (unused there)
     sys.modules.update({"timm.models.layers": tl, "mmaction.models.builder": mb, "mmaction.utils": mu})
 
 
@@ -110,3 +111,18 @@ def reference_module(cfg, state_dict, drop_path_rate=0.0):
     m.init_weights()
     missing = m.load_state_dict(state_dict, strict=True)
     return m
+
+
+def reference_imagenet(cfg, state_dict, drop_path_rate=0.0):
+    """The reference ``vit_imagenet.py::ViT_ImageNet`` (build container only: the file is read from the mounted tree)."""
+    m = load("vit_imagenet.py").ViT_ImageNet(img_size=cfg.input_resolution, num_frames=cfg.num_frames, patch_size=cfg.patch_size,
+                                             embed_dim=cfg.width, depth=cfg.layers, num_heads=cfg.heads,
+                                             adapter_scale=cfg.adapter_scale, num_tadapter=cfg.num_tadapter,
+                                             drop_path_rate=drop_path_rate)
+    m.init_weights()
+    m.load_state_dict(state_dict, strict=True)
+    return m
+
+
+def imagenet_available() -> bool:
+    return os.path.isfile(REF_ROOT + "vit_imagenet.py")

@@ -25,7 +25,20 @@ def collect(ref=REF):
     return out
 
 
+def collect_imagenet(ref=REF):
+    """configs/recognition/vit/vit_imagenet_*.py (type='ViT_ImageNet')."""
+    out = {}
+    for f in sorted(glob.glob(os.path.join(ref, "configs/recognition/vit/vit_imagenet_*.py"))):
+        m = aimb200.load_config(f)["model"]
+        out[os.path.relpath(f, ref)] = {"backbone": m["backbone"], "cls_head": m["cls_head"], "test_cfg": m.get("test_cfg")}
+    return out
+
+
 if __name__ == "__main__":
+    di = collect_imagenet()
+    pi = os.path.join(os.path.dirname(os.path.abspath(__file__)), "vit_imagenet_configs.json")
+    json.dump(di, open(pi, "w"), indent=1, sort_keys=True)
+    print(f"{len(di)} configs -> {pi}")
     d = collect()
     p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "vitclip_configs.json")
     json.dump(d, open(p, "w"), indent=1, sort_keys=True)

@@ -113,11 +113,42 @@ def make_full(block):
           "f32-vs-f64 logit err", O.normalised_max_err(torch.tensor(out["logits_f32"]), torch.tensor(out["logits_f64"])))
 
 
+def make_tiny_imagenet(nt=1):
+    """vit_imagenet.py::ViT_ImageNet (2 layers, width 256): fp64 logits, loss, features and the gradients of the AIM
+    trainable set (the reference freezes nothing; gradients of the adapters do not depend on that)."""
+    from oracle import imagenet_oracle as OI
+    cfg = O.OracleCfg(**TINY, num_tadapter=nt)
+    dt = torch.float64
+    p = OI.fixture_state_dict(cfg, dtype=dt)
+    x = O.fixture_clip(cfg, 2, dtype=dt)
+    hw, hb = O.fixture_head(cfg, 16, dtype=dt)
+    labels = torch.tensor([3, 11])
+    m = R.reference_imagenet(cfg, p).to(dt).eval()
+    feat = m(x)
+    lg = O.head_logits(feat, hw, hb)
+    loss = F.cross_entropy(lg, labels)
+    loss.backward()
+    out = {"logits": lg.detach().numpy(), "loss": loss.detach().numpy(), "feat": feat.detach().numpy(), "labels": labels.numpy(),
+           "state_dict_keys": np.array(list(m.state_dict().keys()))}
+    for name, prm in m.named_parameters():
+        if O.is_trainable(name):
+            out["grad/" + name] = prm.grad.numpy().astype(np.float32)
+    tag = "tiny_imagenet" + ("_nt2" if nt == 2 else "")
+    np.savez_compressed(os.path.join(HERE, tag + ".npz"), **out)
+    print(tag, "loss", float(loss), "n_grads", sum(k.startswith("grad/") for k in out))
+
+
 if __name__ == "__main__":
     assert R.available(), "needs /root/reference"
     torch.manual_seed(0)
+    if "--imagenet-only" in sys.argv:
+        make_tiny_imagenet(1)
+        make_tiny_imagenet(2)
+        sys.exit(0)
     make_tiny("aim", 1)
     make_tiny("aim", 2)
     make_tiny("fork", 1)
     make_full("aim")
     make_full("fork")
+    make_tiny_imagenet(1)
+    make_tiny_imagenet(2)

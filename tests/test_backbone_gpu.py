@@ -419,3 +419,79 @@ def test_checkpoint_true_recomputes_and_matches(block):
     for k in res[False][1]:
         assert torch.allclose(res[False][1][k], res[True][1][k], rtol=1e-5, atol=1e-8), k    # fp32 atomics: order may differ
     assert res[True][2] < 0.8 * res[False][2]          # 2 layers: one shared activation set instead of two
+
+
+# ------------------------------------------------------------------------------------------------ ViT_ImageNet variant (f4)
+def _build_imagenet(cfg: O.OracleCfg, mode: str, drop_path_rate=0.0):
+    from oracle import imagenet_oracle as OI
+    m = aimb200.build_backbone(dict(type="ViT_ImageNet", img_size=cfg.input_resolution, num_frames=cfg.num_frames,
+                                    patch_size=cfg.patch_size, embed_dim=cfg.width, depth=cfg.layers, num_heads=cfg.heads,
+                                    num_tadapter=cfg.num_tadapter, adapter_scale=cfg.adapter_scale,
+                                    drop_path_rate=drop_path_rate, compute_dtype=mode))
+    m.init_weights()
+    m.load_state_dict(OI.fixture_state_dict(cfg))
+    return m.cuda()
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("nt", [1, 2])
+def test_imagenet_tiny_logits_and_all_grads_vs_golden(mode, nt):
+    """aimb200.ViT_ImageNet against goldens generated from vit_imagenet.py::ViT_ImageNet itself."""
+    gold = np.load(os.path.join(G, "tiny_imagenet" + ("_nt2" if nt == 2 else "") + ".npz"))
+    cfg = O.OracleCfg(**TINY, num_tadapter=nt)
+    m = _build_imagenet(cfg, mode)
+    x = O.fixture_clip(cfg, 2)
+    hw, hb = O.fixture_head(cfg, 16)
+    lg, loss, grads = _cuda_logits_and_grads(m, cfg, x, hw, hb, torch.tensor(gold["labels"]))
+    tol_l, tol_g = (1e-3, 1e-3) if mode == "fp32" else (2e-2, 6e-2)
+    assert O.normalised_max_err(lg, torch.tensor(gold["logits"])) < tol_l
+    assert abs(loss - float(gold["loss"])) < tol_l
+    n = 0
+    for k in gold.files:
+        if k.startswith("grad/"):
+            n += 1
+            assert O.normalised_max_err(grads[k[5:]], torch.tensor(gold[k])) < tol_g, k
+    assert n == len(grads)
+    m.eval()
+    with torch.no_grad():
+        feat = m(x.cuda()).cpu()
+    assert O.normalised_max_err(feat, torch.tensor(gold["feat"])) < (1e-3 if mode == "fp32" else 2e-2)
+
+
+def test_imagenet_droppath_is_per_frame_and_matches_oracle():
+    from oracle import imagenet_oracle as OI
+    cfg = O.OracleCfg(**TINY)
+    m = _build_imagenet(cfg, "fp32", drop_path_rate=0.5).train()
+    x = O.fixture_clip(cfg, 2)
+    torch.manual_seed(3)
+    masks = m._drop_masks(m._dims(2), torch.device("cuda"))
+    torch.manual_seed(3)
+    feat = m(x.cuda())
+    n, BT = cfg.tokens, 2 * cfg.num_frames
+    a, b = masks[1]
+    assert a.numel() == BT * n and torch.equal(a.view(BT, n), a.view(BT, n)[:, :1].expand(BT, n))     # one value per frame
+    assert float(a.min()) == 0.0 or float(b.min()) == 0.0, "a dropped frame expected"
+    om = [(None, None), (a.view(BT, n)[:, 0].cpu(), b.view(BT, n)[:, 0].cpu())]
+    ref = OI.backbone(OI.fixture_state_dict(cfg), x, cfg, drop_masks=om)
+    assert O.normalised_max_err(feat.detach().cpu(), ref) < 1e-3
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_imagenet_vitb16_8x224_vs_live_oracle(mode):
+    """Full-size timm ViT-B/16 AIM (vit_imagenet_k400.py), one clip: logits and every adapter gradient against the oracle
+    (pinned to the reference class by the tiny goldens above)."""
+    from oracle import imagenet_oracle as OI
+    cfg = O.OracleCfg()
+    m = _build_imagenet(cfg, mode)
+    x = O.fixture_clip(cfg, 1)
+    hw, hb = O.fixture_head(cfg, 400)
+    labels = torch.tensor([7])
+    lg, loss, grads = _cuda_logits_and_grads(m, cfg, x, hw, hb, labels)
+    rl, rlg, rg = OI.loss_and_grads(OI.fixture_state_dict(cfg), x, labels, cfg, hw, hb)
+    err = O.normalised_max_err(lg, rlg)
+    print(f"[ViT_ImageNet {mode}] logit err {err:.3e}")
+    assert err < (1e-3 if mode == "fp32" else 2e-2) and int(lg.argmax()) == int(rlg.argmax())
+    tol = 1e-3 if mode == "fp32" else 6e-2
+    assert sorted(grads) == sorted(rg)
+    for k, g in rg.items():
+        assert O.normalised_max_err(grads[k], g) < tol, k

@@ -136,3 +136,48 @@ def test_shift_true_raises_in_reference_too():
     with pytest.raises(Exception) as ei, torch.no_grad():
         net(torch.randn(1, 3, 4, 64, 64))
     assert "rearrange" in str(ei.value) or "Shape mismatch" in str(ei.value)
+
+
+# ------------------------------------------------------------------------------------------------ ViT_ImageNet (f4)
+IMAGENET_CONFIGS = json.load(open(os.path.join(ROOT, "tests", "golden", "vit_imagenet_configs.json")))
+
+
+@pytest.mark.parametrize("name", sorted(IMAGENET_CONFIGS))
+def test_vit_imagenet_configs_build_with_the_reference_tree(name):
+    """type='ViT_ImageNet' (vit_imagenet.py:147-180): every in-tree config constructs; state_dict keys / shapes are the
+    reference's (goldens carry the key list of the real class; oracle/imagenet_oracle.py::param_shapes restates it)."""
+    from oracle import imagenet_oracle as OI
+    cfg = dict(IMAGENET_CONFIGS[name]["backbone"])
+    if cfg.get("pretrained"):
+        cfg["pretrained"] = None
+    m = aimb200.build_backbone(cfg)
+    assert type(m).__name__ == "ViT_ImageNet"
+    m.init_weights()
+    ocfg = O.OracleCfg(input_resolution=cfg.get("img_size", 224), num_frames=cfg.get("num_frames", 8), patch_size=cfg.get("patch_size", 16),
+                       width=cfg.get("embed_dim", 768), layers=cfg.get("depth", 12), heads=cfg.get("num_heads", 12),
+                       num_tadapter=cfg.get("num_tadapter", 1))
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == OI.param_shapes(ocfg)
+    # AIM recipe by default: pre-trained tensors frozen, adapters / temporal_embedding / ln_post trainable, D_fc2 zero
+    for k, p in m.named_parameters():
+        assert p.requires_grad == O.is_trainable(k), k
+        if "Adapter" in k and "D_fc2" in k:
+            assert float(p.abs().max()) == 0.0
+    assert m.no_weight_decay() == {"pos_embed", "temporal_embedding"}
+    with pytest.raises(lib.AimbError):
+        m(torch.zeros(1, 3, ocfg.num_frames, 224, 224))       # CPU tensor: no fallback
+
+
+def test_vit_imagenet_matches_reference_key_list_and_engine_names():
+    import numpy as np
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "tiny_imagenet_nt2.npz"))
+    m = aimb200.build_backbone(dict(type="ViT_ImageNet", img_size=64, num_frames=4, patch_size=16, embed_dim=256, depth=2,
+                                    num_heads=4, num_tadapter=2, freeze_backbone=False))
+    assert list(m.state_dict().keys()) == [str(k) for k in gold["state_dict_keys"]]       # same keys, same ORDER
+    m.init_weights()
+    assert all(p.requires_grad for p in m.parameters())     # the reference's own behaviour: nothing frozen ...
+    # ... every name maps onto the engine's key space without collisions
+    keys = {m._ekey(k) for k, _ in m.named_parameters()}
+    assert len(keys) == len(list(m.named_parameters()))
+    assert "conv1.bias" in keys and "transformer.resblocks.1.attn.in_proj_weight" in keys and "transformer.resblocks.0.mlp.c_fc.bias" in keys
+    with pytest.raises(NotImplementedError):
+        aimb200.build_backbone(dict(type="ViT_ImageNet", drop_rate=0.1))

@@ -84,3 +84,45 @@ def test_oracle_matches_live_reference_with_droppath(block):
     m2 = torch.empty(n, 1, 1, dtype=dt).bernoulli_(keep).div_(keep).view(n)
     out = O.backbone(p, x, cfg, drop_masks=[(None, None), (m1, m2)])
     assert O.normalised_max_err(out, ref.detach()) < 1e-12
+
+
+# ------------------------------------------------------------------------------------------------ ViT_ImageNet variant (f4)
+@pytest.mark.parametrize("nt", [1, 2])
+def test_imagenet_oracle_matches_golden_tiny(nt):
+    """oracle/imagenet_oracle.py against vit_imagenet.py::ViT_ImageNet (goldens generated from the real class)."""
+    from oracle import imagenet_oracle as OI
+    gold = np.load(os.path.join(G, "tiny_imagenet" + ("_nt2" if nt == 2 else "") + ".npz"))
+    cfg = O.OracleCfg(**TINY, num_tadapter=nt)
+    dt = torch.float64
+    p = OI.fixture_state_dict(cfg, dtype=dt)
+    assert list(p) and sorted(p) == sorted(str(k) for k in gold["state_dict_keys"])
+    x = O.fixture_clip(cfg, 2, dtype=dt)
+    hw, hb = O.fixture_head(cfg, 16, dtype=dt)
+    loss, lg, grads = OI.loss_and_grads(p, x, torch.tensor(gold["labels"]), cfg, hw, hb)
+    assert O.normalised_max_err(lg, torch.tensor(gold["logits"])) < 1e-12
+    assert abs(float(loss) - float(gold["loss"])) < 1e-12
+    n = 0
+    for k in gold.files:
+        if k.startswith("grad/"):
+            n += 1
+            assert O.normalised_max_err(grads[k[5:]], torch.tensor(gold[k])) < 1e-6, k
+    assert n == (35 if nt == 2 else 27) == len(grads)
+
+
+@pytest.mark.skipif(not R.imagenet_available(), reason="/root/reference not mounted (GPU box)")
+def test_imagenet_oracle_matches_live_reference_with_droppath():
+    """timm DropPath on [(b t), n, d] tensors masks FRAMES (one draw per (b, t)), unlike the LND CLIP variant (tokens)."""
+    from oracle import imagenet_oracle as OI
+    cfg = O.OracleCfg(**TINY)
+    dt = torch.float64
+    p = OI.fixture_state_dict(cfg, dtype=dt)
+    x = O.fixture_clip(cfg, 2, dtype=dt)
+    m = R.reference_imagenet(cfg, p, drop_path_rate=0.5).to(dt).train()
+    torch.manual_seed(11)
+    ref = m(x)
+    torch.manual_seed(11)
+    keep, BT = 0.5, 2 * cfg.num_frames
+    m1 = torch.empty(BT, 1, 1, dtype=dt).bernoulli_(keep).div_(keep).view(BT)
+    m2 = torch.empty(BT, 1, 1, dtype=dt).bernoulli_(keep).div_(keep).view(BT)
+    out = OI.backbone(p, x, cfg, drop_masks=[(None, None), (m1, m2)])
+    assert O.normalised_max_err(out, ref.detach()) < 1e-12
