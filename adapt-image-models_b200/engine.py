@@ -86,6 +86,7 @@ class Engine:
         # K-concatenated launch and a is never materialised; backward: d_o = [dx2 | d_h] [Wo^T | W1o^T]^T the same way.
         self.fuse_s_outproj = os.environ.get("AIMB200_FUSE_S_OUTPROJ", "1") == "1"
         self.s_fused = False
+        self.one_kernel_t = os.environ.get("AIMB200_ONE_KERNEL_T", "0") == "1"   # experiment: adapter_tc_kernel for T_Adapter
         # ln_1 is frozen, so LN(x) Wqkv^T + b = rstd * (x (Wqkv * gamma)^T - mean * rowsum(Wqkv * gamma)) + (b + Wqkv beta):
         # the QKV GEMM reads the un-normalised residual stream and applies the row statistics in its epilogue; the
         # normalised activations are never written (a statistics-only pass replaces the LayerNorm kernel)
@@ -462,10 +463,14 @@ class Engine:
             a_t = None
             h_t = self.buf("T_Adapter_h", (M, r), key=bk) if training else None
             g_t = self.buf("T_Adapter_g", (M, r), key=bk)
-            self.gemm(o_t, W[pre + "T_Adapter.w1o"], g_t, bias=W[pre + "T_Adapter.b1o"], act=lib.ACT_GELU, out_pre=h_t,
-                      row_scale=mask_t)
-            self.gemm(g_t, W[pre + "T_Adapter.D_fc2.weight"], x1, bias=W[pre + "T_Adapter.D_fc2.bias"], row_scale=mask_t,
-                      bias_rowscaled=mask_t is not None, res1=x)
+            epi1 = dict(bias=W[pre + "T_Adapter.b1o"], act=lib.ACT_GELU, out_pre=h_t, row_scale=mask_t)
+            epi2 = dict(bias=W[pre + "T_Adapter.D_fc2.bias"], row_scale=mask_t, bias_rowscaled=mask_t is not None, res1=x)
+            if self.one_kernel_t and lib.adapter_fused_supported(o_t, r, D):
+                # both GEMMs of the adapter in one kernel: the hidden tile stays in shared memory (adapter_tc_kernel)
+                lib.adapter_fused(o_t, W[pre + "T_Adapter.w1o"], W[pre + "T_Adapter.D_fc2.weight"], g_t, x1, epi1, epi2)
+            else:
+                self.gemm(o_t, W[pre + "T_Adapter.w1o"], g_t, **epi1)
+                self.gemm(g_t, W[pre + "T_Adapter.D_fc2.weight"], x1, **epi2)
         else:
             a_t = self.buf("a_t", (M, D), key=bk)
             self.gemm(o_t, Wo, a_t, bias=bo)
@@ -706,9 +711,18 @@ class Engine:
         else:
             self._wgrad(dy, g, grads[k2w])
         d_h = self.buf("d_h", (M, r))
-        self.gemm(dy, WT[k2w], d_h, dact_src=h, dact=lib.ACT_GELU, row_scale=rs, colsum_out=grads[k1b])
-
         G = self.buf("T_Adapter_G", (d.L, r, D), torch.float32)[self._cur_block]
+        epi1 = dict(dact_src=h, dact=lib.ACT_GELU, row_scale=rs, colsum_out=grads[k1b],
+                    colsum_accumulate=self.grads_prezeroed)
+        if self.one_kernel_t and lib.adapter_fused_supported(dy, r, D):
+            lib.adapter_fused(dy, WT[k2w], W[pre + "T_Adapter.w1oT"], d_h, d_o_out, epi1, {})
+            if side:
+                with torch.cuda.stream(self._side_begin()):
+                    lib.gemm_wgrad(d_h, o, G, accumulate=True)
+            else:
+                lib.gemm_wgrad(d_h, o, G, accumulate=True)
+            return
+        lib.gemm_nt(dy, WT[k2w], d_h, impl=self.gemm_impl, **epi1)
         if side:
             with torch.cuda.stream(self._side_begin()):       # ordered after the d_h GEMM (and its fused db1 column sums)
                 lib.gemm_wgrad(d_h, o, G, accumulate=True)                      # d_h^T o, fp32 (zeroed in _prep_fused)
