@@ -15,6 +15,7 @@ contiguous row ranges and temporal attention reads rows at stride n in place.
 """
 from __future__ import annotations
 
+import contextlib
 import os
 from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional
@@ -196,9 +197,15 @@ class Engine:
         return lib.colsum(x, out, row_scale=row_scale, alpha=alpha, accumulate=self.grads_prezeroed)
 
     # ------------------------------------------------------------------ forward
+    def prep_stream(self):
+        """side stream of the per-step weight preparation (backbone.py::_run_forward)"""
+        if getattr(self, "_prep", None) is None:
+            self._prep = torch.cuda.Stream(device=self.device)
+        return self._prep
+
     def forward(self, x: torch.Tensor, W: Dict[str, torch.Tensor], d: Dims, training: bool,
                 drop_masks: Optional[List] = None, WT: Optional[Dict[str, torch.Tensor]] = None,
-                checkpoint: bool = False) -> torch.Tensor:
+                checkpoint: bool = False, weights_ready=None) -> torch.Tensor:
         """x [B,3,T,H,W] (fp32 / bf16 / uint8) -> feat fp32 [B, D, T].  W: weights in compute dtype.
         drop_masks[i] = (mask_t, mask_m): fp32 [n] DropPath multipliers (0 or 1/keep) or None."""
         M, D, r, n, BT = d.M, d.D, d.r, d.n, d.BT
@@ -209,6 +216,20 @@ class Engine:
         # block's saved activations live in ONE shared buffer set and are recomputed block by block in backward
         self.ckpt = bool(checkpoint and training)
         self._eps = d.eps
+        # weights_ready = (event, stream): the trainable weights (W / WT / drop_masks) were prepared on that side stream; the
+        # batched weight products of the fused adapters are appended to it, and the main stream joins it twice: for
+        # temporal_embedding (ready at `event`) before the stem assembly, and for everything before block 0
+        main = torch.cuda.current_stream(self.device)
+        self.t_fused = (self.fuse_t_outproj and d.block == "aim" and d.num_tadapter == 1 and WT is not None
+                        and self.dtype == torch.bfloat16)
+        self.s_fused = (self.fuse_s_outproj and d.block == "aim" and WT is not None and self.dtype == torch.bfloat16
+                        and self.gemm_impl == lib.IMPL_AUTO and not self.fuse_adapters
+                        and lib.dual_supported_dims(M, D, self.dtype, D, 0, r))
+        with torch.cuda.stream(weights_ready[1]) if weights_ready is not None else contextlib.nullcontext():
+            if self.t_fused:
+                self._prep_fused("T_Adapter", W, WT, d, training)
+            if self.s_fused:
+                self._prep_fused("S_Adapter", W, WT, d, training)
         # ---- stem
         cols = self.buf("cols", (BT * d.G * d.G, d.kpad))
         lib.im2col(x, cols, d.patch, W.get("input_mean"), W.get("input_std"))
@@ -217,6 +238,8 @@ class Engine:
         xcur = self.buf("x", (M, D), key=(key, 0))
         mean0 = self.buf("ln_pre_mean", (M,), torch.float32, key)
         rstd0 = self.buf("ln_pre_rstd", (M,), torch.float32, key)
+        if weights_ready is not None:
+            main.wait_event(weights_ready[0])              # temporal_embedding comes out of the per-step cast
         if d.ln_pre:
             z = self.buf("z", (M, D), key=key) if training else None
             lib.stem_assemble_ln(tok, W["class_embedding"], W["positional_embedding"], W["temporal_embedding"],
@@ -229,15 +252,8 @@ class Engine:
             lib.stem_assemble_ln(tok, W["class_embedding"], W["positional_embedding"], W["temporal_embedding"],
                                  W["ln_post.weight"], W["ln_post.bias"], xcur, self.buf("stem_scratch", (M, D)), mean0, rstd0,
                                  d.B, d.T, n, eps=d.eps)
-        self.t_fused = (self.fuse_t_outproj and d.block == "aim" and d.num_tadapter == 1 and WT is not None
-                        and self.dtype == torch.bfloat16)
-        self.s_fused = (self.fuse_s_outproj and d.block == "aim" and WT is not None and self.dtype == torch.bfloat16
-                        and self.gemm_impl == lib.IMPL_AUTO and not self.fuse_adapters
-                        and lib.dual_supported(xcur, D, 0, r))
-        if self.t_fused:
-            self._prep_fused("T_Adapter", W, WT, d, training)
-        if self.s_fused:
-            self._prep_fused("S_Adapter", W, WT, d, training)
+        if weights_ready is not None:
+            main.wait_stream(weights_ready[1])
         for i in range(d.L):
             masks = drop_masks[i] if (drop_masks is not None) else (None, None)
             if d.block == "fork":

@@ -255,14 +255,17 @@ def adapter_fused(a, w1, w2, hidden_out, out, epi1: dict, epi2: dict):
     return out
 
 
-def dual_supported(a, n1: int, n2: int, k2: int = 0) -> bool:
+def dual_supported_dims(M: int, K: int, dtype, n1: int, n2: int, k2: int = 0) -> bool:
     """shapes the paired tcgen05 GEMM (aimb_gemm_dual) tiles; anything else takes the separate gemm_nt calls"""
-    M, K = a.shape
-    if a.dtype != torch.bfloat16 or M < 128 or K % 64 or a.stride(1) != 1 or a.stride(0) % 8:
+    if dtype != torch.bfloat16 or M < 128 or K % 64:
         return False
     if k2:      # KCAT: one [M, n1] output over K + k2
         return k2 % 64 == 0 and (n1 % 192 == 0 or n1 % 256 == 0) and n1 % 16 == 0
     return n1 % 256 == 0 and n2 in (192, 256)
+
+
+def dual_supported(a, n1: int, n2: int, k2: int = 0) -> bool:
+    return a.stride(1) == 1 and a.stride(0) % 8 == 0 and dual_supported_dims(a.shape[0], a.shape[1], a.dtype, n1, n2, k2)
 
 
 def gemm_dual_ncat(a, w1, w2, out1, out2, epi1: dict, epi2: dict):
