@@ -11,6 +11,7 @@ from .backbone import ViT_CLIP, AIM, ViT_ImageNet  # noqa: E402,F401
 from .config import load_config, backbone_cfg  # noqa: E402,F401
 from .parallel import GradSync, shard_indices, gather_scores  # noqa: E402,F401
 from .graphs import GraphedStep  # noqa: E402,F401
+from .optim import FlatAdamW  # noqa: E402,F401
 from .recognizer import Recognizer3D, I3DHead, trainable_state_dict, load_checkpoint  # noqa: E402,F401
 
-__all__ += ["BACKBONES", "build_backbone", "ViT_CLIP", "AIM", "ViT_ImageNet", "load_config", "backbone_cfg", "GradSync", "shard_indices", "gather_scores", "GraphedStep", "Recognizer3D", "I3DHead", "trainable_state_dict", "load_checkpoint"]
+__all__ += ["BACKBONES", "build_backbone", "ViT_CLIP", "AIM", "ViT_ImageNet", "load_config", "backbone_cfg", "GradSync", "shard_indices", "gather_scores", "GraphedStep", "FlatAdamW", "Recognizer3D", "I3DHead", "trainable_state_dict", "load_checkpoint"]

@@ -169,6 +169,7 @@ class ViT_CLIP(nn.Module):
         self._step_ctx = None
         self._gen = 0
         self._norm_dev = None
+        self._last_flat_grad = None
 
     # ------------------------------------------------------------------ reference API
     def init_weights(self, pretrained=None):
@@ -454,6 +455,7 @@ class ViT_CLIP(nn.Module):
                 sync.bucket_done(flat_grad, 0, done_hi[0])
             sync.finish()
         self._step_ctx = None
+        self._last_flat_grad = flat_grad            # optim.FlatAdamW consumes the flat buffer directly
         out = []
         for p_name, p in self.named_parameters():
             out.append(grads.get(self._ekey(p_name)) if p.requires_grad else None)
@@ -613,6 +615,7 @@ class ViT_ImageNet(ViT_CLIP):
         self._step_ctx = None
         self._gen = 0
         self._norm_dev = None
+        self._last_flat_grad = None
         self._zero_qkv_bias = None
 
     def _ekey(self, name: str) -> str:

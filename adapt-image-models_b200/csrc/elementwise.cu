@@ -437,6 +437,49 @@ __global__ void __launch_bounds__(1024) colsum_kernel(const T* __restrict__ x, i
     }
 }
 
+// ------------------------------------------------------------------ AdamW over the flat trainable buffer
+// The 147 trainable tensors of the path are views of ONE flat fp32 buffer (and their gradients of one flat gradient
+// buffer), so the optimizer step of the reference's AdamW (torch.optim.AdamW semantics: decoupled weight decay, bias
+// correction; mmcv builds it from configs/recognition/vit/*.py `optimizer = dict(type='AdamW', ...)`) is one pass over
+// four arrays instead of a multi-tensor launch chain.  wd_mask[i] != 0 selects the elements that decay (adapter weight
+// matrices; biases, LayerNorm and temporal_embedding do not, `paramwise_cfg`).  `step` lives on the device (the call is
+// captured into the step's CUDA graph): the caller increments it before the launch.
+__global__ void __launch_bounds__(256) adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                         float* __restrict__ v, const uint8_t* __restrict__ wd_mask,
+                                                         const float* __restrict__ step, float lr, float beta1, float beta2,
+                                                         float eps, float wd, int64_t n) {
+    pdl_grid_sync();
+    const float t = step[0];
+    const float bc1 = 1.f - powf(beta1, t), bc2s = sqrtf(1.f - powf(beta2, t));
+    const float step_size = lr / bc1;
+    const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i0 >= n) return;
+    if (i0 + 4 <= n) {
+        float4 pp = *reinterpret_cast<float4*>(p + i0), gg = *reinterpret_cast<const float4*>(g + i0);
+        float4 mm = *reinterpret_cast<float4*>(m + i0), vv = *reinterpret_cast<float4*>(v + i0);
+        const uchar4 wm = wd_mask ? *reinterpret_cast<const uchar4*>(wd_mask + i0) : make_uchar4(1, 1, 1, 1);
+        float* P = reinterpret_cast<float*>(&pp); const float* G = reinterpret_cast<const float*>(&gg);
+        float* M = reinterpret_cast<float*>(&mm); float* V = reinterpret_cast<float*>(&vv);
+        const unsigned char W4[4] = {wm.x, wm.y, wm.z, wm.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (W4[j]) P[j] *= 1.f - lr * wd;
+            M[j] = beta1 * M[j] + (1.f - beta1) * G[j];
+            V[j] = beta2 * V[j] + (1.f - beta2) * G[j] * G[j];
+            P[j] -= step_size * M[j] / (sqrtf(V[j]) / bc2s + eps);
+        }
+        *reinterpret_cast<float4*>(p + i0) = pp; *reinterpret_cast<float4*>(m + i0) = mm; *reinterpret_cast<float4*>(v + i0) = vv;
+    } else {
+        for (int64_t i = i0; i < n; ++i) {
+            float pi = p[i];
+            if (!wd_mask || wd_mask[i]) pi *= 1.f - lr * wd;
+            const float mi = beta1 * m[i] + (1.f - beta1) * g[i], vi = beta2 * v[i] + (1.f - beta2) * g[i] * g[i];
+            m[i] = mi; v[i] = vi;
+            p[i] = pi - step_size * mi / (sqrtf(vi) / bc2s + eps);
+        }
+    }
+}
+
 // Batched 2-D transposes in one launch: matrix b (blockIdx.z) is src + table[3b] of shape [table[3b+1], table[3b+2]],
 // written transposed at the same element offset in dst.  (All adapter weights of a step: 6 per block.)
 template <typename T>
@@ -826,6 +869,18 @@ extern "C" int aimb_fork_combine_bwd(const void* dx, const float* lam, const flo
     else if (dtype == AIMB_F32)
         launch_k((fork_combine_bwd_kernel<float>), dim3(grid), dim3(block), 0, s, (const float*)dx, lam, rs, (float*)d_ao, (float*)d_s, n, D);
     else return AIMB_ERR_ARG;
+    AIMB_CHECK_LAUNCH();
+    return AIMB_OK;
+}
+
+extern "C" int aimb_adamw_flat(float* p, const float* g, float* m, float* v, const uint8_t* wd_mask, const float* step, float lr,
+                               float beta1, float beta2, float eps, float weight_decay, int64_t n, void* stream) {
+    if (!p || !g || !m || !v || !step || n < 0) return AIMB_ERR_ARG;
+    if (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15 || (wd_mask && ((uintptr_t)wd_mask & 3))) return AIMB_ERR_ARG;
+    if (n == 0) return AIMB_OK;
+    const unsigned grid = (unsigned)((n + 1023) / 1024);
+    launch_k(adamw_flat_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, wd_mask, step, lr, beta1, beta2, eps,
+             weight_decay, n);
     AIMB_CHECK_LAUNCH();
     return AIMB_OK;
 }

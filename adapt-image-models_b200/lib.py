@@ -56,6 +56,7 @@ SIGNATURES = {
     "aimb_gemm_wgrad": [_P, _L, _P, _L, _P, _L, _I, _I, _F, _I, _I, _I, _P],
     "aimb_colsum": [_P, _L, _P, _I, _F, _P, _L, _I, _I, _I, _P],
     "aimb_transpose": [_P, _P, _I, _I, _I, _P],
+    "aimb_adamw_flat": [_P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _L, _P],
     "aimb_transpose_batched": [_P, _P, _P, _I, _I, _P],
     "aimb_attn_spatial_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "aimb_attn_spatial_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
@@ -329,6 +330,16 @@ def transpose(src, dst):
     _count()
     _chk(load().aimb_transpose(_ptr(_c(src)), _ptr(_c(dst)), R, Cn, dt_code(src), _stream()), "transpose")
     return dst
+
+
+def adamw_flat(p, g, m, v, wd_mask, step, lr, beta1, beta2, eps, weight_decay):
+    """one AdamW step over flat fp32 arrays; step = 1-element fp32 CUDA tensor holding the (already incremented) step count"""
+    n = p.numel()
+    assert p.dtype == g.dtype == m.dtype == v.dtype == torch.float32 and g.numel() == n and step.dtype == torch.float32
+    assert wd_mask is None or (wd_mask.dtype == torch.uint8 and wd_mask.numel() == n)
+    _count()
+    _chk(load().aimb_adamw_flat(_ptr(_c(p)), _ptr(_c(g)), _ptr(_c(m)), _ptr(_c(v)), _ptr(wd_mask), _ptr(step), lr, beta1, beta2,
+                                eps, weight_decay, n, _stream()), "adamw_flat")
 
 
 def transpose_batched(src_flat, dst_flat, table_dev, nmat):

@@ -224,9 +224,16 @@ class Trainer:
                 self.backbone.attach_grad_sync(self.sync)
             decay = [p for n, p in self.backbone.named_parameters() if p.requires_grad and "Adapter" in n and n.endswith("weight")]
             nodecay = [p for n, p in self.backbone.named_parameters() if p.requires_grad and not ("Adapter" in n and n.endswith("weight"))]
-            self.opt = torch.optim.AdamW([{"params": decay + [self.hw], "weight_decay": 0.05},
-                                          {"params": nodecay + [self.hb], "weight_decay": 0.0}], lr=3e-4, fused=True,
-                                         capturable=True)
+            if os.environ.get("AIMB200_FLAT_ADAMW", "1") == "1":
+                # the backbone's trainable tensors are views of one flat buffer: one AdamW kernel for all of them
+                # (aimb200.FlatAdamW, same update as torch.optim.AdamW); the two head tensors stay on torch's optimizer
+                head_opt = torch.optim.AdamW([{"params": [self.hw], "weight_decay": 0.05}, {"params": [self.hb], "weight_decay": 0.0}],
+                                             lr=3e-4, fused=True, capturable=True)
+                self.opt = aimb200.FlatAdamW(self.backbone, lr=3e-4, weight_decay=0.05, extra=head_opt)
+            else:
+                self.opt = torch.optim.AdamW([{"params": decay + [self.hw], "weight_decay": 0.05},
+                                              {"params": nodecay + [self.hb], "weight_decay": 0.0}], lr=3e-4, fused=True,
+                                             capturable=True)
 
     def step(self, x, labels):
         if not self.train:

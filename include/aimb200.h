@@ -169,6 +169,13 @@ int aimb_gemm_dual(int32_t mode, const void* A1, int64_t lda1, const void* W1, i
 int aimb_colsum(const void* x, int64_t ld, const float* row_scale, int32_t row_mod, float alpha, float* out,
                 int64_t R, int32_t C, int32_t accumulate, int32_t dtype, void* stream);
 int aimb_transpose(const void* in, void* out, int32_t R, int32_t C, int32_t dtype, void* stream);
+/* One AdamW step (torch.optim.AdamW semantics: p *= 1 - lr*wd where wd_mask[i] != 0 (NULL: everywhere); m, v moments; bias
+ * correction with the DEVICE scalar step[0] >= 1) over the flat fp32 buffer that holds every trainable tensor of the path and
+ * the flat gradient buffer the backward fills — replaces the optimizer's multi-tensor launch chain
+ * (configs/recognition/vit/vitclip_base_k400.py `optimizer = dict(type='AdamW', ...)`, mmcv build_optimizer). */
+int aimb_adamw_flat(float* p, const float* g, float* m, float* v, const uint8_t* wd_mask, const float* step, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, int64_t n, void* stream);
+
 /* One launch for many transposes (the per-step transposes of the trainable adapter weights for dgrad):
  * matrix b = src + table[3b] (elements), shape [table[3b+1], table[3b+2]], written transposed at dst + table[3b].
  * `table` is a DEVICE array of 3*nmat int64. */

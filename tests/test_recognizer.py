@@ -95,3 +95,46 @@ def test_recognizer_train_and_test_step_gpu():
     ref = O.head_logits(O.backbone(p, views.reshape(6, 3, 4, 64, 64), cfg), hw, hb)
     ref = torch.softmax(ref, -1).view(2, 3, 16).mean(1)
     assert O.normalised_max_err(prob.cpu(), ref) < 2e-2
+
+
+@pytest.mark.gpu
+def test_flat_adamw_matches_torch_adamw():
+    """aimb200.FlatAdamW (one kernel over the flat trainable buffer) against torch.optim.AdamW with the same groups, three
+    training steps of the tiny backbone: every parameter agrees."""
+    import aimb200
+    from oracle import aim_oracle as O
+    cfg = O.OracleCfg(input_resolution=64, num_frames=4, patch_size=16, width=256, layers=2, heads=4)
+    x = O.fixture_clip(cfg, 2).cuda()
+    hw, hb = O.fixture_head(cfg, 16)
+    labels = torch.tensor([3, 11]).cuda()
+
+    def run(flat: bool):
+        m = aimb200.build_backbone(dict(type="ViT_CLIP", input_resolution=64, num_frames=4, patch_size=16, width=256, layers=2,
+                                        heads=4, drop_path_rate=0.0, compute_dtype="fp32"))
+        m.init_weights()
+        m.load_state_dict(O.fixture_state_dict(cfg))
+        m = m.cuda().train()
+        w, b = hw.clone().cuda().requires_grad_(True), hb.clone().cuda().requires_grad_(True)
+        named = [(n, p) for n, p in m.named_parameters() if p.requires_grad]
+        dec = [p for n, p in named if "Adapter" in n and n.endswith("weight")]
+        nod = [p for n, p in named if not ("Adapter" in n and n.endswith("weight"))]
+        if flat:
+            head = torch.optim.AdamW([{"params": [w], "weight_decay": 0.05}, {"params": [b], "weight_decay": 0.0}], lr=1e-3)
+            opt = aimb200.FlatAdamW(m, lr=1e-3, weight_decay=0.05, extra=head)
+        else:
+            opt = torch.optim.AdamW([{"params": dec + [w], "weight_decay": 0.05}, {"params": nod + [b], "weight_decay": 0.0}], lr=1e-3)
+        for _ in range(3):
+            opt.zero_grad(set_to_none=True)
+            loss = torch.nn.functional.cross_entropy(O.head_logits(m(x), w, b), labels)
+            loss.backward()
+            opt.step()
+        torch.cuda.synchronize()
+        return {n: p.detach().clone() for n, p in named}, w.detach().clone(), float(loss)
+
+    pa, wa, la = run(True)
+    pb, wb, lb = run(False)
+    assert abs(la - lb) < 1e-5
+    assert torch.allclose(wa, wb, atol=1e-6)
+    worst = max(float((pa[n] - pb[n]).abs().max()) for n in pa)
+    moved = max(float((pa[n] - O.fixture_state_dict(cfg)[n].cuda()).abs().max()) for n in pa)
+    assert moved > 1e-3 and worst < 2e-6, (worst, moved)
