@@ -342,6 +342,7 @@ class ViT_CLIP(nn.Module):
                 WT[name] = ent[2]
         # ---- trainable: one cast of the flat master per step
         flat_c = self._flat if cd == torch.float32 else self._flat.to(cd)
+        self._step_tmp = [flat_c] if flat_c is not self._flat else []
         for name in self.trainable_names():
             o, k = self._offsets[name]
             shape = params[name].shape
@@ -357,6 +358,7 @@ class ViT_CLIP(nn.Module):
                 rows = [[self._offsets[n][0], params[n].shape[0], params[n].shape[1]] for n in wnames]
                 self._tr_table = (self._flat, torch.tensor(rows, dtype=torch.int64, device=self._flat.device))
             flat_t = torch.empty_like(flat_c)
+            self._step_tmp.append(flat_t)
             lib.transpose_batched(flat_c, flat_t, self._tr_table[1], len(wnames))
             for n in wnames:
                 o, k = self._offsets[n]
@@ -409,7 +411,7 @@ class ViT_CLIP(nn.Module):
                 masks = self._drop_masks(d, x.device) if training else None
                 ready = None
                 if overlap:
-                    for t in {id(v): v for v in list(W.values()) + list(WT.values())}.values():
+                    for t in self._step_tmp:            # the per-step allocations (bf16 copy of the flat master, its transposes):
                         t.record_stream(main)           # produced on the side stream, consumed (and later freed) on the main one
                     for pair in (masks or []):
                         for t in pair:
