@@ -1570,26 +1570,42 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
         const int quad = warp & 3;
         ptx::mbar_wait(done_bar, 0);
         ptx::tc_fence_after();
-        const int m = mt * 128 + quad * 32 + lane;          // column of P == row of the (untransposed) result
+        const bool vec_atomics = ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && (ldo % 4 == 0);
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
         for (int c = 0; c < NS; c += 32) {
             uint32_t r[32];
             ptx::tmem_ld_32x32b_x32(taddr + c, r);
             ptx::tmem_wait_ld();
-            if (transposed_out) {
+            // All `splits` CTAs of a column tile add into the same addresses and same-address atomics serialise in L2: the
+            // 32 x 32 block goes through a padded smem tile so that every lane owns 4 consecutive floats of the result and
+            // issues ONE 16-byte vector atomic for them (4x fewer serialised operations than scalar adds).
+            float* st = wstg + quad * (32 * 33);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) atomicAdd(out + (int64_t)(c + j) * ldo + m, alpha * __uint_as_float(r[j]));
-            } else {    // rows of the result are contiguous: transpose through smem so each red covers 32 floats of a row
-                float* st = wstg + quad * (32 * 33);
+            for (int j = 0; j < 32; ++j) st[lane * 33 + j] = alpha * __uint_as_float(r[j]);      // [lane = row m][column j]
+            __syncwarp();
+            const int64_t m0 = (int64_t)mt * 128 + quad * 32;
+            const int a4 = lane >> 3, b4 = (lane & 7) * 4;
+            if (transposed_out) {       // out[(c + j) * ldo + m]: 4 consecutive m per lane
 #pragma unroll
-                for (int j = 0; j < 32; ++j) st[lane * 33 + j] = alpha * __uint_as_float(r[j]);
-                __syncwarp();
-                const int64_t m0 = (int64_t)mt * 128 + quad * 32;
-#pragma unroll 4
-                for (int rr = 0; rr < 32; ++rr) atomicAdd(out + (m0 + rr) * ldo + c + lane, st[rr * 33 + lane]);
-                __syncwarp();
+                for (int it = 0; it < 8; ++it) {
+                    const int j = it * 4 + a4;
+                    float* o = out + (int64_t)(c + j) * ldo + m0 + b4;
+                    const float4 v = make_float4(st[(b4 + 0) * 33 + j], st[(b4 + 1) * 33 + j], st[(b4 + 2) * 33 + j], st[(b4 + 3) * 33 + j]);
+                    if (vec_atomics) atomicAdd(reinterpret_cast<float4*>(o), v);
+                    else { atomicAdd(o, v.x); atomicAdd(o + 1, v.y); atomicAdd(o + 2, v.z); atomicAdd(o + 3, v.w); }
+                }
+            } else {                    // out[(m0 + rr) * ldo + c + col]: 4 consecutive columns per lane
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int rr = it * 4 + a4;
+                    float* o = out + (m0 + rr) * ldo + c + b4;
+                    const float4 v = make_float4(st[rr * 33 + b4], st[rr * 33 + b4 + 1], st[rr * 33 + b4 + 2], st[rr * 33 + b4 + 3]);
+                    if (vec_atomics) atomicAdd(reinterpret_cast<float4*>(o), v);
+                    else { atomicAdd(o, v.x); atomicAdd(o + 1, v.y); atomicAdd(o + 2, v.z); atomicAdd(o + 3, v.w); }
+                }
             }
+            __syncwarp();
         }
     }
     ptx::tc_fence_before();
