@@ -64,6 +64,22 @@ __device__ int g_dbg_skip_epilogue = 0;   // 1 = drain TMEM but skip the epilogu
 constexpr int g_dbg_skip_epilogue = 0;
 #endif
 
+// Column-sum flush of one tile: `ncols` per-CTA partials from shared memory into the global fp32 vector.  Every row tile of
+// the GEMM adds into the same addresses (99 CTAs at M = 12 608) and same-address atomics serialise in L2, so 4 columns go
+// out as ONE 16-byte vector atomic (scalar fallback for an unaligned destination).  Called by the first `ncols` epilogue threads.
+__device__ __forceinline__ void colsum_flush(float* __restrict__ dst, float* scol, int te, int ncols) {
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        if (te < ncols / 4) {
+            const float4 v = *reinterpret_cast<const float4*>(scol + 4 * te);
+            atomicAdd(reinterpret_cast<float4*>(dst) + te, v);
+            *reinterpret_cast<float4*>(scol + 4 * te) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    } else if (te < ncols) {
+        atomicAdd(dst + te, scol[te]);
+        scol[te] = 0.f;
+    }
+}
+
 struct EpiExt {
     uint4 d[4], r1[4], r2[4];
 };
@@ -407,7 +423,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (epi.colsum_out) {      // one global atomic per column per tile (the 8 epilogue warps meet on named barrier 1)
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 const int te = threadIdx.x - 64;
-                if (te < BN) { atomicAdd(epi.colsum_out + n_blk * BN + te, scol[te]); scol[te] = 0.f; }
+                colsum_flush(epi.colsum_out + n_blk * BN, scol, te, BN);
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
             if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
@@ -780,7 +796,7 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (epi.colsum_out) {
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_W) : "memory");
                 const int te = threadIdx.x - 64;
-                if (te < BN) { atomicAdd(epi.colsum_out + n_blk * BN + te, scol[te]); scol[te] = 0.f; }
+                colsum_flush(epi.colsum_out + n_blk * BN, scol, te, BN);
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_W) : "memory");
             }
         }
@@ -1193,7 +1209,7 @@ adapter_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (epi1.colsum_out) {
             asm volatile("bar.sync 1, 256;" ::: "memory");
             const int te = threadIdx.x - 64;
-            if (te < R) { atomicAdd(epi1.colsum_out + te, scol[te]); scol[te] = 0.f; }
+            colsum_flush(epi1.colsum_out, scol, te, R);
             asm volatile("bar.sync 1, 256;" ::: "memory");
         }
         // ---- epilogue 2: output chunks
