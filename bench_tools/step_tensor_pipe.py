@@ -18,9 +18,16 @@ for r in rows[hi + 1:]:
         continue
     d = per.setdefault(r[ix["ID"]], {"name": r[ix["Kernel Name"]]})
     d[r[ix["Metric Name"]]] = float(r[ix["Metric Value"]].replace(",", ""))
+# keep ONE training step: the launches from one im2col (first kernel of a step) up to the next, the window must hold attn_bwd
+seq = list(per.values())
+starts = [i for i, d in enumerate(seq) if "im2col" in d["name"]]
+for a, b in zip(starts, starts[1:]):
+    if any("attn_bwd" in d["name"] for d in seq[a:b]):
+        seq = seq[a:b]
+        break
 agg = collections.OrderedDict()
 tot_t = tot_w = 0.0
-for d in per.values():
+for d in seq:
     t = d.get("gpu__time_duration.sum", 0.0) / 1e3
     tp = d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", 0.0)
     name = re.sub(r"\(.*", "", d["name"]).replace("void ", "").replace("aimb::", "")
@@ -30,7 +37,7 @@ for d in per.values():
     tot_t += t; tot_w += t * tp
 out = {"source": sys.argv[2] if len(sys.argv) > 2 else sys.argv[1],
        "metric": "sum_k(duration_k * sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active_k) / sum_k duration_k over the launches of one step",
-       "launches": len(per), "step_kernel_time_ms": tot_t / 1e3, "tensor_pipe_active_pct_time_weighted": tot_w / tot_t if tot_t else None,
+       "launches": len(seq), "step_kernel_time_ms": tot_t / 1e3, "tensor_pipe_active_pct_time_weighted": tot_w / tot_t if tot_t else None,
        "per_kernel": [{"kernel": k, "launches": n, "time_us": round(t, 1), "share": round(t / tot_t, 4),
                        "tensor_pipe_active_pct": round(w / t, 1) if t else 0.0, "dram_MB_per_launch": round(b / n / 1e6, 1)}
                       for k, (n, t, w, b) in sorted(agg.items(), key=lambda kv: -kv[1][1]) if t / tot_t > 0.001]}
